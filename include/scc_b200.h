@@ -1,0 +1,224 @@
+/*
+ * scc_b200.h — C ABI of the B200-native latent-space clustering hot path.
+ *
+ * Drop-in boundary for ONE path of Julia310/Spectrogram-Cube-Clustering: the DEC
+ * clustering layer (soft assignment, target distribution, KL loss + gradients)
+ * and the full-covariance GMM E-step / M-step that seeds the centroids.  The
+ * reference is pure Python (torch + scikit-learn) and has no FFI of its own;
+ * each entry point below names the reference code (file:line under
+ * /root/reference, or `sklearn:` for scikit-learn 1.9.0) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the ctypes binding a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *  - Plain C: raw DEVICE pointers, sizes, scalars, a CUDA stream handle
+ *    (cudaStream_t passed as void*; NULL = legacy default stream).  No torch types.
+ *  - Every function returns SCC_OK (0) or a negative scc_status; nothing is
+ *    thrown, nothing is printed.  Launches are asynchronous on `stream`.
+ *  - Latent points z are row-major [n, d] float32, 16-byte aligned base pointer.
+ *    Centroids / means are row-major [K, d].  d in [1,32], K in [1,16];
+ *    scc_supported(d, K) says whether kernels are instantiated for (d, K).
+ *  - Statistics that are sums over points come back as float64 in a caller
+ *    buffer (`stats`), already reduced over the grid in a fixed order
+ *    (deterministic for a given device), ready for a cross-GPU allreduce(sum).
+ *  - `workspace` is a caller-owned device scratch buffer of at least
+ *    scc_workspace_bytes(d, K) bytes, zeroed ONCE with scc_workspace_init and
+ *    then reusable by every call on the same stream (calls that share a
+ *    workspace must be stream-ordered).
+ *  - There is no CPU fallback: on a machine without an sm_100 device every
+ *    compute entry point returns SCC_ERR_CUDA.
+ */
+#ifndef SCC_B200_H_
+#define SCC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCC_ABI_VERSION 1
+#define SCC_MAX_D 32
+#define SCC_MAX_K 16
+
+typedef enum scc_status {
+    SCC_OK = 0,
+    SCC_ERR_INVALID = -1,      /* null pointer, n < 0, K or d out of range, bad flag   */
+    SCC_ERR_UNSUPPORTED = -2,  /* (d, K) has no kernel instantiation                   */
+    SCC_ERR_MISALIGNED = -3,   /* a pointer violates the documented alignment          */
+    SCC_ERR_WORKSPACE = -4,    /* workspace NULL or smaller than scc_workspace_bytes   */
+    SCC_ERR_CUDA = -5          /* a CUDA runtime call failed; see scc_last_cuda_error  */
+} scc_status;
+
+typedef void* scc_stream_t;    /* cudaStream_t */
+
+int scc_abi_version(void);
+const char* scc_status_string(int status);
+const char* scc_last_cuda_error(void);          /* thread-local text of the last CUDA failure */
+int scc_supported(int d, int K);                /* DEC kernels instantiated for (d, K)? 1 / 0 */
+int scc_gmm_supported(int d, int K);            /* GMM kernels instantiated for (d, K)? 1 / 0 */
+
+size_t scc_workspace_bytes(int d, int K);
+int scc_workspace_init(void* workspace, size_t bytes, scc_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * DEC stage
+ * ------------------------------------------------------------------------- */
+
+/* Length (in doubles) of the stats buffer each DEC call fills. */
+#define SCC_DEC_ASSIGN_STATS(K) ((K) + 1)             /* f[K], n_label_changes            */
+#define SCC_DEC_GRAD_STATS(K, d) ((K) * (d) + 2)       /* loss, sum_i s_i, dmu[K*d]        */
+
+/*
+ * Student's-t soft assignment  q_ij = t_ij / sum_j t_ij,
+ * t_ij = (1 + ||z_i - mu_j||^2 / alpha)^-((alpha+1)/2)
+ *   replaces Cluster/networks.py:279-288 (ClusteringLayer.forward),
+ *   the argmax of Cluster/models.py:92, the np.round(q, 5) of models.py:94,
+ *   the column sums f_j = sum_i q_ij of models.py:1320 and the label-change
+ *   count of models.py:1098-1099 — one pass over z.
+ *
+ * round_decimals: 0 keeps q as computed; 5 reproduces np.round(q, 5) and the
+ *   column sums are then taken over the ROUNDED q, as the reference's
+ *   batch_eval -> target_distribution chain does.  Labels always come from the
+ *   unrounded q (first index wins on ties).
+ * q            [n, K] float32 out, or NULL (fused latent-buffer mode writes nothing n-sized)
+ * labels       [n] int32 out, or NULL
+ * labels_prev  [n] int32 in, or NULL (then n_label_changes = 0)
+ * stats        [K+1] float64 out: f[0..K), number of labels that differ from labels_prev
+ */
+int scc_dec_assign(const float* z, int64_t n, int d,
+                   const float* mu, int K, float alpha, int round_decimals,
+                   float* q, int32_t* labels, const int32_t* labels_prev,
+                   double* stats, void* workspace, size_t workspace_bytes,
+                   scc_stream_t stream);
+
+/*
+ * Target distribution  p_ij = (q_ij^2 / f_j) / sum_j (q_ij^2 / f_j)
+ *   replaces Cluster/models.py:1320-1322 (target_distribution) given the
+ *   column sums f from scc_dec_assign (after any cross-GPU allreduce).
+ * round_decimals: 0, or 5 for the reference's np.round(p, 5).
+ * A column with f_j == 0 yields NaN rows exactly like the reference.
+ */
+int scc_dec_target(const float* q, int64_t n, int K, const double* f,
+                   int round_decimals, float* p, scc_stream_t stream);
+
+/*
+ * Column sums f_j = sum_i q_ij of an existing [n, K] matrix (models.py:1320, for
+ * callers that hand target_distribution a q they did not get from scc_dec_assign).
+ * workspace: at least scc_workspace_bytes(4, K) bytes.
+ */
+int scc_colsum(const float* q, int64_t n, int K, double* f,
+               void* workspace, size_t workspace_bytes, scc_stream_t stream);
+
+/*
+ * KL(P||Q) loss and its gradients, q recomputed from z (never re-read):
+ *   loss   = scale * sum_ij p_ij (log p_ij - log q_ij)      (terms with p_ij == 0 are 0)
+ *   dz_i   =  scale (alpha+1)/alpha sum_j (p_ij - q_ij s_i) u_ij (z_i - mu_j)
+ *   dmu_j  = -scale (alpha+1)/alpha sum_i (p_ij - q_ij s_i) u_ij (z_i - mu_j)
+ *   replaces `gamma * KLDivLoss('sum')(log q, p) / B` + autograd backward,
+ *   Cluster/models.py:1124-1127 (scale = gamma / B).
+ *
+ * p  [n, K] float32 target (API mode), or NULL: then p is rebuilt per point from
+ *    f_cols[K] exactly as scc_dec_assign + scc_dec_target would have produced it
+ *    (same round_decimals on q and on p) — the fused latent-buffer mode.
+ * dz [n, d] float32 out, or NULL (centroid-only refinement)
+ * stats [K*d + 2] float64 out: loss, sum_i s_i, dmu (row-major [K, d])
+ */
+int scc_dec_kl_grad(const float* z, int64_t n, int d,
+                    const float* mu, int K, float alpha,
+                    const float* p, const double* f_cols, int round_decimals,
+                    float scale, float* dz, double* stats,
+                    void* workspace, size_t workspace_bytes, scc_stream_t stream);
+
+/*
+ * Backward of the layer for an arbitrary upstream gradient G = dL/dq
+ * (the autograd path of the literal reference loop, models.py:1122-1127):
+ *   dz [n, d] float32 out or NULL; stats [K*d + 2] float64 out: 0, 0, dmu[K*d].
+ */
+int scc_dec_backward(const float* z, int64_t n, int d,
+                     const float* mu, int K, float alpha,
+                     const float* grad_q, float* dz, double* stats,
+                     void* workspace, size_t workspace_bytes, scc_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * GMM stage (full covariance)
+ * ------------------------------------------------------------------------- */
+
+/* Packed float32 parameter block the E-step reads (written by scc_gmm_finalize
+ * or scc_gmm_pack_params): means[K*d], U[K*d*(d+1)/2] (upper-triangular
+ * precision-Cholesky factor, column-packed: U[a][b], a<=b at b(b+1)/2+a),
+ * cst[K] = log det U_k + log pi_k - d/2 log(2 pi). */
+#define SCC_GMM_TRI(d) ((d) * ((d) + 1) / 2)
+#define SCC_GMM_PARAM_FLOATS(K, d) ((K) * (d) + (K) * SCC_GMM_TRI(d) + (K))
+/* Packed float64 statistics of one fused E+M pass:
+ * [0] sum_i log p(x_i); then per k: N_k ; then S1[K*d] = sum_i r_ik (x_i - mu_k);
+ * then S2[K*TRI] = sum_i r_ik (x_i-mu_k)_a (x_i-mu_k)_b, a<=b column-packed. */
+#define SCC_GMM_STAT_DOUBLES(K, d) (1 + (K) + (K) * (d) + (K) * SCC_GMM_TRI(d))
+/* Control block (float64[8]) shared by finalize calls of one fit:
+ * [0] lower bound of the last E-step, [1] previous lower bound, [2] n_iter,
+ * [3] converged flag, [4] not-positive-definite flag (index k+1 of first bad
+ * component), [5] frozen flag (set with converged: later passes are no-ops). */
+#define SCC_GMM_CTRL_DOUBLES 8
+
+/*
+ * One fused E-step + M-step sufficient-statistics pass over z:
+ *   replaces sklearn:mixture/_base.py:314-332,552-582 (_e_step, log-sum-exp
+ *   responsibilities), sklearn:mixture/_gaussian_mixture.py:490-553 (Cholesky
+ *   log-likelihoods) and the sums of :282-320,168-197 (_m_step) — the calls
+ *   Cluster/models.py:411 (GMM.fit_predict) spends its time in.
+ * Moments are centred on the CURRENT means (the ones in `params`), so the
+ * finalize step applies mu_new = mu + S1/N_k, Sigma = S2/N_k - dd^T + reg I.
+ * labels [n] int32 out or NULL: argmax_k of the responsibilities (final pass).
+ * resp   [n, K] float32 out or NULL: the responsibilities themselves.
+ * ctrl   float64[8] or NULL: if ctrl[5] != 0 the pass is skipped (frozen fit).
+ * mode: SCC_GMM_ESTEP_ONLY skips the M-step sums (label-only final E-step);
+ *   SCC_GMM_SOFT is the EM pass; SCC_GMM_HARD replaces r_ik by the one-hot
+ *   argmax_k (the initial responsibilities sklearn builds from k-means labels,
+ *   sklearn:mixture/_base.py:119-128, when params hold Sigma = I, pi = 1/K).
+ */
+#define SCC_GMM_ESTEP_ONLY 0
+#define SCC_GMM_SOFT 1
+#define SCC_GMM_HARD 2
+int scc_gmm_em_step(const float* z, int64_t n, int d, int K,
+                    const float* params, double* stats,
+                    int32_t* labels, float* resp, const double* ctrl,
+                    int mode,
+                    void* workspace, size_t workspace_bytes, scc_stream_t stream);
+
+/*
+ * M-step finalisation on the device (one thread block; float64):
+ *   N_k += 10 eps; pi = N_k / sum N_k; mu, Sigma (+reg_covar on the diagonal);
+ *   L = chol(Sigma); U = L^-T; log det; lower bound = stats[0] / n_total;
+ *   converged if |lower - previous| < tol.
+ *   replaces sklearn:mixture/_gaussian_mixture.py:883-901, 282-320 (divisions),
+ *   323-385 (_compute_precision_cholesky), 448-487 and the convergence test of
+ *   sklearn:mixture/_base.py:270-278.
+ * stats        float64 packed sums (after any cross-GPU allreduce)
+ * means        float64 [K, d] in/out (current means in, new means out)
+ * weights      float64 [K] out;  covariances float64 [K, d, d] out;
+ * prec_chol    float64 [K, d, d] out (upper triangular, sklearn's precisions_cholesky_)
+ * params       float32 packed block for the next E-step, out
+ * ctrl         float64[8] in/out (see SCC_GMM_CTRL_DOUBLES)
+ */
+int scc_gmm_finalize(const double* stats, double n_total, int d, int K,
+                     double reg_covar, double nk_eps, double tol,
+                     double* means, double* weights, double* covariances,
+                     double* prec_chol, float* params, double* ctrl,
+                     scc_stream_t stream);
+
+/*
+ * Build the packed E-step parameter block from explicit (pi, mu, Sigma) float64
+ * device arrays — the initial state (weights_init / means_init + initial
+ * covariances, sklearn:mixture/_gaussian_mixture.py:848-881).  Also fills
+ * prec_chol [K,d,d] (may be NULL) and resets ctrl.
+ */
+int scc_gmm_pack_params(const double* weights, const double* means,
+                        const double* covariances, int d, int K,
+                        double* prec_chol, float* params, double* ctrl,
+                        scc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCC_B200_H_ */

@@ -1,0 +1,104 @@
+// scc_api.cu — the extern "C" boundary declared in include/scc_b200.h.
+// Thin argument forwarding only; all validation lives next to the launchers.
+#include <stdio.h>
+#include <string.h>
+
+#include "scc_launch.h"
+
+namespace scc {
+
+static thread_local char g_cuda_error[512] = "";
+
+void set_cuda_error(cudaError_t e, const char* what, int line) {
+    snprintf(g_cuda_error, sizeof(g_cuda_error), "%s (%s) at %s [line %d]", cudaGetErrorName(e),
+             cudaGetErrorString(e), what, line);
+}
+
+size_t workspace_bytes(int d, int K) {
+    if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return 0;
+    const size_t dec = (size_t)kMaxDecGrid * (size_t)(K * d + 2);
+    const size_t gmm = (size_t)kMaxGmmGrid * (size_t)SCC_GMM_STAT_DOUBLES(K, d);
+    return kWorkspaceHeader + sizeof(double) * (dec > gmm ? dec : gmm);
+}
+
+}  // namespace scc
+
+extern "C" {
+
+int scc_abi_version(void) { return SCC_ABI_VERSION; }
+
+const char* scc_status_string(int status) {
+    switch (status) {
+        case SCC_OK: return "ok";
+        case SCC_ERR_INVALID: return "invalid argument";
+        case SCC_ERR_UNSUPPORTED: return "unsupported (d, K): no kernel instantiation";
+        case SCC_ERR_MISALIGNED: return "misaligned pointer (16-byte alignment required)";
+        case SCC_ERR_WORKSPACE: return "workspace missing or too small";
+        case SCC_ERR_CUDA: return "CUDA runtime error";
+        default: return "unknown status";
+    }
+}
+
+const char* scc_last_cuda_error(void) { return scc::g_cuda_error; }
+
+int scc_supported(int d, int K) { return scc::dec_supported(d, K) ? 1 : 0; }
+int scc_gmm_supported(int d, int K) { return scc::gmm_supported(d, K) ? 1 : 0; }
+
+size_t scc_workspace_bytes(int d, int K) { return scc::workspace_bytes(d, K); }
+
+int scc_workspace_init(void* workspace, size_t bytes, scc_stream_t stream) {
+    if (!workspace || bytes < scc::kWorkspaceHeader) return SCC_ERR_WORKSPACE;
+    SCC_CUDA(cudaMemsetAsync(workspace, 0, scc::kWorkspaceHeader, (cudaStream_t)stream));
+    return SCC_OK;
+}
+
+int scc_dec_assign(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
+                   float* q, int32_t* labels, const int32_t* labels_prev, double* stats, void* workspace,
+                   size_t workspace_bytes, scc_stream_t stream) {
+    return scc::dec_assign(z, n, d, mu, K, alpha, round_decimals, q, labels, labels_prev, stats, workspace,
+                           workspace_bytes, (cudaStream_t)stream);
+}
+
+int scc_dec_target(const float* q, int64_t n, int K, const double* f, int round_decimals, float* p,
+                   scc_stream_t stream) {
+    return scc::dec_target(q, n, K, f, round_decimals, p, (cudaStream_t)stream);
+}
+
+int scc_colsum(const float* q, int64_t n, int K, double* f, void* workspace, size_t workspace_bytes,
+               scc_stream_t stream) {
+    return scc::colsum(q, n, K, f, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int scc_dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* p,
+                    const double* f_cols, int round_decimals, float scale, float* dz, double* stats,
+                    void* workspace, size_t workspace_bytes, scc_stream_t stream) {
+    return scc::dec_kl_grad(z, n, d, mu, K, alpha, p, f_cols, round_decimals, scale, dz, stats, workspace,
+                            workspace_bytes, (cudaStream_t)stream);
+}
+
+int scc_dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* grad_q,
+                     float* dz, double* stats, void* workspace, size_t workspace_bytes, scc_stream_t stream) {
+    return scc::dec_backward(z, n, d, mu, K, alpha, grad_q, dz, stats, workspace, workspace_bytes,
+                             (cudaStream_t)stream);
+}
+
+int scc_gmm_em_step(const float* z, int64_t n, int d, int K, const float* params, double* stats, int32_t* labels,
+                    float* resp, const double* ctrl, int mode, void* workspace,
+                    size_t workspace_bytes, scc_stream_t stream) {
+    return scc::gmm_em_step(z, n, d, K, params, stats, labels, resp, ctrl, mode, workspace,
+                            workspace_bytes, (cudaStream_t)stream);
+}
+
+int scc_gmm_finalize(const double* stats, double n_total, int d, int K, double reg_covar, double nk_eps, double tol,
+                     double* means, double* weights, double* covariances, double* prec_chol, float* params,
+                     double* ctrl, scc_stream_t stream) {
+    return scc::gmm_finalize(stats, n_total, d, K, reg_covar, nk_eps, tol, means, weights, covariances, prec_chol,
+                             params, ctrl, (cudaStream_t)stream);
+}
+
+int scc_gmm_pack_params(const double* weights, const double* means, const double* covariances, int d, int K,
+                        double* prec_chol, float* params, double* ctrl, scc_stream_t stream) {
+    return scc::gmm_pack_params(weights, means, covariances, d, K, prec_chol, params, ctrl, (cudaStream_t)stream);
+}
+
+}  // extern "C"

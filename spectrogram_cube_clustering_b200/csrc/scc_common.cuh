@@ -1,0 +1,237 @@
+// scc_common.cuh — shared device helpers for the sm_100a clustering kernels.
+//
+// Data movement model: every N-sized pass is a persistent grid
+// of CTAs that stream TILE-point tiles of the row-major latent buffer z[n,d]
+// through a shared-memory ring.  Dense row layouts (odd d, or d = 4 mod 8) are
+// filled by one elected thread with a 1-D TMA bulk copy (cp.async.bulk ->
+// UBLKCP) completing on an mbarrier; layouts that need padding to stay free of
+// bank conflicts (d = 0 mod 8, even d) are filled cooperatively with coalesced
+// 128-bit loads.  Each thread then owns one latent point (its row lives in
+// registers), centroids / Cholesky factors are broadcast from shared memory,
+// and per-cluster statistics are reduced warp -> CTA -> grid in a fixed order.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "scc_b200.h"
+
+namespace scc {
+
+constexpr int kWarp = 32;
+
+// ----------------------------------------------------------------------------
+// Shared-memory row layout of a tile of latent points.
+// ----------------------------------------------------------------------------
+template <int D>
+struct RowLayout {
+    static constexpr bool kVec4 = (D % 4 == 0);
+    // Row stride (floats) chosen so that "lane i reads row i" is conflict free:
+    //  * float4 reads: (LD/4) must be odd  -> d = 0 mod 8 gets 4 floats of padding
+    //  * scalar reads: LD must be odd      -> even d (not multiple of 4) gets 1
+    static constexpr int LD = kVec4 ? (((D / 4) % 2 == 1) ? D : D + 4) : ((D % 2 == 1) ? D : D + 1);
+    static constexpr bool kDense = (LD == D);
+};
+
+template <int D>
+__device__ __forceinline__ void load_row(const float* __restrict__ tile, int t, float (&r)[D]) {
+    const float* p = tile + t * RowLayout<D>::LD;
+    if constexpr (RowLayout<D>::kVec4) {
+#pragma unroll
+        for (int c = 0; c < D / 4; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(p + 4 * c);
+            r[4 * c + 0] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < D; ++c) r[c] = p[c];
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void store_row(float* __restrict__ tile, int t, const float (&r)[D]) {
+    float* p = tile + t * RowLayout<D>::LD;
+    if constexpr (RowLayout<D>::kVec4) {
+#pragma unroll
+        for (int c = 0; c < D / 4; ++c)
+            *reinterpret_cast<float4*>(p + 4 * c) = make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < D; ++c) p[c] = r[c];
+    }
+}
+
+// ----------------------------------------------------------------------------
+// mbarrier + TMA bulk copy (1-D) wrappers.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// global -> shared::cta bulk copy; dst/src 16-byte aligned, bytes multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared::cta -> global bulk store (bulk async-group completion).
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// ----------------------------------------------------------------------------
+// Streaming ring of z tiles.
+//   TILE points per tile, STAGES buffers, NT threads per CTA.
+//   Protocol per CTA (tile_i = blockIdx.x + i * gridDim.x):
+//     prologue : issue(s, tile_s) for s < STAGES ; __syncthreads()
+//     iteration: wait(stage) ; read rows into registers ; __syncthreads() ;
+//                issue(stage, tile_{i+STAGES}) ; compute
+//   STAGES >= 2 so a cooperatively (non-TMA) filled stage is always separated
+//   from its consumer by the __syncthreads() of an intervening iteration.
+// ----------------------------------------------------------------------------
+template <int D, int TILE, int STAGES, int NT>
+struct ZRing {
+    using L = RowLayout<D>;
+    static constexpr int kTileFloats = TILE * L::LD;
+    static constexpr uint32_t kTileBytes = TILE * D * sizeof(float);
+    static_assert(STAGES >= 2, "ring needs two stages");
+    static_assert((TILE * D) % 4 == 0, "tile must be a multiple of 16 bytes");
+
+    float* buf;
+    uint64_t* bar;
+    const float* z;
+    int64_t n;
+    int64_t num_tiles;
+
+    __device__ __forceinline__ void init(float* b, uint64_t* br, const float* z_, int64_t n_) {
+        buf = b; bar = br; z = z_; n = n_;
+        num_tiles = (n_ + TILE - 1) / TILE;
+        if (L::kDense && threadIdx.x == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
+            fence_mbar_init();
+        }
+    }
+    __device__ __forceinline__ int points(int64_t tile) const {
+        const int64_t rem = n - tile * TILE;
+        return rem >= TILE ? TILE : static_cast<int>(rem);
+    }
+    __device__ __forceinline__ float* stage_ptr(int stage) const { return buf + stage * kTileFloats; }
+
+    // Called by ALL threads at the same program point.
+    __device__ __forceinline__ void issue(int stage, int64_t tile) {
+        if (tile >= num_tiles) return;
+        float* dst = stage_ptr(stage);
+        const float* src = z + tile * (int64_t)TILE * D;
+        const int np = points(tile);
+        if (L::kDense && np == TILE) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar[stage], kTileBytes);
+                bulk_g2s(dst, src, kTileBytes, &bar[stage]);
+            }
+        } else if constexpr (L::kVec4) {
+            const int nvec = np * (D / 4);
+            const float4* src4 = reinterpret_cast<const float4*>(src);
+            for (int v = threadIdx.x; v < nvec; v += NT) {
+                const int row = v / (D / 4), c4 = v - row * (D / 4);
+                *reinterpret_cast<float4*>(dst + row * L::LD + 4 * c4) = ldg_stream4(src4 + v);
+            }
+        } else {
+            const int nf = np * D;
+            for (int f = threadIdx.x; f < nf; f += NT) {
+                const int row = f / D, c = f - row * D;
+                dst[row * L::LD + c] = ldg_stream(src + f);
+            }
+        }
+    }
+    // use_index = how many times this stage has been consumed before (i / STAGES).
+    __device__ __forceinline__ void wait(int stage, int64_t tile, uint32_t use_index) {
+        if (L::kDense && points(tile) == TILE) mbar_wait(&bar[stage], use_index & 1u);
+    }
+};
+
+// ----------------------------------------------------------------------------
+// Reductions.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// CTA-level statistics (float64, in shared memory) -> per-CTA slot of `partials`
+// -> the last CTA to arrive sums all slots in CTA order into `out`.
+// Deterministic for a fixed grid.  `counter` must be 0 on entry and is reset.
+__device__ __forceinline__ void grid_publish(const double* cta_stats, int S, double* partials,
+                                             unsigned int* counter, double* out) {
+    __shared__ bool s_last;
+    double* mine = partials + (size_t)blockIdx.x * S;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) mine[s] = cta_stats[s];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(counter, 1u);
+        s_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const int G = gridDim.x;
+        for (int s = threadIdx.x; s < S; s += blockDim.x) {
+            double acc = 0.0;
+            for (int b = 0; b < G; ++b) acc += __ldcg(partials + (size_t)b * S + s);
+            out[s] = acc;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
+__device__ __forceinline__ float round_dec5(float x) {
+    // np.round(x, 5): rint (half-to-even) of x * 1e5, scaled back.
+    return rintf(x * 100000.0f) * 1.0e-5f;
+}
+
+}  // namespace scc

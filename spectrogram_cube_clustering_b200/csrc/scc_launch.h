@@ -1,0 +1,56 @@
+// scc_launch.h — host-side declarations shared by the kernel translation units
+// and the C-ABI glue (scc_api.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "scc_b200.h"
+
+namespace scc {
+
+// Latent dimensions with kernel instantiations.  Other d in [1,32] are served
+// by the Python host through zero-padding of z and mu (exact for the DEC path).
+#define SCC_FOR_EACH_DIM(M, A) M(4, A) M(8, A) M(9, A) M(10, A) M(12, A) M(16, A) M(20, A) M(24, A) M(32, A)
+
+constexpr int kMaxCtasPerSm = 8;
+constexpr int kMaxDecGrid = 2048;      // persistent DEC grids never exceed this many CTAs
+constexpr int kMaxGmmGrid = 512;
+constexpr size_t kWorkspaceHeader = 256;   // counters live in front of the partial slots
+
+void set_cuda_error(cudaError_t e, const char* what, int line);
+size_t workspace_bytes(int d, int K);
+bool dec_supported(int d, int K);
+bool gmm_supported(int d, int K);
+
+#define SCC_CUDA(expr)                                                   \
+    do {                                                                 \
+        cudaError_t scc_e_ = (expr);                                     \
+        if (scc_e_ != cudaSuccess) {                                     \
+            ::scc::set_cuda_error(scc_e_, #expr, __LINE__);              \
+            return SCC_ERR_CUDA;                                         \
+        }                                                                \
+    } while (0)
+
+int dec_assign(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
+               float* q, int32_t* labels, const int32_t* labels_prev, double* stats,
+               void* ws, size_t ws_bytes, cudaStream_t st);
+int dec_target(const float* q, int64_t n, int K, const double* f, int round_decimals, float* p, cudaStream_t st);
+int colsum(const float* q, int64_t n, int K, double* f, void* ws, size_t ws_bytes, cudaStream_t st);
+int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* p,
+                const double* f_cols, int round_decimals, float scale, float* dz, double* stats,
+                void* ws, size_t ws_bytes, cudaStream_t st);
+int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* grad_q,
+                 float* dz, double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
+
+int gmm_em_step(const float* z, int64_t n, int d, int K, const float* params, double* stats,
+                int32_t* labels, float* resp, const double* ctrl, int mode,
+                void* ws, size_t ws_bytes, cudaStream_t st);
+int gmm_finalize(const double* stats, double n_total, int d, int K, double reg_covar, double nk_eps, double tol,
+                 double* means, double* weights, double* covariances, double* prec_chol, float* params,
+                 double* ctrl, cudaStream_t st);
+int gmm_pack_params(const double* weights, const double* means, const double* covariances, int d, int K,
+                    double* prec_chol, float* params, double* ctrl, cudaStream_t st);
+
+}  // namespace scc

@@ -1,0 +1,264 @@
+"""Device operators of the clustering hot path: torch tensors in, C-ABI launches out.
+
+Every function takes CUDA tensors, launches the hand-written sm_100a kernels of
+``libscc_b200.so`` on the CURRENT torch stream through the C ABI
+(``include/scc_b200.h``) and returns freshly allocated CUDA tensors.  They are
+also registered as PyTorch custom ops under ``torch.ops.scc_b200``.
+There is no CPU path: a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+SUPPORTED_DIMS = (4, 8, 9, 10, 12, 16, 20, 24, 32)
+MAX_K = _lib.MAX_K
+
+_workspaces: dict = {}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.SccError(f"{name} must be a CUDA tensor: the clustering ops have no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def workspace(device, d: int, K: int) -> torch.Tensor:
+    """Per-(device, stream, d, K) scratch buffer for the grid reductions."""
+    lib = _lib.load()
+    key = (torch.device(device).index, _stream(), d, K)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = lib.scc_workspace_bytes(d, K)
+        if nbytes == 0:
+            raise ValueError(f"unsupported shape d={d}, K={K}")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.check(lib.scc_workspace_init(ws.data_ptr(), nbytes, _stream()), "scc_workspace_init")
+        _workspaces[key] = ws
+    return ws
+
+
+def padded_dim(d: int) -> int:
+    """Smallest instantiated latent dimension >= d (zero-padding is exact for DEC)."""
+    for s in SUPPORTED_DIMS:
+        if s >= d:
+            return s
+    raise ValueError(f"latent dimension {d} exceeds {_lib.MAX_D}")
+
+
+# --------------------------------------------------------------------------- DEC
+def dec_assign(z, mu, alpha=1.0, round_decimals=0, want_q=True, want_labels=True, labels_prev=None,
+               out_q=None, out_labels=None, out_stats=None):
+    """z [n,d], mu [K,d] -> (q [n,K] | None, labels int32 [n] | None, stats float64 [K+1]).
+
+    stats = (f_0..f_{K-1}, number of labels != labels_prev).  networks.py:279-288,
+    models.py:92,94,1098-1099,1320.
+    """
+    lib = _lib.load()
+    _require(z, "z"); _require(mu, "mu")
+    n, d = z.shape
+    K = mu.shape[0]
+    if mu.shape[1] != d:
+        raise ValueError("mu and z disagree on the latent dimension")
+    q = out_q if out_q is not None else (torch.empty(n, K, dtype=torch.float32, device=z.device) if want_q else None)
+    labels = out_labels if out_labels is not None else (
+        torch.empty(n, dtype=torch.int32, device=z.device) if want_labels else None)
+    if labels_prev is not None:
+        _require(labels_prev, "labels_prev", torch.int32)
+    stats = out_stats if out_stats is not None else torch.empty(K + 1, dtype=torch.float64, device=z.device)
+    ws = workspace(z.device, d, K)
+    rc = lib.scc_dec_assign(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), int(round_decimals), _ptr(q),
+                            _ptr(labels), _ptr(labels_prev), stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "scc_dec_assign")
+    return q, labels, stats
+
+
+def dec_target(q, f, round_decimals=0, out=None):
+    """q [n,K], f float64 [>=K] -> p [n,K].  models.py:1320-1322."""
+    lib = _lib.load()
+    _require(q, "q"); _require(f, "f", torch.float64)
+    n, K = q.shape
+    p = out if out is not None else torch.empty_like(q)
+    rc = lib.scc_dec_target(q.data_ptr(), n, K, f.data_ptr(), int(round_decimals), p.data_ptr(), _stream())
+    _lib.check(rc, "scc_dec_target")
+    return p
+
+
+def colsum(q):
+    """f_j = sum_i q_ij (float64 [K]) of a caller-supplied q.  models.py:1320."""
+    lib = _lib.load()
+    _require(q, "q")
+    n, K = q.shape
+    f = torch.empty(K, dtype=torch.float64, device=q.device)
+    ws = workspace(q.device, 4, K)
+    _lib.check(lib.scc_colsum(q.data_ptr(), n, K, f.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "scc_colsum")
+    return f
+
+
+def dec_kl_grad(z, mu, alpha=1.0, p=None, f=None, round_decimals=0, scale=1.0, want_dz=True,
+                out_dz=None, out_stats=None):
+    """-> (stats float64 [K*d+2] = (loss, sum_i s_i, dmu[K,d]), dz [n,d] | None).  models.py:1124-1127."""
+    lib = _lib.load()
+    _require(z, "z"); _require(mu, "mu")
+    n, d = z.shape
+    K = mu.shape[0]
+    if p is not None:
+        _require(p, "p")
+        if tuple(p.shape) != (n, K):
+            raise ValueError("p must be [n, K]")
+    if f is not None:
+        _require(f, "f", torch.float64)
+    if p is None and f is None:
+        raise ValueError("need the target p or the column sums f")
+    dz = out_dz if out_dz is not None else (torch.empty_like(z) if want_dz else None)
+    stats = out_stats if out_stats is not None else torch.empty(K * d + 2, dtype=torch.float64, device=z.device)
+    ws = workspace(z.device, d, K)
+    rc = lib.scc_dec_kl_grad(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), _ptr(p), _ptr(f),
+                             int(round_decimals), float(scale), _ptr(dz), stats.data_ptr(), ws.data_ptr(),
+                             ws.numel(), _stream())
+    _lib.check(rc, "scc_dec_kl_grad")
+    return stats, dz
+
+
+def dec_backward(z, mu, grad_q, alpha=1.0, want_dz=True):
+    """Layer backward for an arbitrary dL/dq -> (dz [n,d] | None, dmu float64 [K,d])."""
+    lib = _lib.load()
+    _require(z, "z"); _require(mu, "mu"); _require(grad_q, "grad_q")
+    n, d = z.shape
+    K = mu.shape[0]
+    dz = torch.empty_like(z) if want_dz else None
+    stats = torch.empty(K * d + 2, dtype=torch.float64, device=z.device)
+    ws = workspace(z.device, d, K)
+    rc = lib.scc_dec_backward(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), grad_q.data_ptr(), _ptr(dz),
+                              stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "scc_dec_backward")
+    return dz, stats[2:].view(K, d)
+
+
+# --------------------------------------------------------------------------- GMM
+def gmm_param_floats(K, d):
+    return K * d + K * (d * (d + 1) // 2) + K
+
+
+def gmm_stat_doubles(K, d):
+    return 1 + K + K * d + K * (d * (d + 1) // 2)
+
+
+def gmm_supported(d, K):
+    return bool(_lib.load().scc_gmm_supported(d, K))
+
+
+def gmm_pack_params(weights, means, covariances, params=None, prec_chol=None, ctrl=None):
+    """(pi [K], mu [K,d], Sigma [K,d,d]) float64 -> packed float32 E-step block, U, ctrl."""
+    lib = _lib.load()
+    _require(weights, "weights", torch.float64); _require(means, "means", torch.float64)
+    _require(covariances, "covariances", torch.float64)
+    K, d = means.shape
+    dev = means.device
+    params = params if params is not None else torch.empty(gmm_param_floats(K, d), dtype=torch.float32, device=dev)
+    prec_chol = prec_chol if prec_chol is not None else torch.empty(K, d, d, dtype=torch.float64, device=dev)
+    ctrl = ctrl if ctrl is not None else torch.zeros(8, dtype=torch.float64, device=dev)
+    rc = lib.scc_gmm_pack_params(weights.data_ptr(), means.data_ptr(), covariances.data_ptr(), d, K,
+                                 prec_chol.data_ptr(), params.data_ptr(), ctrl.data_ptr(), _stream())
+    _lib.check(rc, "scc_gmm_pack_params")
+    return params, prec_chol, ctrl
+
+
+GMM_ESTEP_ONLY, GMM_SOFT, GMM_HARD = 0, 1, 2
+
+
+def gmm_em_step(z, K, params, stats=None, labels=None, resp=None, ctrl=None, mode=GMM_SOFT):
+    """One fused E+M statistics pass.  Returns the packed float64 stats tensor."""
+    lib = _lib.load()
+    _require(z, "z"); _require(params, "params")
+    n, d = z.shape
+    stats = stats if stats is not None else torch.empty(gmm_stat_doubles(K, d), dtype=torch.float64, device=z.device)
+    ws = workspace(z.device, d, K)
+    rc = lib.scc_gmm_em_step(z.data_ptr(), n, d, K, params.data_ptr(), stats.data_ptr(), _ptr(labels), _ptr(resp),
+                             _ptr(ctrl), int(mode), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "scc_gmm_em_step")
+    return stats
+
+
+def gmm_finalize(stats, n_total, means, weights, covariances, prec_chol, params, ctrl,
+                 reg_covar=1e-6, nk_eps=10 * 2.220446049250313e-16, tol=1e-3):
+    """M-step finalisation on the device (in place on means/weights/covariances/prec_chol/params/ctrl)."""
+    lib = _lib.load()
+    K, d = means.shape
+    rc = lib.scc_gmm_finalize(stats.data_ptr(), float(n_total), d, K, float(reg_covar), float(nk_eps), float(tol),
+                              means.data_ptr(), weights.data_ptr(), covariances.data_ptr(), prec_chol.data_ptr(),
+                              params.data_ptr(), ctrl.data_ptr(), _stream())
+    _lib.check(rc, "scc_gmm_finalize")
+
+
+# --------------------------------------------------------------------------- torch.library registration
+def _register_custom_ops():
+    """Expose the launches as PyTorch custom ops (torch.ops.scc_b200.*)."""
+    from torch.library import custom_op
+
+    @custom_op("scc_b200::dec_assign", mutates_args=(), device_types="cuda")
+    def _dec_assign(z: torch.Tensor, mu: torch.Tensor, alpha: float, round_decimals: int) -> tuple[
+            torch.Tensor, torch.Tensor, torch.Tensor]:
+        q, labels, stats = dec_assign(z, mu, alpha, round_decimals)
+        return q, labels, stats
+
+    @_dec_assign.register_fake
+    def _(z, mu, alpha, round_decimals):
+        n, K = z.shape[0], mu.shape[0]
+        return (z.new_empty(n, K), z.new_empty(n, dtype=torch.int32), z.new_empty(K + 1, dtype=torch.float64))
+
+    @custom_op("scc_b200::dec_target", mutates_args=(), device_types="cuda")
+    def _dec_target(q: torch.Tensor, f: torch.Tensor, round_decimals: int) -> torch.Tensor:
+        return dec_target(q, f, round_decimals)
+
+    @_dec_target.register_fake
+    def _(q, f, round_decimals):
+        return torch.empty_like(q)
+
+    @custom_op("scc_b200::dec_kl_grad", mutates_args=(), device_types="cuda")
+    def _dec_kl_grad(z: torch.Tensor, mu: torch.Tensor, p: torch.Tensor, alpha: float, scale: float) -> tuple[
+            torch.Tensor, torch.Tensor]:
+        stats, dz = dec_kl_grad(z, mu, alpha, p=p, scale=scale)
+        return stats, dz
+
+    @_dec_kl_grad.register_fake
+    def _(z, mu, p, alpha, scale):
+        return z.new_empty(mu.numel() + 2, dtype=torch.float64), torch.empty_like(z)
+
+    @custom_op("scc_b200::dec_backward", mutates_args=(), device_types="cuda")
+    def _dec_backward(z: torch.Tensor, mu: torch.Tensor, grad_q: torch.Tensor, alpha: float) -> tuple[
+            torch.Tensor, torch.Tensor]:
+        dz, dmu = dec_backward(z, mu, grad_q, alpha)
+        return dz, dmu.clone()
+
+    @_dec_backward.register_fake
+    def _(z, mu, grad_q, alpha):
+        return torch.empty_like(z), mu.new_empty(mu.shape, dtype=torch.float64)
+
+    @custom_op("scc_b200::gmm_em_step", mutates_args=(), device_types="cuda")
+    def _gmm_em_step(z: torch.Tensor, params: torch.Tensor, K: int) -> torch.Tensor:
+        return gmm_em_step(z, K, params)
+
+    @_gmm_em_step.register_fake
+    def _(z, params, K):
+        return z.new_empty(gmm_stat_doubles(K, z.shape[1]), dtype=torch.float64)
+
+
+try:
+    _register_custom_ops()
+except Exception as _exc:  # pragma: no cover - registration is best effort on exotic torch builds
+    import warnings
+    warnings.warn(f"scc_b200 custom-op registration skipped: {_exc}")

@@ -1,0 +1,283 @@
+"""GPU parity: the CUDA path (through the C ABI) vs golden vectors produced by the
+reference, and vs the float64 oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): hard labels bit-identical except at exact ties;
+q, p, loss, gradients, means, covariances within 1e-5 relative (max-normalised,
+fp32 kernels vs float64 reference).  Outputs that pass through the reference's
+5-decimal rounding are compared to one rounding quantum (1e-5 absolute): an
+fp32 q within ~1e-7 of a rounding boundary legitimately lands on the other side.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err, DEC_CASES, GMM_CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+QUANTUM = 1.0e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from spectrogram_cube_clustering_b200 import ops as _ops
+    assert torch.cuda.is_available()
+    return _ops
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(device="cuda", dtype=dtype).contiguous()
+
+
+@pytest.mark.parametrize("case", DEC_CASES)
+def test_dec_assign_golden(ops, case):
+    g = load_golden("dec", case)
+    z, mu = dev(g["z"]), dev(g["mu"])
+    q, labels, stats = ops.dec_assign(z, mu, float(g["alpha"]), 0)
+    assert rel_err(q.cpu().numpy(), g["q"]) < TOL
+    lab = labels.cpu().numpy().astype(np.int64)
+    mism = lab != g["labels"]
+    if mism.any():                       # only exact-tie rows may differ (fp64 ties that fp32 breaks)
+        qs = np.sort(g["q"][mism], axis=1)
+        assert np.all(qs[:, -1] - qs[:, -2] < 1e-6)
+    assert mism.mean() < 1e-3
+    assert rel_err(stats[:-1].cpu().numpy(), g["q"].sum(0)) < TOL
+    assert stats[-1].item() == 0
+    # rounded mode: np.round(q, 5), f over the rounded q
+    qr, _, stats_r = ops.dec_assign(z, mu, float(g["alpha"]), 5)
+    dq = np.abs(qr.cpu().numpy() - g["q_round"])
+    assert dq.max() <= QUANTUM * 1.01 and (dq > 1e-7).mean() < 0.03
+    assert rel_err(stats_r[:-1].cpu().numpy(), g["f"]) < TOL
+
+
+@pytest.mark.parametrize("case", DEC_CASES)
+def test_dec_target_golden(ops, case):
+    g = load_golden("dec", case)
+    q_round = dev(g["q_round"])
+    f = dev(g["f"], torch.float64)
+    p5 = ops.dec_target(q_round, f, 5).cpu().numpy()
+    d = np.abs(p5 - g["p"])
+    assert d.max() <= QUANTUM * 1.01 and (d > 1e-7).mean() < 0.03
+    from oracle import dec as odec
+    p0 = ops.dec_target(q_round, f, 0).cpu().numpy()
+    assert rel_err(p0, odec.target_distribution(g["q_round"], None)) < TOL
+    assert rel_err(ops.colsum(q_round).cpu().numpy(), g["f"]) < 1e-6
+
+
+@pytest.mark.parametrize("case", DEC_CASES)
+def test_dec_kl_grad_api_mode_golden(ops, case):
+    """p supplied (the reference's own rounded target) -> loss, dz, dmu of autograd."""
+    g = load_golden("dec", case)
+    n, d = g["z"].shape
+    K = g["mu"].shape[0]
+    z, mu, p = dev(g["z"]), dev(g["mu"]), dev(g["p"])
+    stats, dz = ops.dec_kl_grad(z, mu, float(g["alpha"]), p=p, scale=float(g["gamma"]) / n)
+    stats = stats.cpu().numpy()
+    assert abs(stats[0] - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    assert abs(stats[1] - g["p"].sum()) <= 1e-6 * n
+    assert rel_err(dz.cpu().numpy(), g["dz"]) < TOL
+    assert rel_err(stats[2:].reshape(K, d), g["dmu"]) < TOL
+    stats2, none = ops.dec_kl_grad(z, mu, float(g["alpha"]), p=p, scale=float(g["gamma"]) / n, want_dz=False)
+    assert none is None and np.array_equal(stats2.cpu().numpy(), stats)      # deterministic reduction
+
+
+@pytest.mark.parametrize("case", DEC_CASES)
+def test_dec_kl_grad_fused_mode_oracle(ops, case):
+    """p rebuilt in-kernel from the column sums, unrounded -> oracle unrounded chain."""
+    from oracle import dec as odec
+    g = load_golden("dec", case)
+    n, d = g["z"].shape
+    K = g["mu"].shape[0]
+    alpha, gamma = float(g["alpha"]), float(g["gamma"])
+    ref = odec.dec_step(g["z"], g["mu"], alpha, gamma, round_to=None)
+    z, mu = dev(g["z"]), dev(g["mu"])
+    _, _, st = ops.dec_assign(z, mu, alpha, 0, want_q=False, want_labels=False)
+    stats, dz = ops.dec_kl_grad(z, mu, alpha, f=st, round_decimals=0, scale=gamma / n)
+    stats = stats.cpu().numpy()
+    assert abs(stats[0] - ref["loss"]) <= TOL * abs(ref["loss"])
+    assert rel_err(dz.cpu().numpy(), ref["dz"]) < TOL
+    assert rel_err(stats[2:].reshape(K, d), ref["dmu"]) < TOL
+    # rounded fused mode reproduces the reference's quantised chain to the quantisation noise
+    _, _, st5 = ops.dec_assign(z, mu, alpha, 5, want_q=False, want_labels=False)
+    stats5, _ = ops.dec_kl_grad(z, mu, alpha, f=st5, round_decimals=5, scale=gamma / n, want_dz=False)
+    stats5 = stats5.cpu().numpy()
+    assert abs(stats5[0] - float(g["loss"])) <= 2e-4 * abs(float(g["loss"]))
+    assert rel_err(stats5[2:].reshape(K, d), g["dmu"]) < 2e-4
+
+
+@pytest.mark.parametrize("case", DEC_CASES)
+def test_dec_backward_generic_golden(ops, case):
+    g = load_golden("dec", case)
+    z, mu, G = dev(g["z"]), dev(g["mu"]), dev(g["G"])
+    dz, dmu = ops.dec_backward(z, mu, G, float(g["alpha"]))
+    assert rel_err(dz.cpu().numpy(), g["dz_generic"]) < TOL
+    assert rel_err(dmu.cpu().numpy(), g["dmu_generic"]) < TOL
+
+
+@pytest.mark.parametrize("n,d,K", [(1, 9, 8), (255, 9, 5), (257, 32, 16), (4097, 16, 7), (1000, 10, 16),
+                                   (777, 8, 3), (300, 4, 2), (513, 12, 16), (1025, 20, 8), (640, 24, 12)])
+def test_dec_shapes_vs_oracle(ops, n, d, K):
+    from oracle import dec as odec
+    rng = np.random.default_rng(n + d + K)
+    z = rng.normal(size=(n, d)).astype(np.float32) * 1.5 + 1.0
+    mu = rng.normal(size=(K, d)).astype(np.float32) + 1.0
+    ref = odec.dec_step(z, mu, 1.0, 1e-3, round_to=None)
+    zt, mt = dev(z), dev(mu)
+    q, labels, st = ops.dec_assign(zt, mt, 1.0, 0)
+    assert rel_err(q.cpu().numpy(), ref["q"]) < TOL
+    assert (labels.cpu().numpy() != ref["labels"]).mean() < 2e-3
+    assert rel_err(st[:-1].cpu().numpy(), ref["f"]) < TOL
+    p = ops.dec_target(q, st, 0)
+    assert rel_err(p.cpu().numpy(), ref["p"]) < 2 * TOL
+    stats, dz = ops.dec_kl_grad(zt, mt, 1.0, f=st, scale=1e-3 / n)
+    stats = stats.cpu().numpy()
+    if n == 1:          # p == q exactly: loss and gradients vanish, only fp32 noise is left
+        assert abs(stats[0]) < 1e-8 and np.abs(dz.cpu().numpy()).max() < 1e-8
+        return
+    assert abs(stats[0] - ref["loss"]) <= TOL * abs(ref["loss"])
+    assert rel_err(dz.cpu().numpy(), ref["dz"]) < TOL
+    assert rel_err(stats[2:].reshape(K, d), ref["dmu"]) < TOL
+    # property: translation invariance  sum_i dz_i = - sum_j dmu_j
+    np.testing.assert_allclose(dz.double().sum(0).cpu().numpy(), -stats[2:].reshape(K, d).sum(0),
+                               atol=1e-6 * np.abs(stats[2:]).max() * K)
+
+
+def test_dec_empty_and_label_changes(ops):
+    z = torch.zeros(0, 9, device="cuda")
+    mu = torch.randn(8, 9, device="cuda")
+    q, labels, st = ops.dec_assign(z, mu)
+    assert q.shape == (0, 8) and torch.all(st == 0)
+    z = torch.randn(5000, 9, device="cuda")
+    _, lab, _ = ops.dec_assign(z, mu)
+    prev = lab.clone()
+    prev[:137] = (prev[:137] + 1) % 8
+    _, _, st = ops.dec_assign(z, mu, labels_prev=prev)
+    assert st[-1].item() == 137
+
+
+def test_dec_zero_column_gives_nan_like_reference(ops):
+    q = torch.rand(64, 8, device="cuda")
+    q[:, 3] = 0
+    f = ops.colsum(q)
+    p = ops.dec_target(q, f, 0)
+    assert torch.isnan(p).all(dim=1).all()          # q^2/0 -> nan poisons every row (models.py:1320-1321)
+
+
+# ------------------------------------------------------------------------------ GMM
+class _GmmState:
+    def __init__(self, ops, w, mu, cov):
+        self.ops = ops
+        self.means = dev(mu, torch.float64)
+        self.weights = dev(w, torch.float64)
+        self.cov = dev(cov, torch.float64)
+        self.K, self.d = self.means.shape
+        self.params, self.pchol, self.ctrl = ops.gmm_pack_params(self.weights, self.means, self.cov)
+
+    def em(self, z, resp=None, tol=0.0):
+        stats = self.ops.gmm_em_step(z, self.K, self.params, resp=resp, ctrl=self.ctrl)
+        self.ops.gmm_finalize(stats, z.shape[0], self.means, self.weights, self.cov, self.pchol, self.params,
+                              self.ctrl, tol=tol)
+        c = self.ctrl.cpu().numpy()
+        return dict(lb=c[0], weights=self.weights.cpu().numpy().copy(), means=self.means.cpu().numpy().copy(),
+                    cov=self.cov.cpu().numpy().copy(), pchol=self.pchol.cpu().numpy().copy(), ctrl=c)
+
+    def labels(self, z):
+        lab = torch.empty(z.shape[0], dtype=torch.int32, device="cuda")
+        self.ops.gmm_em_step(z, self.K, self.params, labels=lab, mode=self.ops.GMM_ESTEP_ONLY)
+        return lab.cpu().numpy()
+
+
+def _mat_err(a, b):
+    return max(rel_err(a[k], b[k]) for k in range(a.shape[0]))
+
+
+GMM_GPU_CASES = [c for c in GMM_CASES]
+
+
+@pytest.mark.parametrize("case", GMM_GPU_CASES)
+def test_gmm_step_from_identical_state_golden(ops, case):
+    """One fused EM iteration from sklearn's own state of the previous iteration
+    (parity is pinned per iteration from identical state)."""
+    g = load_golden("gmm", case)
+    if not ops.gmm_supported(g["z"].shape[1], g["mu0"].shape[0]):
+        pytest.skip("GMM kernels not instantiated for this d")
+    z = dev(g["z"])
+    n, K = z.shape[0], g["mu0"].shape[0]
+    iters = g["it_lower_bound"].shape[0]
+    for it in range(iters):
+        if it == 0:
+            st = _GmmState(ops, g["w0"], g["mu0"], g["cov0"])
+        else:
+            st = _GmmState(ops, g["it_weights"][it - 1], g["it_means"][it - 1], g["it_covariances"][it - 1])
+            assert _mat_err(st.pchol.cpu().numpy(), g["it_pchol"][it - 1]) < 1e-9      # float64 Cholesky path
+        resp = torch.empty(n, K, device="cuda") if it == 0 else None
+        h = st.em(z, resp=resp)
+        if it == 0:
+            assert np.max(np.abs(resp.cpu().numpy() - np.exp(g["log_resp0"]))) < TOL
+        assert abs(h["lb"] - g["it_lower_bound"][it]) < TOL * abs(g["it_lower_bound"][it])
+        assert rel_err(h["weights"], g["it_weights"][it]) < TOL
+        assert rel_err(h["means"], g["it_means"][it]) < TOL
+        assert _mat_err(h["cov"], g["it_covariances"][it]) < TOL
+        # U = chol(Sigma)^-T amplifies by cond(Sigma) (up to 1/reg_covar = 1e6 here): compare the
+        # precision it represents through Sigma, i.e. U U^T Sigma_ref = I
+        for k in range(K):
+            prod = h["pchol"][k] @ h["pchol"][k].T @ g["it_covariances"][it][k]
+            assert np.abs(prod - np.eye(prod.shape[0])).max() < 2e-2
+    st = _GmmState(ops, g["it_weights"][-1], g["it_means"][-1], g["it_covariances"][-1])
+    assert (st.labels(z) != g["labels_after"]).mean() < 2e-3
+
+
+@pytest.mark.parametrize("case", GMM_GPU_CASES)
+def test_gmm_fit_trajectory_golden(ops, case):
+    """Whole device-resident fit (tol = 1e-3, sklearn's stop rule) vs GaussianMixture.fit_predict:
+    same iteration count and converged flag; parameters to 1e-4 (errors compound over iterations
+    through components whose covariance has cond ~ 1/reg_covar), labels to 0.2 %."""
+    g = load_golden("gmm", case)
+    if not ops.gmm_supported(g["z"].shape[1], g["mu0"].shape[0]):
+        pytest.skip("GMM kernels not instantiated for this d")
+    z = dev(g["z"])
+    st = _GmmState(ops, g["w0"], g["mu0"], g["cov0"])
+    h = None
+    for it in range(100):
+        h = st.em(z, tol=float(g["tol"]))
+    c = h["ctrl"]
+    assert int(c[2]) == int(g["fit_n_iter"]) and bool(c[3]) == bool(g["fit_converged"]) and c[4] == 0
+    assert abs(c[0] - float(g["fit_lower_bound"])) < 1e-4 * abs(float(g["fit_lower_bound"]))
+    assert rel_err(h["means"], g["fit_means"]) < 1e-4
+    assert rel_err(h["weights"], g["fit_weights"]) < 1e-4
+    assert _mat_err(h["cov"], g["fit_covariances"]) < 2e-4
+    assert (st.labels(z) != g["fit_labels"]).mean() < 2e-3
+
+
+def test_gmm_hard_assign_matches_onehot_moments(ops):
+    """mode=HARD with Sigma=I, pi=1/K gives the one-hot (nearest-mean) statistics sklearn derives
+    from k-means labels (_base.py:119-128 -> _gaussian_mixture.py:282-320)."""
+    from oracle import gmm as ogmm
+    g = load_golden("gmm", "c1")
+    X = g["z"].astype(np.float64)
+    mu0 = g["mu0"]
+    K, d = mu0.shape
+    lab = np.argmin(((X[:, None, :] - mu0[None]) ** 2).sum(2), axis=1)
+    resp = np.zeros((X.shape[0], K)); resp[np.arange(X.shape[0]), lab] = 1
+    with np.errstate(divide="ignore"):
+        w_ref, mu_ref, cov_ref, _, _ = ogmm.m_step(X, np.log(resp))
+    st = _GmmState(ops, np.full(K, 1.0 / K), mu0, np.tile(np.eye(d), (K, 1, 1)))
+    z = dev(g["z"])
+    stats = ops.gmm_em_step(z, K, st.params, mode=ops.GMM_HARD)
+    ops.gmm_finalize(stats, z.shape[0], st.means, st.weights, st.cov, st.pchol, st.params, st.ctrl, tol=0.0)
+    assert rel_err(st.weights.cpu().numpy(), w_ref) < 1e-6
+    assert rel_err(st.means.cpu().numpy(), mu_ref) < TOL
+    assert _mat_err(st.cov.cpu().numpy(), cov_ref) < TOL
+
+
+def test_gmm_not_positive_definite_flag(ops):
+    """Degenerate data (all points identical, reg_covar = 0) must raise the not-PD flag
+    (sklearn raises ValueError, _gaussian_mixture.py:343-367) and freeze the fit."""
+    z = torch.ones(512, 9, device="cuda")
+    K, d = 4, 9
+    st = _GmmState(ops, np.full(K, 0.25), np.ones((K, d)) + 0.01 * np.arange(K)[:, None], np.tile(np.eye(d), (K, 1, 1)))
+    stats = ops.gmm_em_step(z, K, st.params, ctrl=st.ctrl)
+    ops.gmm_finalize(stats, 512, st.means, st.weights, st.cov, st.pchol, st.params, st.ctrl, reg_covar=0.0, tol=0.0)
+    c = st.ctrl.cpu().numpy()
+    assert c[4] > 0 and c[5] == 1
