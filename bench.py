@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the latent-space clustering hot path on B200.
+
+Workload at every N (weak scaling, per-GPU work fixed) = BASELINE.json configs[1]:
+  "DEC ClusteringLayer forward/backward + target distribution, N=1M latent points
+   d=9 K=8 alpha=1"  — one STEP is the reference chain over one latent set:
+     dec_assign  (q, labels, f; np.round(q,5))        networks.py:279-288, models.py:92-94
+     dec_target  (p = target_distribution(q))          models.py:1320-1322
+     dec_kl_grad (loss, dL/dz, dL/dmu; q recomputed)   models.py:1124-1127
+  with (N>1) the two packed-statistics all-reduces between/after them.
+
+Contract (one JSON line on rank 0): metric/value/unit, n_gpus, steps, warmup,
+ms_per_step, higher_is_better, scaling, vs_baseline, dtype, data, config, clocks,
+e2e, gpu_launches, roofline, cpu_baseline (+ "extra": GMM EM iteration and the
+fused d=32 latent-buffer DEC pass).  `--impl reference` times the reference's own
+CPU op chain (oracle port, torch CPU autograd + numpy, float64 as the reference
+runs it) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "latent points/sec per DEC step (ClusteringLayer fwd+bwd + target distribution)"
+UNIT = "points/s"
+N_PER_GPU, D, K, ALPHA, GAMMA = 1_000_000, 9, 8, 1.0, 1e-3
+N_SETS = 4                      # distinct input/output sets cycled so no step re-finds its data in L2
+WORKLOAD = "DEC fwd/bwd + target distribution, N=1M latent points per GPU, d=9, K=8, alpha=1 (BASELINE configs[1])"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Polls NVML (or nvidia-smi) for SM clock and throttle reasons while the GPU is under load."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons = index, [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _poll_once(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+        for bit, name in names.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._poll_once()
+            except Exception:
+                break
+            time.sleep(0.0005)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def reference_step_fn(n, dtype_name="float64"):
+    """The reference's own CPU op chain for one step (oracle port: same torch/numpy calls)."""
+    import torch
+    from oracle import dec as odec
+    from spectrogram_cube_clustering_b200 import synth
+    z, mu = synth.latent_points(n, D, K, rank=0, device="cpu")
+    dt = torch.float64 if dtype_name == "float64" else torch.float32
+    z, mu = z.to(dt), mu.to(dt)
+    return lambda: odec.torch_dec_step(z, mu, ALPHA, GAMMA)
+
+
+def time_reference(steps, warmup, budget_s=150.0):
+    import torch
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    n = N_PER_GPU
+    fn = reference_step_fn(n)
+    t0 = time.perf_counter(); fn(); first = time.perf_counter() - t0
+    if first * (steps + warmup) > budget_s:            # bound the sample so the run ends in minutes
+        n = max(10_000, int(n * budget_s / (first * (steps + warmup))))
+        fn = reference_step_fn(n)
+    for _ in range(max(0, warmup - 1)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=n / dt, ms_per_step=dt * 1e3, cores=cores, n=n,
+                sample=f"{steps} steps of the float64 reference op chain (torch CPU autograd + numpy "
+                       f"target_distribution) on {n} of {N_PER_GPU} points, {cores} threads")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = time_reference(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_points": r["n"], "d": D, "K": K, "alpha": ALPHA,
+                   "host": "reference CPU path (PyTorch CPU + numpy), no GPU"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from spectrogram_cube_clustering_b200 import ops, synth
+    from spectrogram_cube_clustering_b200.latent_buffer import LatentBuffer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    n_total = N_PER_GPU * world
+    hbm_peak, peak_src = peaks()
+
+    _, mu = synth.latent_points(16, D, K, device=dev)
+    sets = []
+    for s in range(N_SETS):
+        z, _ = synth.latent_points(N_PER_GPU, D, K, rank=rank * N_SETS + s, device=dev)
+        sets.append(dict(z=z, q=torch.empty(N_PER_GPU, K, device=dev), p=torch.empty(N_PER_GPU, K, device=dev),
+                         dz=torch.empty(N_PER_GPU, D, device=dev),
+                         labels=torch.empty(N_PER_GPU, dtype=torch.int32, device=dev),
+                         st1=torch.empty(K + 1, dtype=torch.float64, device=dev),
+                         st2=torch.empty(K * D + 2, dtype=torch.float64, device=dev)))
+    scale = GAMMA / n_total
+
+    def allreduce(t):
+        if world > 1:
+            dist.all_reduce(t, group=group)
+
+    def k_assign(s):
+        ops.dec_assign(s["z"], mu, ALPHA, 5, out_q=s["q"], out_labels=s["labels"], out_stats=s["st1"])
+
+    def k_target(s):
+        ops.dec_target(s["q"], s["st1"], 5, out=s["p"])
+
+    def k_grad(s):
+        ops.dec_kl_grad(s["z"], mu, ALPHA, p=s["p"], scale=scale, out_dz=s["dz"], out_stats=s["st2"])
+
+    def step(s):
+        k_assign(s); allreduce(s["st1"]); k_target(s); k_grad(s); allreduce(s["st2"])
+
+    # warm-up (eager): also creates workspaces and primes NCCL
+    for w in range(max(args.warmup, 3)):
+        step(sets[w % N_SETS])
+    torch.cuda.synchronize()
+
+    # CUDA graphs: one per input set (pointers are baked in)
+    graphs, use_graphs = [], not args.no_graphs
+    if use_graphs:
+        try:
+            cap_stream = torch.cuda.Stream()
+            with torch.cuda.stream(cap_stream):
+                for s in sets:
+                    step(s)                      # workspaces for the capture stream
+                cap_stream.synchronize()
+                for s in sets:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=cap_stream):
+                        step(s)
+                    graphs.append(g)
+            torch.cuda.synchronize()
+            for g in graphs:
+                g.replay()
+            torch.cuda.synchronize()
+        except Exception as exc:                  # pragma: no cover
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({exc}); timing eager launches", file=sys.stderr)
+            graphs, use_graphs = [], False
+
+    def run_step(i):
+        if use_graphs:
+            graphs[i % N_SETS].replay()
+        else:
+            step(sets[i % N_SETS])
+
+    for i in range(3):
+        run_step(i)
+    sampler = ClockSampler(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- timed region: EXACTLY `steps` steps ----------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    ev0.record()
+    for i in range(args.steps):
+        run_step(i)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    # keep the same load running a little longer so NVML gets samples even for very short regions
+    t_end = time.perf_counter() + 0.15
+    i = 0
+    while time.perf_counter() < t_end:
+        run_step(i); i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # ---------------- per-kernel durations (CUDA events, launch queue pre-loaded) ----------------
+    # The stream is first blocked by a spin kernel so that all launches + event records are queued
+    # before the GPU starts: consecutive events then bracket exactly one kernel.
+    kern = {"dec_assign": [], "dec_target": [], "dec_kl_grad": []}
+    reps = min(args.steps, 40)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(reps)]
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(4e8))
+    for r in range(reps):
+        s = sets[r % N_SETS]
+        evs[r][0].record(); k_assign(s); evs[r][1].record(); k_target(s); evs[r][2].record(); k_grad(s)
+        evs[r][3].record()
+    torch.cuda.synchronize()
+    for r in range(reps):
+        kern["dec_assign"].append(evs[r][0].elapsed_time(evs[r][1]))
+        kern["dec_target"].append(evs[r][1].elapsed_time(evs[r][2]))
+        kern["dec_kl_grad"].append(evs[r][2].elapsed_time(evs[r][3]))
+    kavg = {k: sum(v) / len(v) for k, v in kern.items()}
+    alg_bytes = {"dec_assign": 4 * D + 4 * K + 4, "dec_target": 8 * K, "dec_kl_grad": 8 * D + 4 * K}   # per point
+    dominant = max(kavg, key=kavg.get)
+    achieved = alg_bytes[dominant] * N_PER_GPU / (kavg[dominant] * 1e-3) / 1e9
+    step_bytes = sum(alg_bytes.values())
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_point": alg_bytes[dominant],
+                "kernels_ms": kavg,
+                "kernels_gbs": {k: alg_bytes[k] * N_PER_GPU / (kavg[k] * 1e-3) / 1e9 for k in kavg},
+                "step_gbs": step_bytes * N_PER_GPU / (ms_per_step * 1e-3) / 1e9,
+                "step_frac": step_bytes * N_PER_GPU / (ms_per_step * 1e-3) / 1e9 / hbm_peak}
+
+    # ---------------- end to end: host buffers in, host results out, every step ----------------
+    zh = [s["z"].cpu().pin_memory() for s in sets[:2]]
+    mu_h = mu.cpu().pin_memory()
+    res_h = torch.empty(K * D + 2 + K + 1, dtype=torch.float64).pin_memory()
+    zd = torch.empty(N_PER_GPU, D, device=dev)
+    mud = torch.empty_like(mu)
+    sd = sets[0]
+
+    def e2e_step(i):
+        zd.copy_(zh[i % 2], non_blocking=True)
+        mud.copy_(mu_h, non_blocking=True)
+        ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"])
+        allreduce(sd["st1"])
+        ops.dec_target(sd["q"], sd["st1"], 5, out=sd["p"])
+        ops.dec_kl_grad(zd, mud, ALPHA, p=sd["p"], scale=scale, out_dz=sd["dz"], out_stats=sd["st2"])
+        allreduce(sd["st2"])
+        res_h[:K * D + 2].copy_(sd["st2"], non_blocking=True)
+        res_h[K * D + 2:].copy_(sd["st1"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller reads loss / dmu on the host
+        return float(res_h[0])
+
+    for i in range(3):
+        e2e_step(i)
+    e2e_steps = max(5, min(args.steps, 50))
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for i in range(e2e_steps):
+        loss_h = e2e_step(i)
+    ev1.record()
+    barrier()
+    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3) / e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": int(zd.numel() * 4 + mud.numel() * 4), "d2h_bytes_per_step": int(res_h.numel() * 8),
+           "ms_per_step": e2e_ms, "api": "ops.dec_assign/dec_target/dec_kl_grad on a pinned host latent set; "
+                                         "loss, dmu, f, label-change count read back", "loss": loss_h}
+
+    extra = {}
+    if world == 1 and not args.no_extra:
+        extra = extra_benchmarks(torch, ops, synth, dev, hbm_peak)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = time_reference(3, 1, budget_s=25.0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_points_per_gpu": N_PER_GPU, "n_points_total": n_total, "d": D,
+                       "K": K, "alpha": ALPHA, "gamma": GAMMA, "round_decimals": 5,
+                       "parallelism": f"latent points sharded over {world} GPU(s); packed f64 stat all-reduce x2/step"
+                                      if world > 1 else "single GPU",
+                       "launch": "CUDA graph replay per step" if use_graphs else "eager launches",
+                       "l2": f"inputs/outputs rotate over {N_SETS} sets ({N_SETS * 140} MB) > 126 MB L2",
+                       "timing": "CUDA events around the K steps, max over ranks; per-kernel durations from "
+                                 "CUDA events in a second pass with the launch queue pre-loaded"},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": 3 * args.steps, "roofline": roofline,
+            "cpu_baseline": cpu, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_benchmarks(torch, ops, synth, dev, hbm_peak):
+    """Secondary figures (not the headline): GMM EM iteration and the fused d=32 DEC pass."""
+    out = {}
+
+    def timeit(fn, reps, flush=None):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(reps):
+            if flush is not None:
+                flush.zero_()
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    try:
+        # GMM EM iteration, BASELINE configs[2] shape on one GPU: N=10M d=9 K=16
+        n, d, k = 10_000_000, 9, 16
+        z, _ = synth.latent_points(n, d, k, rank=77, device=dev)
+        w0, mu0, cov0 = synth.gmm_initial_state(d, k, dev)
+        params, pchol, ctrl = ops.gmm_pack_params(w0, mu0, cov0)
+        means, weights, cov = mu0.clone(), w0.clone(), cov0.clone()
+        stats = torch.empty(ops.gmm_stat_doubles(k, d), dtype=torch.float64, device=dev)
+
+        def em():
+            ops.gmm_em_step(z, k, params, stats=stats, ctrl=ctrl)
+            ops.gmm_finalize(stats, n, means, weights, cov, pchol, params, ctrl, tol=0.0)
+        for _ in range(5):
+            em()
+        ms = timeit(em, 10)
+        flops = 2.0 * k * (d * d + 4 * d)
+        out["gmm_em_iteration"] = {"workload": "fused E+M pass + device finalize, N=10M d=9 K=16 (configs[2] on 1 GPU)",
+                                   "points_per_s": n / (ms * 1e-3), "ms": ms,
+                                   "hbm_gbs": 4 * d * n / (ms * 1e-3) / 1e9, "hbm_frac": 4 * d * n / (ms * 1e-3) / 1e9 / hbm_peak,
+                                   "fp32_tflops_algorithmic": flops * n / (ms * 1e-3) / 1e12,
+                                   "bound": "fp32 FMA issue (SURVEY.md 8d), not HBM"}
+        del z
+        # fused latent-buffer DEC pass at the configs[3] per-GPU shard: N=12.5M d=32 K=16
+        n, d, k = 12_500_000, 32, 16
+        z, mu = synth.latent_points(n, d, k, rank=78, device=dev)
+        st1 = torch.empty(k + 1, dtype=torch.float64, device=dev)
+        st2 = torch.empty(k * d + 2, dtype=torch.float64, device=dev)
+
+        def fused():
+            ops.dec_assign(z, mu, 1.0, 0, want_q=False, want_labels=False, out_stats=st1)
+            ops.dec_kl_grad(z, mu, 1.0, f=st1, scale=1e-3 / n, want_dz=False, out_stats=st2)
+        ms = timeit(fused, 10)
+        out["dec_fused_d32"] = {"workload": "fused latent-buffer DEC step (assign + KL grads, centroid-only), "
+                                            "N=12.5M d=32 K=16 (configs[3] shard of one GPU)",
+                                "points_per_s": n / (ms * 1e-3), "ms": ms, "algorithmic_bytes_per_point": 8 * d,
+                                "hbm_gbs": 8 * d * n / (ms * 1e-3) / 1e9, "hbm_frac": 8 * d * n / (ms * 1e-3) / 1e9 / hbm_peak}
+        del z
+        n, d, k = 100_000_000 // 8, 9, 8
+        z, mu = synth.latent_points(n, d, k, rank=79, device=dev)
+        st1 = torch.empty(k + 1, dtype=torch.float64, device=dev)
+        st2 = torch.empty(k * d + 2, dtype=torch.float64, device=dev)
+        ms = timeit(fused, 10)
+        out["dec_fused_d9"] = {"workload": "fused latent-buffer DEC step (assign + KL grads, centroid-only), N=12.5M d=9 K=8",
+                               "points_per_s": n / (ms * 1e-3), "ms": ms, "algorithmic_bytes_per_point": 8 * d,
+                               "hbm_gbs": 8 * d * n / (ms * 1e-3) / 1e9, "hbm_frac": 8 * d * n / (ms * 1e-3) / 1e9 / hbm_peak}
+    except Exception as exc:  # pragma: no cover
+        out["error"] = repr(exc)
+    del flush
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -551,14 +551,8 @@ dec_grad_tiled_kernel(const DecArgs a) {
 // ---------------------------------------------------------------------------
 template <typename Kern>
 static int launch_persistent(Kern kern, const DecArgs& args, size_t smem, int64_t num_tiles, cudaStream_t stream) {
-    int dev = 0, sms = 0, occ = 0;
-    SCC_CUDA(cudaGetDevice(&dev));
-    SCC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDecThreads, smem));
-    if (occ < 1) return SCC_ERR_UNSUPPORTED;
-    if (occ > kMaxCtasPerSm) occ = kMaxCtasPerSm;
-    int64_t grid = (int64_t)sms * occ;
+    int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), kDecThreads, smem, kMaxCtasPerSm);
+    if (grid < 0) return (int)grid;
     if (grid > kMaxDecGrid) grid = kMaxDecGrid;
     if (grid > num_tiles) grid = num_tiles;
     if (grid < 1) grid = 1;

@@ -354,14 +354,9 @@ static int launch_gmm_full(const GmmArgs& a, cudaStream_t st) {
     constexpr int NT = 32 * KP;
     auto kern = gmm_em_full_kernel<D, KP>;
     const size_t smem = gmm_full_smem<D, KP>();
-    int dev = 0, sms = 0, occ = 0;
-    SCC_CUDA(cudaGetDevice(&dev));
-    SCC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
-    if (occ < 1) return SCC_ERR_UNSUPPORTED;
     const int64_t tiles = (a.n + NT - 1) / NT;
-    int64_t grid = (int64_t)sms * occ;
+    int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), NT, smem, 2);
+    if (grid < 0) return (int)grid;
     if (grid > kMaxGmmGrid) grid = kMaxGmmGrid;
     if (grid > tiles) grid = tiles;
     if (grid < 1) grid = 1;

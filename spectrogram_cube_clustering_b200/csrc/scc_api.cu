@@ -3,6 +3,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+
 #include "scc_launch.h"
 
 namespace scc {
@@ -12,6 +15,40 @@ static thread_local char g_cuda_error[512] = "";
 void set_cuda_error(cudaError_t e, const char* what, int line) {
     snprintf(g_cuda_error, sizeof(g_cuda_error), "%s (%s) at %s [line %d]", cudaGetErrorName(e),
              cudaGetErrorString(e), what, line);
+}
+
+namespace {
+struct GridKey {
+    const void* fn; int dev; size_t smem;
+    bool operator<(const GridKey& o) const {
+        if (fn != o.fn) return fn < o.fn;
+        if (dev != o.dev) return dev < o.dev;
+        return smem < o.smem;
+    }
+};
+std::mutex g_grid_mu;
+std::map<GridKey, int> g_grid_cache;
+}  // namespace
+
+int persistent_grid(const void* kernel, int threads, size_t smem, int max_ctas_per_sm) {
+    int dev = 0;
+    SCC_CUDA(cudaGetDevice(&dev));
+    const GridKey key{kernel, dev, smem};
+    {
+        std::lock_guard<std::mutex> lk(g_grid_mu);
+        auto it = g_grid_cache.find(key);
+        if (it != g_grid_cache.end()) return it->second;
+    }
+    int sms = 0, occ = 0;
+    SCC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SCC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+    if (occ < 1) return SCC_ERR_UNSUPPORTED;
+    if (occ > max_ctas_per_sm) occ = max_ctas_per_sm;
+    const int grid = sms * occ;
+    std::lock_guard<std::mutex> lk(g_grid_mu);
+    g_grid_cache[key] = grid;
+    return grid;
 }
 
 size_t workspace_bytes(int d, int K) {

@@ -20,6 +20,11 @@ constexpr int kMaxGmmGrid = 512;
 constexpr size_t kWorkspaceHeader = 256;   // counters live in front of the partial slots
 
 void set_cuda_error(cudaError_t e, const char* what, int line);
+
+// Cached per-kernel launch configuration: opts the kernel into `smem` bytes of dynamic shared
+// memory once and returns the persistent-grid size (SMs x resident CTAs per SM, capped).
+// Returns a negative scc_status on failure.
+int persistent_grid(const void* kernel, int threads, size_t smem, int max_ctas_per_sm);
 size_t workspace_bytes(int d, int K);
 bool dec_supported(int d, int K);
 bool gmm_supported(int d, int K);

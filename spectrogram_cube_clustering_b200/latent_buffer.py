@@ -1,0 +1,130 @@
+"""Sharded latent-buffer manager (new subsystem named by BASELINE.json north_star).
+
+The reference streams every batch's q and z back to host numpy
+(``Cluster/models.py:84-90``), computes ``target_distribution`` there and
+re-uploads p slice by slice (``models.py:1113-1114``).  Here the N latent points
+live in HBM for the whole refinement: rank g of G owns the contiguous row block
+``[g*N/G, (g+1)*N/G)`` as float32 ``[n_local, d]``; centroids / mixture
+parameters are replicated; every pass is one fused kernel over the shard and the
+only thing that crosses GPUs is the packed float64 statistics vector
+(f_j; loss + dL/dmu; N_k, sum r z, sum r zz^T), one ``all_reduce(SUM)`` per pass
+over NCCL/NVLink.  With ``group=None`` (single process) no collective is issued.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+
+
+def shard_bounds(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous row block of ``rank``: sizes differ by at most one row."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+@dataclass
+class DecStepResult:
+    loss: float | torch.Tensor
+    dmu: torch.Tensor          # float64 [K, d], already summed over all shards
+    f: torch.Tensor            # float64 [K]
+    n_changed: torch.Tensor    # float64 scalar tensor (label changes vs previous pass)
+    dz: torch.Tensor | None
+
+
+class LatentBuffer:
+    """Device-resident shard of the latent set + the passes that run over it."""
+
+    def __init__(self, z: torch.Tensor, n_total: int | None = None, group=None):
+        if z.dim() != 2:
+            raise ValueError("z must be [n_local, d]")
+        self.z = z.contiguous() if z.dtype == torch.float32 else z.float().contiguous()
+        self.n_local, self.d = self.z.shape
+        self.group = group
+        self.world = 1 if group is None else torch.distributed.get_world_size(group)
+        self.rank = 0 if group is None else torch.distributed.get_rank(group)
+        self.n_total = int(n_total) if n_total is not None else self._sum_int(self.n_local)
+        self.labels = None          # int32 [n_local] of the last assign pass
+        self._labels_spare = None
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_host(cls, z_host, device, group=None, pin: bool = True):
+        """Shard a host array [N, d] by rows and upload this rank's block."""
+        zt = torch.as_tensor(z_host)
+        world = 1 if group is None else torch.distributed.get_world_size(group)
+        rank = 0 if group is None else torch.distributed.get_rank(group)
+        lo, hi = shard_bounds(zt.shape[0], rank, world)
+        blk = zt[lo:hi].to(torch.float32).contiguous()
+        if pin and torch.cuda.is_available() and torch.device(device).type == "cuda":
+            blk = blk.pin_memory()
+        return cls(blk.to(device, non_blocking=True), n_total=zt.shape[0], group=group)
+
+    def _sum_int(self, v: int) -> int:
+        if self.group is None:
+            return int(v)
+        t = torch.tensor([v], dtype=torch.int64, device=self.z.device)
+        torch.distributed.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    def _allreduce(self, t: torch.Tensor) -> torch.Tensor:
+        if self.group is not None and self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        return t
+
+    # ------------------------------------------------------------------ DEC passes
+    def dec_assign(self, mu: torch.Tensor, alpha: float = 1.0, round_decimals: int = 0,
+                   want_q: bool = False, track_labels: bool = True):
+        """Pass 1: q (optional), labels, f_j and the label-change count; f and the count are
+        summed over shards.  networks.py:279-288, models.py:92-94,1098-1099,1320."""
+        prev = self.labels if track_labels else None
+        out_labels = None
+        if track_labels:
+            out_labels = self._labels_spare if self._labels_spare is not None else torch.empty(
+                self.n_local, dtype=torch.int32, device=self.z.device)
+        q, labels, stats = ops.dec_assign(self.z, mu, alpha, round_decimals, want_q=want_q,
+                                          want_labels=track_labels, labels_prev=prev, out_labels=out_labels)
+        if track_labels:
+            self._labels_spare, self.labels = self.labels, labels
+        self._allreduce(stats)
+        return q, stats
+
+    def dec_grad(self, mu: torch.Tensor, f_stats: torch.Tensor, alpha: float = 1.0, gamma: float = 1e-3,
+                 round_decimals: int = 0, p: torch.Tensor | None = None, want_dz: bool = False):
+        """Pass 2: loss, dL/dmu (summed over shards) and optionally dL/dz for the encoder.
+        scale = gamma / N_total, i.e. the whole latent set is one batch (models.py:1124-1125)."""
+        stats, dz = ops.dec_kl_grad(self.z, mu, alpha, p=p, f=None if p is not None else f_stats,
+                                    round_decimals=round_decimals, scale=gamma / self.n_total, want_dz=want_dz)
+        self._allreduce(stats)
+        return stats, dz
+
+    def dec_step(self, mu: torch.Tensor, alpha: float = 1.0, gamma: float = 1e-3, round_decimals: int = 0,
+                 want_dz: bool = False) -> DecStepResult:
+        """Fused latent-buffer DEC step: assign -> (allreduce f) -> KL gradients -> (allreduce dmu)."""
+        _, st = self.dec_assign(mu, alpha, round_decimals)
+        stats, dz = self.dec_grad(mu, st, alpha, gamma, round_decimals, want_dz=want_dz)
+        K = mu.shape[0]
+        return DecStepResult(loss=stats[0], dmu=stats[2:].view(K, self.d), f=st[:K], n_changed=st[K], dz=dz)
+
+    def delta_label(self, assign_stats: torch.Tensor) -> float:
+        """models.py:1098-1099 from the fused count (one host sync)."""
+        return float(assign_stats[-1].item()) / self.n_total
+
+    # ------------------------------------------------------------------ GMM passes
+    def gmm_em_pass(self, K: int, params: torch.Tensor, stats: torch.Tensor | None = None, ctrl=None,
+                    mode: int = ops.GMM_SOFT, labels: torch.Tensor | None = None):
+        stats = ops.gmm_em_step(self.z, K, params, stats=stats, ctrl=ctrl, mode=mode, labels=labels)
+        if mode != ops.GMM_ESTEP_ONLY:
+            self._allreduce(stats)
+        return stats
+
+
+def update_interval(m: int, batch_size: int, config_update_interval: int = -1) -> int:
+    """models.py:985-989."""
+    if config_update_interval == -1:
+        return int(math.ceil(m / (batch_size * 2)))
+    return int(math.ceil(m / (batch_size * config_update_interval)))
