@@ -1,0 +1,206 @@
+// dec_api.cu — DEC entry points: argument validation, per-dimension dispatch, and the two
+// dimension-independent kernels (target distribution, column sums).
+#include "dec_kernels.cuh"
+
+namespace scc {
+
+#define SCC_DECL_DIM(D_, X)                                             \
+    int dec_assign_dim##D_(const DecArgs& a, cudaStream_t st);          \
+    int dec_grad_dim##D_(const DecArgs& a, int mode, cudaStream_t st);
+SCC_FOR_EACH_DIM(SCC_DECL_DIM, 0)
+#undef SCC_DECL_DIM
+
+// ---------------------------------------------------------------------------
+// dec_target: p = normalise_rows(q^2 / f)   (models.py:1320-1322)
+// LPR lanes cooperate on one row (K = 4*LPR) so that global accesses are
+// 128-bit and fully coalesced; LPR = 0 is the scalar thread-per-row fallback.
+// ---------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256)
+dec_target_kernel(const float* __restrict__ q, int64_t n, int K, const double* __restrict__ f,
+                  int round5, float* __restrict__ p) {
+    __shared__ float inv_f[SCC_MAX_K];
+    if (threadIdx.x < K) inv_f[threadIdx.x] = (float)(1.0 / f[threadIdx.x]);
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if constexpr (LPR > 0) {
+        const int64_t nvec = n * LPR;
+        const int sub = threadIdx.x % LPR;       // blockDim (256) is a multiple of LPR, so is the grid stride
+        const float i0 = inv_f[4 * sub], i1 = inv_f[4 * sub + 1], i2 = inv_f[4 * sub + 2], i3 = inv_f[4 * sub + 3];
+        const int64_t nvec_pad = (nvec + 31) & ~int64_t(31);
+        for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec_pad; v += stride) {
+            const bool ok = v < nvec;
+            float4 x = ok ? ldg_stream4(reinterpret_cast<const float4*>(q) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 w = make_float4(x.x * x.x * i0, x.y * x.y * i1, x.z * x.z * i2, x.w * x.w * i3);
+            float s = (w.x + w.y) + (w.z + w.w);
+#pragma unroll
+            for (int o = 1; o < LPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float inv = 1.f / s;
+            w.x *= inv; w.y *= inv; w.z *= inv; w.w *= inv;
+            if (round5) { w.x = round_dec5(w.x); w.y = round_dec5(w.y); w.z = round_dec5(w.z); w.w = round_dec5(w.w); }
+            if (ok) reinterpret_cast<float4*>(p)[v] = w;
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            float w[SCC_MAX_K];
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < SCC_MAX_K; ++j) {
+                if (j < K) { const float x = q[i * K + j]; w[j] = x * x * inv_f[j]; s += w[j]; }
+            }
+            const float inv = 1.f / s;
+#pragma unroll
+            for (int j = 0; j < SCC_MAX_K; ++j) {
+                if (j < K) { float v = w[j] * inv; if (round5) v = round_dec5(v); p[i * K + j] = v; }
+            }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// colsum: f_j = sum_i q_ij for a caller-supplied q (models.py:1320)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDecThreads)
+colsum_kernel(const float* __restrict__ q, int64_t n, int K, double* stats, double* partials, unsigned int* counter) {
+    constexpr int KP = SCC_MAX_K;
+    __shared__ double scratch[kDecThreads];
+    __shared__ double cta_stats[KP];
+    float acc[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) acc[j] = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float v[KP];
+        load_krow<KP, false>(q + i * K, K, v);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) acc[j] += v[j];
+    }
+    cta_reduce<KP, kDecThreads>(acc, scratch, cta_stats);
+    grid_publish<kDecThreads>(cta_stats, K, partials, counter, stats, scratch);
+}
+
+int colsum(const float* q, int64_t n, int K, double* f, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!q || !f || n < 0 || K < 1 || K > SCC_MAX_K) return SCC_ERR_INVALID;
+    if ((K % 4 == 0) && (reinterpret_cast<uintptr_t>(q) & 15u)) return SCC_ERR_MISALIGNED;
+    if (!ws || ws_bytes < workspace_bytes(4, K)) return SCC_ERR_WORKSPACE;
+    if (n == 0) { SCC_CUDA(cudaMemsetAsync(f, 0, sizeof(double) * K, st)); return SCC_OK; }
+    int dev = 0, sms = 0;
+    SCC_CUDA(cudaGetDevice(&dev));
+    SCC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t grid = (n + kDecThreads - 1) / kDecThreads;
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    if (grid > kMaxDecGrid) grid = kMaxDecGrid;
+    colsum_kernel<<<(unsigned)grid, kDecThreads, 0, st>>>(
+        q, n, K, f, reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + kWorkspaceHeader),
+        reinterpret_cast<unsigned int*>(ws));
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
+
+
+int dec_target(const float* q, int64_t n, int K, const double* f, int round_decimals, float* p, cudaStream_t st) {
+    if (!q || !f || !p || n < 0 || K < 1 || K > SCC_MAX_K) return SCC_ERR_INVALID;
+    if (round_decimals != 0 && round_decimals != 5) return SCC_ERR_INVALID;
+    if (n == 0) return SCC_OK;
+    int dev = 0, sms = 0;
+    SCC_CUDA(cudaGetDevice(&dev));
+    SCC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const bool vec = (K % 4 == 0) && ((K / 4) == 1 || (K / 4) == 2 || (K / 4) == 4) &&
+                     !((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(p)) & 15u);
+    const int64_t work = vec ? n * (K / 4) : n;
+    int64_t grid = (work + 255) / 256;
+    const int64_t cap = (int64_t)sms * 8;
+    if (grid > cap) grid = cap;
+    const int r5 = round_decimals == 5;
+    if (vec && K == 4) dec_target_kernel<1><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p);
+    else if (vec && K == 8) dec_target_kernel<2><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p);
+    else if (vec && K == 16) dec_target_kernel<4><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p);
+    else dec_target_kernel<0><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
+
+
+bool dec_supported(int d, int K) {
+    if (K < 1 || K > SCC_MAX_K) return false;
+#define SCC_SUP(D_, X) if (d == D_) return true;
+    SCC_FOR_EACH_DIM(SCC_SUP, 0)
+#undef SCC_SUP
+    return false;
+}
+
+static int check_common(const float* z, int64_t n, int d, const float* mu, int K, float alpha, double* stats,
+                        void* ws, size_t ws_bytes) {
+    if ((!z && n > 0) || !mu || !stats || n < 0 || !(alpha > 0.f)) return SCC_ERR_INVALID;
+    if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return SCC_ERR_INVALID;
+    if (n > (int64_t)kDecTile * 2147483647LL) return SCC_ERR_INVALID;
+    if (!dec_supported(d, K)) return SCC_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(z) & 15u) != 0) return SCC_ERR_MISALIGNED;
+    if (!ws || ws_bytes < workspace_bytes(d, K)) return SCC_ERR_WORKSPACE;
+    return SCC_OK;
+}
+
+static void fill_reduction(DecArgs& a, void* ws) {
+    a.counter = reinterpret_cast<unsigned int*>(ws);
+    a.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + kWorkspaceHeader);
+}
+
+int dec_assign(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
+               float* q, int32_t* labels, const int32_t* labels_prev, double* stats,
+               void* ws, size_t ws_bytes, cudaStream_t st) {
+    int rc = check_common(z, n, d, mu, K, alpha, stats, ws, ws_bytes);
+    if (rc != SCC_OK) return rc;
+    if (round_decimals != 0 && round_decimals != 5) return SCC_ERR_INVALID;
+    if (q && (K % 4 == 0) && (reinterpret_cast<uintptr_t>(q) & 15u)) return SCC_ERR_MISALIGNED;
+    if (n == 0) { SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (K + 1), st)); return SCC_OK; }
+    DecArgs a{};
+    a.z = z; a.n = n; a.mu = mu; a.K = K; a.alpha = alpha; a.round5 = round_decimals == 5;
+    a.q = q; a.labels = labels; a.labels_prev = labels_prev; a.stats = stats;
+    fill_reduction(a, ws);
+#define SCC_CASE(D_, X) if (d == D_) return dec_assign_dim##D_(a, st);
+    SCC_FOR_EACH_DIM(SCC_CASE, 0)
+#undef SCC_CASE
+    return SCC_ERR_UNSUPPORTED;
+}
+
+static int dec_grad_dispatch(const DecArgs& a, int d, int mode, cudaStream_t st) {
+#define SCC_CASE(D_, X) if (d == D_) return dec_grad_dim##D_(a, mode, st);
+    SCC_FOR_EACH_DIM(SCC_CASE, 0)
+#undef SCC_CASE
+    return SCC_ERR_UNSUPPORTED;
+}
+
+int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* p,
+                const double* f_cols, int round_decimals, float scale, float* dz, double* stats,
+                void* ws, size_t ws_bytes, cudaStream_t st) {
+    int rc = check_common(z, n, d, mu, K, alpha, stats, ws, ws_bytes);
+    if (rc != SCC_OK) return rc;
+    if (!p && !f_cols) return SCC_ERR_INVALID;
+    if (round_decimals != 0 && round_decimals != 5) return SCC_ERR_INVALID;
+    if (p && (K % 4 == 0) && (reinterpret_cast<uintptr_t>(p) & 15u)) return SCC_ERR_MISALIGNED;
+    if (dz && (reinterpret_cast<uintptr_t>(dz) & 15u)) return SCC_ERR_MISALIGNED;
+    if (n == 0) { SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (K * d + 2), st)); return SCC_OK; }
+    DecArgs a{};
+    a.z = z; a.n = n; a.mu = mu; a.K = K; a.alpha = alpha; a.round5 = round_decimals == 5;
+    a.p = p; a.f_cols = f_cols; a.scale = scale; a.dz = dz; a.stats = stats;
+    fill_reduction(a, ws);
+    return dec_grad_dispatch(a, d, MODE_KL, st);
+}
+
+int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* grad_q,
+                 float* dz, double* stats, void* ws, size_t ws_bytes, cudaStream_t st) {
+    int rc = check_common(z, n, d, mu, K, alpha, stats, ws, ws_bytes);
+    if (rc != SCC_OK) return rc;
+    if (!grad_q) return SCC_ERR_INVALID;
+    if ((K % 4 == 0) && (reinterpret_cast<uintptr_t>(grad_q) & 15u)) return SCC_ERR_MISALIGNED;
+    if (dz && (reinterpret_cast<uintptr_t>(dz) & 15u)) return SCC_ERR_MISALIGNED;
+    if (n == 0) { SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (K * d + 2), st)); return SCC_OK; }
+    DecArgs a{};
+    a.z = z; a.n = n; a.mu = mu; a.K = K; a.alpha = alpha;
+    a.grad_q = grad_q; a.scale = 1.f; a.dz = dz; a.stats = stats;
+    fill_reduction(a, ws);
+    return dec_grad_dispatch(a, d, MODE_GENERIC, st);
+}
+
+}  // namespace scc

@@ -1,0 +1,604 @@
+// dec_kernels.cuh — DEC clustering-layer kernel templates for sm_100a (CUDA cores, HBM-bound).
+//
+//   dec_assign_kernel   z -> q, labels, f_j = sum_i q_ij, label-change count   (one read of z)
+//                       replaces Cluster/networks.py:279-288 + models.py:92,94,1098-1099,1320
+//   dec_grad_reg_kernel / dec_grad_tiled_kernel
+//                       z (+p | +f | +dL/dq) -> loss, dz, dmu                   (models.py:1124-1127 + autograd)
+//       REG   variant: dmu accumulated in per-thread registers          (KP*D <= 160)
+//       TILED variant: warp-level 4x4 register-blocked W^T Z over the staged tile (D % 4 == 0)
+//
+// One thread owns one latent point: its row sits in registers, centroids are broadcast from
+// shared memory, q / coefficients never leave registers.  Template parameters:
+//   D      latent dimension          KP     compile-time bound on the cluster count (4, 8, 16)
+//   EXACT  K == KP (no per-cluster guards)      ALPHA1  alpha == 1 (no pow)
+// Instantiated per dimension by dec_inst.cu (one translation unit per D, built in parallel).
+#pragma once
+
+#include "scc_common.cuh"
+#include "scc_launch.h"
+
+namespace scc {
+
+constexpr int kDecThreads = 256;
+constexpr int kDecTile = 256;
+
+template <int D>
+__host__ __device__ constexpr int dec_stages() { return RowLayout<D>::kDense ? 4 : 2; }
+
+// ---------------------------------------------------------------------------
+// q_i, u_i and the hard label of one point.  networks.py:279-288, models.py:92.
+// Distances use the exact difference form (z_c - mu_jc)^2: no cancellation.
+// ---------------------------------------------------------------------------
+template <int D, int KP, bool EXACT, bool ALPHA1>
+__device__ __forceinline__ void soft_assign_row(const float (&zr)[D], const float* __restrict__ mu_s, int K,
+                                                float inv_alpha, float expo, float (&u)[KP], float (&q)[KP],
+                                                int& label) {
+    float tsum = 0.f, best = 3.4e38f;
+    label = 0;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+        u[j] = 0.f; q[j] = 0.f;
+        if (EXACT || j < K) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const float df = zr[c] - mu_s[j * D + c];
+                acc = fmaf(df, df, acc);
+            }
+            if (acc < best) { best = acc; label = j; }          // argmax q == argmin distance, first wins
+            const float uu = __fdividef(1.f, ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f));
+            const float t = ALPHA1 ? uu : __powf(uu, expo);
+            u[j] = uu; q[j] = t; tsum += t;
+        }
+    }
+    const float inv = __fdividef(1.f, tsum);
+#pragma unroll
+    for (int j = 0; j < KP; ++j) q[j] *= inv;
+}
+
+template <int KP, bool EXACT>
+__device__ __forceinline__ void store_krow(float* __restrict__ dst, int K, const float (&v)[KP]) {
+    if (EXACT || (K & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < KP; j += 4)
+            if (EXACT || j < K) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < KP; ++j)
+            if (j < K) dst[j] = v[j];
+    }
+}
+template <int KP, bool EXACT>
+__device__ __forceinline__ void load_krow(const float* __restrict__ src, int K, float (&v)[KP]) {
+    if (EXACT || (K & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < KP; j += 4) {
+            if (EXACT || j < K) {
+                const float4 x = ldg_stream4(reinterpret_cast<const float4*>(src + j));
+                v[j] = x.x; v[j + 1] = x.y; v[j + 2] = x.z; v[j + 3] = x.w;
+            } else { v[j] = 0.f; v[j + 1] = 0.f; v[j + 2] = 0.f; v[j + 3] = 0.f; }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) v[j] = (j < K) ? ldg_stream(src + j) : 0.f;
+    }
+}
+
+// Reduce NV per-thread floats across the CTA into cta_stats[0..NV) (float64).
+// scratch: [num_warps][NV] doubles.  Deterministic (fixed warp order).
+template <int NV, int NT>
+__device__ __forceinline__ void cta_reduce(const float (&v)[NV], double* scratch, double* cta_stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < NV; ++s) {
+        const float w = warp_sum(v[s]);
+        if (lane == 0) scratch[warp * NV + s] = (double)w;
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < NV; s += NT) {
+        double acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) acc += scratch[w * NV + s];
+        cta_stats[s] = acc;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// dec_assign
+// ---------------------------------------------------------------------------
+template <int D, int KP, bool EXACT, bool ALPHA1>
+__global__ void __launch_bounds__(kDecThreads)
+dec_assign_kernel(const DecArgs a) {
+    constexpr int S = dec_stages<D>();
+    constexpr int NW = kDecThreads / 32;
+    using Ring = ZRing<D, kDecTile, S, kDecThreads>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring_buf = reinterpret_cast<float*>(smem_raw);
+    float* mu_s = ring_buf + S * Ring::kTileFloats;                           // [KP*D]
+    double* scratch = reinterpret_cast<double*>(mu_s + ((KP * D + 3) & ~3));  // [max(NW*(KP+1), NT)]
+    double* cta_stats = scratch + (NW * (KP + 1) > kDecThreads ? NW * (KP + 1) : kDecThreads);   // [KP+1]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + (KP + 1));
+
+    const int K = EXACT ? KP : a.K;
+    for (int i = threadIdx.x; i < KP * D; i += kDecThreads) mu_s[i] = (i < K * D) ? a.mu[i] : 0.f;
+
+    Ring ring;
+    ring.init(ring_buf, bars, a.z, a.n);
+    __syncthreads();
+    const int G = gridDim.x;
+#pragma unroll
+    for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
+    __syncthreads();
+
+    const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
+    const bool round5 = a.round5 != 0;
+    float facc[KP + 1];
+#pragma unroll
+    for (int j = 0; j <= KP; ++j) facc[j] = 0.f;
+
+    int stage = 0;
+    uint32_t use = 0;
+    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
+        ring.wait(stage, tile, use);
+        const int np = ring.points(tile);
+        const bool active = (int)threadIdx.x < np;
+        float zr[D];
+        if (active) load_row<D>(ring.stage_ptr(stage), threadIdx.x, zr);
+        __syncthreads();
+        ring.issue(stage, tile + S * G);
+        if (active) {
+            const size_t i = (size_t)tile * kDecTile + threadIdx.x;
+            float u[KP], q[KP];
+            int label;
+            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label);
+            if (round5) {
+#pragma unroll
+                for (int j = 0; j < KP; ++j) q[j] = round_dec5(q[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < KP; ++j) facc[j] += q[j];
+            if (a.q) store_krow<KP, EXACT>(a.q + i * K, K, q);
+            if (a.labels) a.labels[i] = label;
+            if (a.labels_prev) facc[KP] += (a.labels_prev[i] != label) ? 1.f : 0.f;
+        }
+        if (++stage == S) { stage = 0; ++use; }
+    }
+    cta_reduce<KP + 1, kDecThreads>(facc, scratch, cta_stats);
+    if (!EXACT) {                       // stats layout is [K+1]: compact the KP-padded vector
+        if (threadIdx.x == 0 && K < KP) cta_stats[K] = cta_stats[KP];
+        __syncthreads();
+    }
+    grid_publish<kDecThreads>(cta_stats, K + 1, a.partials, a.counter, a.stats, scratch);
+}
+
+// ---------------------------------------------------------------------------
+// Per-point gradient coefficients c_ij with dz_i = sum_j c_ij (z_i - mu_j),
+// dmu_j = -sum_i c_ij (z_i - mu_j).
+//   MODE_KL      : c_ij = scale (alpha+1)/alpha (p_ij - q_ij s_i) u_ij   (+ loss)
+//   MODE_GENERIC : c_ij = -(alpha+1)/alpha q_ij (G_ij - sum_j G_ij q_ij) u_ij
+// ---------------------------------------------------------------------------
+template <int KP, bool EXACT, int MODE>
+__device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, int K, const float* __restrict__ inv_f,
+                                                  const float (&u)[KP], const float (&q)[KP], float cscale,
+                                                  float (&coef)[KP], float& loss, float& ssum) {
+    if constexpr (MODE == MODE_KL) {
+        float p[KP];
+        if (a.p) {
+            load_krow<KP, EXACT>(a.p + i * K, K, p);
+        } else {                                   // rebuild p from the column sums (fused mode)
+            float wsum = 0.f;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+                const float qq = a.round5 ? round_dec5(q[j]) : q[j];
+                p[j] = (EXACT || j < K) ? qq * qq * inv_f[j] : 0.f;
+                wsum += p[j];
+            }
+            const float inv = 1.f / wsum;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+                p[j] *= inv;
+                if (a.round5) p[j] = round_dec5(p[j]);
+            }
+        }
+        float s = 0.f, l = 0.f;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            if (EXACT || j < K) {
+                s += p[j];
+                // xlogy(p,p) - p log q ; 0 when p == 0 (torch KLDivLoss); NaN targets still propagate
+                const float term = p[j] * __log2f(__fdividef(p[j], q[j]));
+                l += (p[j] == 0.f) ? 0.f : term;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KP; ++j) coef[j] = (EXACT || j < K) ? (p[j] - q[j] * s) * u[j] * cscale : 0.f;
+        loss = fmaf(l, 0.693147180559945f, loss); ssum += s;
+    } else {
+        float g[KP];
+        load_krow<KP, EXACT>(a.grad_q + i * K, K, g);
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) dot = fmaf(g[j], q[j], dot);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) coef[j] = (EXACT || j < K) ? -cscale * q[j] * (g[j] - dot) * u[j] : 0.f;
+    }
+}
+
+// dz_c = (sum_j c_j) zc_c - sum_j c_j mc_jc  with zc = z - c0, mc = mu - c0 (algebraic form of
+// sum_j c_j (z_c - mu_jc): K*D FMAs instead of K*D (FADD + FMA)).
+template <int D, int KP, bool EXACT>
+__device__ __forceinline__ void dz_from_coefficients(const float (&zc)[D], const float (&coef)[KP], float csum,
+                                                     const float* __restrict__ mc_s, int K, float (&dzr)[D]) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) dzr[c] = csum * zc[c];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+        if (EXACT || j < K) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) dzr[c] = fmaf(-coef[j], mc_s[j * D + c], dzr[c]);
+        }
+    }
+}
+
+// Coalesced copy of a staged [np, D] tile (row stride LD) to global rows.
+template <int D, int NT>
+__device__ __forceinline__ void copy_tile_out(const float* __restrict__ tile, float* __restrict__ dst, int np) {
+    using L = RowLayout<D>;
+    if constexpr (L::kVec4) {
+        const int nvec = np * (D / 4);
+        for (int v = threadIdx.x; v < nvec; v += NT) {
+            const int row = v / (D / 4), c4 = v - row * (D / 4);
+            reinterpret_cast<float4*>(dst)[v] = *reinterpret_cast<const float4*>(tile + row * L::LD + 4 * c4);
+        }
+    } else if constexpr (L::kDense) {
+        const int nf = np * D;                       // dense tile: flat copy, 128-bit where aligned
+        const int nvec = nf / 4;
+        for (int v = threadIdx.x; v < nvec; v += NT)
+            reinterpret_cast<float4*>(dst)[v] = reinterpret_cast<const float4*>(tile)[v];
+        for (int f = nvec * 4 + threadIdx.x; f < nf; f += NT) dst[f] = tile[f];
+    } else {
+        const int nf = np * D;
+        for (int f = threadIdx.x; f < nf; f += NT) {
+            const int row = f / D, c = f - row * D;
+            dst[f] = tile[row * L::LD + c];
+        }
+    }
+}
+
+// Shared prologue of the gradient kernels: centroids, centred centroids, c0, 1/f.
+template <int D, int KP>
+__device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, float* mu_s, float* mc_s, float* c0_s,
+                                                    float* inv_f) {
+    if (threadIdx.x < D) {
+        float m = 0.f;
+        for (int j = 0; j < K; ++j) m += a.mu[j * D + threadIdx.x];
+        c0_s[threadIdx.x] = m / (float)K;
+    }
+    if (threadIdx.x < KP)
+        inv_f[threadIdx.x] = (a.f_cols && (int)threadIdx.x < K) ? (float)(1.0 / a.f_cols[threadIdx.x]) : 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < KP * D; i += kDecThreads) {
+        const float m = (i < K * D) ? a.mu[i] : 0.f;
+        mu_s[i] = m;
+        mc_s[i] = (i < K * D) ? m - c0_s[i % D] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// dec_grad, REG variant.  Per-thread accumulators: loss, sum s, W_j = sum_i c_ij,
+// B_jc = sum_i c_ij (z_ic - c0_c);  dmu_jc = -(B_jc - W_j (mu_jc - c0_c)).
+// stats out: [loss, sum_i s_i, dmu[K*D]]
+// ---------------------------------------------------------------------------
+template <int D, int KP, bool EXACT, bool ALPHA1, int MODE>
+__global__ void __launch_bounds__(kDecThreads, (2 + KP + KP * D) <= 100 ? 2 : 1)
+dec_grad_reg_kernel(const DecArgs a) {
+    constexpr int S = dec_stages<D>();
+    constexpr int NW = kDecThreads / 32;
+    using Ring = ZRing<D, kDecTile, S, kDecThreads>;
+    constexpr int NV = 2 + KP + KP * D;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring_buf = reinterpret_cast<float*>(smem_raw);
+    float* out_tile = ring_buf + S * Ring::kTileFloats;                      // [TILE*LD]
+    float* mu_s = out_tile + Ring::kTileFloats;                              // [KP*D]
+    float* mc_s = mu_s + ((KP * D + 3) & ~3);                                // [KP*D]
+    float* c0_s = mc_s + ((KP * D + 3) & ~3);                                // [D]
+    float* inv_f = c0_s + ((D + 3) & ~3);                                    // [KP]
+    constexpr int SCR = NW * NV > kDecThreads ? NW * NV : kDecThreads;
+    double* scratch = reinterpret_cast<double*>(inv_f + ((KP + 3) & ~3));    // [max(NW*NV, NT)]
+    double* cta_stats = scratch + SCR;                                       // [NV]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NV);
+
+    const int K = EXACT ? KP : a.K;
+    load_grad_constants<D, KP>(a, K, mu_s, mc_s, c0_s, inv_f);
+
+    Ring ring;
+    ring.init(ring_buf, bars, a.z, a.n);
+    __syncthreads();
+    const int G = gridDim.x;
+#pragma unroll
+    for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
+    __syncthreads();
+
+    const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
+    const float cscale = (MODE == MODE_KL ? a.scale : 1.f) * (a.alpha + 1.f) / a.alpha;
+    const bool want_dz = a.dz != nullptr;
+    float acc[NV];
+#pragma unroll
+    for (int s = 0; s < NV; ++s) acc[s] = 0.f;
+
+    int stage = 0;
+    uint32_t use = 0;
+    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
+        ring.wait(stage, tile, use);
+        const int np = ring.points(tile);
+        const bool active = (int)threadIdx.x < np;
+        float zr[D];
+        if (active) load_row<D>(ring.stage_ptr(stage), threadIdx.x, zr);
+        __syncthreads();                 // stage free; previous out_tile fully copied out
+        ring.issue(stage, tile + S * G);
+        if (active) {
+            const size_t i = (size_t)tile * kDecTile + threadIdx.x;
+            float u[KP], q[KP], coef[KP];
+            int label;
+            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label);
+            grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, coef, acc[0], acc[1]);
+            float csum = 0.f;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) { acc[2 + j] += coef[j]; csum += coef[j]; }
+#pragma unroll
+            for (int c = 0; c < D; ++c) zr[c] -= c0_s[c];
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+                if (EXACT || j < K) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c)
+                        acc[2 + KP + j * D + c] = fmaf(coef[j], zr[c], acc[2 + KP + j * D + c]);
+                }
+            }
+            if (want_dz) {
+                float dzr[D];
+                dz_from_coefficients<D, KP, EXACT>(zr, coef, csum, mc_s, K, dzr);
+                store_row<D>(out_tile, threadIdx.x, dzr);
+            }
+        }
+        if (want_dz) {
+            __syncthreads();
+            copy_tile_out<D, kDecThreads>(out_tile, a.dz + (size_t)tile * (kDecTile * D), np);
+        }
+        if (++stage == S) { stage = 0; ++use; }
+    }
+    acc[0] *= a.scale;                   // loss = scale * sum p log(p/q)
+    __syncthreads();
+    cta_reduce<NV, kDecThreads>(acc, scratch, cta_stats);
+    // dmu_jc = -(B_jc - W_j (mu_jc - c0_c)), compacted to [loss, sum s, dmu[K*D]]
+    double dmu = 0.0;
+    const int o = threadIdx.x;
+    if (o < K * D) dmu = -(cta_stats[2 + KP + o] - cta_stats[2 + o / D] * (double)mc_s[o]);
+    __syncthreads();
+    if (o < K * D) cta_stats[2 + o] = dmu;
+    __syncthreads();
+    grid_publish<kDecThreads>(cta_stats, K * D + 2, a.partials, a.counter, a.stats, scratch);
+}
+
+// ---------------------------------------------------------------------------
+// dec_grad, TILED variant (D % 4 == 0, KP % 4 == 0): phase 1 = thread per point
+// (coefficients + dz), phase 2 = each warp accumulates W^T (Z - c0) over its
+// share of the tile with 4x4 register blocks (one LDS.128 of W and one of Z per
+// 16 FMAs).  c0 = mean centroid, removed to keep the sums well conditioned:
+//   dmu_jc = -( A_jc - Wsum_j (mu_jc - c0_c) ),  A = sum_i c_ij (z_ic - c0_c).
+// ---------------------------------------------------------------------------
+template <int D, int KP, bool EXACT, bool ALPHA1, int MODE>
+__global__ void __launch_bounds__(kDecThreads)
+dec_grad_tiled_kernel(const DecArgs a) {
+    static_assert(D % 4 == 0 && KP % 4 == 0, "tiled variant needs 4-aligned shapes");
+    constexpr int S = 2;
+    using Ring = ZRing<D, kDecTile, S, kDecThreads>;
+    using L = RowLayout<D>;
+    constexpr int NB = (KP / 4) * (D / 4);            // 4x4 output blocks
+    constexpr int G2 = (32 / NB) > 0 ? (32 / NB) : 1; // point groups per warp
+    constexpr int NW = kDecThreads / 32;
+    constexpr int NSM = KP + 2;                       // loss, sum s, Wsum_j
+    constexpr int NS = KP * D + 2;
+    static_assert(NB <= 32, "too many output blocks for one warp");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring_buf = reinterpret_cast<float*>(smem_raw);
+    float* out_tile = ring_buf + S * Ring::kTileFloats;      // [TILE*LD] dz staging
+    float* w_tile = out_tile + Ring::kTileFloats;            // [TILE*KP] coefficients
+    float* mu_s = w_tile + kDecTile * KP;                    // [KP*D]
+    float* mc_s = mu_s + KP * D;                             // [KP*D]
+    float* c0_s = mc_s + KP * D;                             // [D]
+    float* inv_f = c0_s + D;                                 // [KP]
+    double* scratch = reinterpret_cast<double*>(inv_f + KP); // [max(NW*NSM, NT)]
+    double* small_s = scratch + (NW * NSM > kDecThreads ? NW * NSM : kDecThreads);   // [NSM]
+    double* cta_stats = small_s + NSM;                       // [NS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NS);
+
+    const int K = EXACT ? KP : a.K;
+    load_grad_constants<D, KP>(a, K, mu_s, mc_s, c0_s, inv_f);
+
+    Ring ring;
+    ring.init(ring_buf, bars, a.z, a.n);
+    __syncthreads();
+    const int G = gridDim.x;
+#pragma unroll
+    for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
+    __syncthreads();
+
+    const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
+    const float cscale = (MODE == MODE_KL ? a.scale : 1.f) * (a.alpha + 1.f) / a.alpha;
+    const bool want_dz = a.dz != nullptr;
+    float small[NSM];
+#pragma unroll
+    for (int s = 0; s < NSM; ++s) small[s] = 0.f;
+    float blk[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) blk[s] = 0.f;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / NB, lb = lane - grp * NB;  // lanes >= G2*NB idle in phase 2
+    const int jb = lb / (D / 4), cb = lb - jb * (D / 4);
+    const bool p2_active = grp < G2;
+
+    int stage = 0;
+    uint32_t use = 0;
+    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
+        ring.wait(stage, tile, use);
+        const int np = ring.points(tile);
+        const bool active = (int)threadIdx.x < np;
+        float* ztile = ring.stage_ptr(stage);
+        float coef[KP];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) coef[j] = 0.f;
+        if (active) {
+            float zr[D];
+            load_row<D>(ztile, threadIdx.x, zr);
+            const size_t i = (size_t)tile * kDecTile + threadIdx.x;
+            float u[KP], q[KP];
+            int label;
+            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label);
+            grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, coef, small[0], small[1]);
+            float csum = 0.f;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) { small[2 + j] += coef[j]; csum += coef[j]; }
+#pragma unroll
+            for (int c = 0; c < D; ++c) zr[c] -= c0_s[c];
+            store_row<D>(ztile, threadIdx.x, zr);     // own row, centred, for phase 2
+            if (want_dz) {
+                float dzr[D];
+                dz_from_coefficients<D, KP, EXACT>(zr, coef, csum, mc_s, K, dzr);
+                store_row<D>(out_tile, threadIdx.x, dzr);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KP; j += 4)
+            *reinterpret_cast<float4*>(w_tile + threadIdx.x * KP + j) =
+                make_float4(coef[j], coef[j + 1], coef[j + 2], coef[j + 3]);
+        __syncthreads();
+        if (want_dz) copy_tile_out<D, kDecThreads>(out_tile, a.dz + (size_t)tile * (kDecTile * D), np);
+        if (p2_active) {
+            for (int r = warp * G2 + grp; r < np; r += NW * G2) {
+                const float4 w = *reinterpret_cast<const float4*>(w_tile + r * KP + 4 * jb);
+                const float4 x = *reinterpret_cast<const float4*>(ztile + r * L::LD + 4 * cb);
+                blk[0] = fmaf(w.x, x.x, blk[0]);  blk[1] = fmaf(w.x, x.y, blk[1]);
+                blk[2] = fmaf(w.x, x.z, blk[2]);  blk[3] = fmaf(w.x, x.w, blk[3]);
+                blk[4] = fmaf(w.y, x.x, blk[4]);  blk[5] = fmaf(w.y, x.y, blk[5]);
+                blk[6] = fmaf(w.y, x.z, blk[6]);  blk[7] = fmaf(w.y, x.w, blk[7]);
+                blk[8] = fmaf(w.z, x.x, blk[8]);  blk[9] = fmaf(w.z, x.y, blk[9]);
+                blk[10] = fmaf(w.z, x.z, blk[10]); blk[11] = fmaf(w.z, x.w, blk[11]);
+                blk[12] = fmaf(w.w, x.x, blk[12]); blk[13] = fmaf(w.w, x.y, blk[13]);
+                blk[14] = fmaf(w.w, x.z, blk[14]); blk[15] = fmaf(w.w, x.w, blk[15]);
+            }
+        }
+        __syncthreads();                 // phase 2 done: stage, w_tile and out_tile reusable
+        ring.issue(stage, tile + S * G);
+        if (++stage == S) { stage = 0; ++use; }
+    }
+    // ---- CTA reduction ----
+    small[0] *= a.scale;
+    cta_reduce<NSM, kDecThreads>(small, scratch, small_s);
+    // per-(warp, group) 4x4 partials -> shared (the ring buffer is free now), fixed-order sum
+    double* part = reinterpret_cast<double*>(ring_buf);                      // [NW*G2][KP*D]
+    if (p2_active) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                part[(size_t)(warp * G2 + grp) * (KP * D) + (4 * jb + r) * D + 4 * cb + c] = (double)blk[4 * r + c];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < K * D; o += kDecThreads) {
+        double accd = 0.0;
+#pragma unroll
+        for (int g = 0; g < NW * G2; ++g) accd += part[(size_t)g * (KP * D) + o];
+        cta_stats[2 + o] = -(accd - small_s[2 + o / D] * (double)mc_s[o]);
+    }
+    if (threadIdx.x == 0) { cta_stats[0] = small_s[0]; cta_stats[1] = small_s[1]; }
+    __syncthreads();
+    grid_publish<kDecThreads>(cta_stats, K * D + 2, a.partials, a.counter, a.stats, scratch);
+}
+
+// ---------------------------------------------------------------------------
+// Shared-memory footprints and launchers (per instantiation)
+// ---------------------------------------------------------------------------
+template <int D, int KP>
+constexpr size_t assign_smem() {
+    constexpr int S = dec_stages<D>();
+    constexpr int NW = kDecThreads / 32;
+    constexpr int scr = NW * (KP + 1) > kDecThreads ? NW * (KP + 1) : kDecThreads;
+    return sizeof(float) * (S * kDecTile * RowLayout<D>::LD + ((KP * D + 3) & ~3)) +
+           sizeof(double) * (scr + (KP + 1)) + sizeof(uint64_t) * S;
+}
+template <int D, int KP>
+constexpr size_t grad_reg_smem() {
+    constexpr int S = dec_stages<D>();
+    constexpr int NV = 2 + KP + KP * D;
+    constexpr int NW = kDecThreads / 32;
+    constexpr int SCR = NW * NV > kDecThreads ? NW * NV : kDecThreads;
+    return sizeof(float) * ((S + 1) * kDecTile * RowLayout<D>::LD + 2 * ((KP * D + 3) & ~3) + ((D + 3) & ~3) +
+                            ((KP + 3) & ~3)) +
+           sizeof(double) * (SCR + NV) + sizeof(uint64_t) * S;
+}
+template <int D, int KP>
+constexpr size_t grad_tiled_smem() {
+    constexpr int S = 2;
+    constexpr int NB = (KP / 4) * (D / 4);
+    constexpr int G2 = (32 / NB) > 0 ? (32 / NB) : 1;
+    constexpr int NW = kDecThreads / 32;
+    constexpr int NSM = KP + 2;
+    constexpr int scr = NW * NSM > kDecThreads ? NW * NSM : kDecThreads;
+    size_t bytes = sizeof(float) * ((S + 1) * kDecTile * RowLayout<D>::LD + kDecTile * KP + 2 * KP * D + D + KP) +
+                   sizeof(double) * (scr + NSM + KP * D + 2) + sizeof(uint64_t) * S;
+    // the ring buffer is reused for the [NW*G2][KP*D] float64 partials at the end
+    const size_t part = sizeof(double) * NW * G2 * KP * D;
+    const size_t ring = sizeof(float) * S * kDecTile * RowLayout<D>::LD;
+    if (part > ring) bytes += part - ring;
+    return bytes;
+}
+
+template <typename Kern>
+static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t stream) {
+    const int64_t num_tiles = (args.n + kDecTile - 1) / kDecTile;
+    int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), kDecThreads, smem, kMaxCtasPerSm);
+    if (grid < 0) return (int)grid;
+    if (grid > kMaxDecGrid) grid = kMaxDecGrid;
+    if (grid > num_tiles) grid = num_tiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kDecThreads, smem, stream>>>(args);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
+
+template <int D, int KP>
+struct DecOps {
+    static int assign(const DecArgs& a, cudaStream_t st) {
+        const bool exact = a.K == KP, a1 = a.alpha == 1.0f;
+        constexpr size_t smem = assign_smem<D, KP>();
+        if (exact && a1) return launch_dec(dec_assign_kernel<D, KP, true, true>, a, smem, st);
+        if (exact) return launch_dec(dec_assign_kernel<D, KP, true, false>, a, smem, st);
+        if (a1) return launch_dec(dec_assign_kernel<D, KP, false, true>, a, smem, st);
+        return launch_dec(dec_assign_kernel<D, KP, false, false>, a, smem, st);
+    }
+    template <int MODE, bool EXACT, bool A1>
+    static int grad_inst(const DecArgs& a, cudaStream_t st) {
+        constexpr bool kTiled = (KP * D > 160);
+        if constexpr (kTiled) {
+            if constexpr (D % 4 == 0 && KP % 4 == 0)
+                return launch_dec(dec_grad_tiled_kernel<D, KP, EXACT, A1, MODE>, a, grad_tiled_smem<D, KP>(), st);
+            else
+                return SCC_ERR_UNSUPPORTED;
+        } else {
+            return launch_dec(dec_grad_reg_kernel<D, KP, EXACT, A1, MODE>, a, grad_reg_smem<D, KP>(), st);
+        }
+    }
+    template <int MODE>
+    static int grad(const DecArgs& a, cudaStream_t st) {
+        const bool exact = a.K == KP, a1 = a.alpha == 1.0f;
+        if (exact && a1) return grad_inst<MODE, true, true>(a, st);
+        if (exact) return grad_inst<MODE, true, false>(a, st);
+        if (a1) return grad_inst<MODE, false, true>(a, st);
+        return grad_inst<MODE, false, false>(a, st);
+    }
+};
+
+}  // namespace scc

@@ -73,7 +73,8 @@ gmm_em_full_kernel(const GmmArgs a) {
     Ring ring;
     ring.init(ring_buf, bars, a.z, a.n);
     __syncthreads();
-    for (int s = 0; s < S; ++s) ring.issue(s, (int64_t)blockIdx.x + (int64_t)s * gridDim.x);
+    const int G = gridDim.x;
+    for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
     __syncthreads();
 
     // phase-2 state of this warp's component
@@ -98,7 +99,7 @@ gmm_em_full_kernel(const GmmArgs a) {
     };
 
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile < ring.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G, ++it) {
         const int stage = it % S;
         ring.wait(stage, tile, (uint32_t)(it / S));
         const int np = ring.points(tile);
@@ -149,7 +150,7 @@ gmm_em_full_kernel(const GmmArgs a) {
                 lp[k] = r;
             }
             if (active) {
-                const int64_t i = tile * TILE + threadIdx.x;
+                const size_t i = (size_t)tile * TILE + threadIdx.x;
                 if (a.labels) a.labels[i] = label;
                 if (a.resp) {
 #pragma unroll
@@ -180,7 +181,7 @@ gmm_em_full_kernel(const GmmArgs a) {
             if ((it + 1) % FLUSH == 0) flush();
         }
         __syncthreads();
-        ring.issue(stage, tile + (int64_t)S * gridDim.x);
+        ring.issue(stage, tile + S * G);
     }
     if (a.accumulate) flush();
     {
@@ -207,7 +208,8 @@ gmm_em_full_kernel(const GmmArgs a) {
         cta_stats[s] = v;
     }
     __syncthreads();
-    grid_publish(cta_stats, NS, a.partials, a.counter, a.stats);
+    // per-CTA slot; the host-side launcher follows up with reduce_partials_kernel (fixed order)
+    for (int s = threadIdx.x; s < NS; s += NT) a.partials[(size_t)blockIdx.x * NS + s] = cta_stats[s];
 }
 
 // ---------------------------------------------------------------------------
@@ -361,6 +363,9 @@ static int launch_gmm_full(const GmmArgs& a, cudaStream_t st) {
     if (grid > tiles) grid = tiles;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, NT, smem, st>>>(a);
+    SCC_CUDA(cudaGetLastError());
+    const int NS = SCC_GMM_STAT_DOUBLES(a.K, D);
+    reduce_partials_kernel<<<(NS + 255) / 256, 256, 0, st>>>(a.partials, NS, (int)grid, a.stats, a.ctrl);
     SCC_CUDA(cudaGetLastError());
     return SCC_OK;
 }

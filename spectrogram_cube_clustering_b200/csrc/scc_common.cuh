@@ -138,29 +138,27 @@ struct ZRing {
     float* buf;
     uint64_t* bar;
     const float* z;
-    int64_t n;
-    int64_t num_tiles;
+    int num_tiles;      // tiles in the whole buffer (n <= 2^31 * TILE points)
+    int last_points;    // points in the final tile (1..TILE)
 
     __device__ __forceinline__ void init(float* b, uint64_t* br, const float* z_, int64_t n_) {
-        buf = b; bar = br; z = z_; n = n_;
-        num_tiles = (n_ + TILE - 1) / TILE;
+        buf = b; bar = br; z = z_;
+        num_tiles = (int)((n_ + TILE - 1) / TILE);
+        last_points = (int)(n_ - (int64_t)(num_tiles - 1) * TILE);
         if (L::kDense && threadIdx.x == 0) {
 #pragma unroll
             for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
             fence_mbar_init();
         }
     }
-    __device__ __forceinline__ int points(int64_t tile) const {
-        const int64_t rem = n - tile * TILE;
-        return rem >= TILE ? TILE : static_cast<int>(rem);
-    }
+    __device__ __forceinline__ int points(int tile) const { return tile == num_tiles - 1 ? last_points : TILE; }
     __device__ __forceinline__ float* stage_ptr(int stage) const { return buf + stage * kTileFloats; }
 
     // Called by ALL threads at the same program point.
-    __device__ __forceinline__ void issue(int stage, int64_t tile) {
+    __device__ __forceinline__ void issue(int stage, int tile) {
         if (tile >= num_tiles) return;
         float* dst = stage_ptr(stage);
-        const float* src = z + tile * (int64_t)TILE * D;
+        const float* src = z + (size_t)tile * (TILE * D);
         const int np = points(tile);
         if (L::kDense && np == TILE) {
             if (threadIdx.x == 0) {
@@ -183,7 +181,7 @@ struct ZRing {
         }
     }
     // use_index = how many times this stage has been consumed before (i / STAGES).
-    __device__ __forceinline__ void wait(int stage, int64_t tile, uint32_t use_index) {
+    __device__ __forceinline__ void wait(int stage, int tile, uint32_t use_index) {
         if (L::kDense && points(tile) == TILE) mbar_wait(&bar[stage], use_index & 1u);
     }
 };
@@ -203,30 +201,86 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // CTA-level statistics (float64, in shared memory) -> per-CTA slot of `partials`
-// -> the last CTA to arrive sums all slots in CTA order into `out`.
-// Deterministic for a fixed grid.  `counter` must be 0 on entry and is reset.
-__device__ __forceinline__ void grid_publish(const double* cta_stats, int S, double* partials,
-                                             unsigned int* counter, double* out) {
-    __shared__ bool s_last;
+// -> the last CTA to arrive sums all slots into `out` with ALL its threads:
+// thread t owns statistic s = t % S and the CTA rows r, r+R, r+2R, ... (R = NT / S row groups),
+// then the R partial sums are combined in row-group order.  The summation order depends only
+// on (grid, S, NT), so the result is deterministic for a given device.
+// `counter` must be 0 on entry and is reset.  scratch: NT doubles of shared memory.
+// Returns true in the CTA that arrived last (after `out` is complete).
+template <int NT>
+__device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, double* partials,
+                                             unsigned int* counter, double* out, double* scratch) {
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
     double* mine = partials + (size_t)blockIdx.x * S;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) mine[s] = cta_stats[s];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(counter, 1u);
-        s_last = (prev == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last) {
+    if (tid < S || S > NT) {
+        for (int s = tid; s < S; s += NT) mine[s] = cta_stats[s];
         __threadfence();
-        const int G = gridDim.x;
-        for (int s = threadIdx.x; s < S; s += blockDim.x) {
-            double acc = 0.0;
-            for (int b = 0; b < G; ++b) acc += __ldcg(partials + (size_t)b * S + s);
-            out[s] = acc;
-        }
-        if (threadIdx.x == 0) *counter = 0u;
     }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(counter, 1u);
+        s_last = (prev == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    const int G = gridDim.x;
+    if (S <= NT) {
+        const int R = NT / S;
+        const int s = tid % S, r = tid / S;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (r < R) {
+            int b = r;
+            for (; b + 3 * R < G; b += 4 * R) {
+                a0 += __ldcg(partials + (size_t)b * S + s);
+                a1 += __ldcg(partials + (size_t)(b + R) * S + s);
+                a2 += __ldcg(partials + (size_t)(b + 2 * R) * S + s);
+                a3 += __ldcg(partials + (size_t)(b + 3 * R) * S + s);
+            }
+            for (; b < G; b += R) a0 += __ldcg(partials + (size_t)b * S + s);
+        }
+        scratch[tid] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (tid < S) {
+            double t = 0.0;
+            for (int rr = 0; rr < R; ++rr) t += scratch[rr * S + tid];
+            out[tid] = t;
+        }
+    } else {
+        for (int s = tid; s < S; s += NT) {
+            double a0 = 0.0, a1 = 0.0;
+            int b = 0;
+            for (; b + 1 < G; b += 2) {
+                a0 += __ldcg(partials + (size_t)b * S + s);
+                a1 += __ldcg(partials + (size_t)(b + 1) * S + s);
+            }
+            if (b < G) a0 += __ldcg(partials + (size_t)b * S + s);
+            out[s] = a0 + a1;
+        }
+    }
+    if (tid == 0) *counter = 0u;
+    return true;
+}
+
+// Stand-alone fixed-order reduction of per-CTA partial slots, for statistics vectors too long
+// for one CTA to sum quickly (GMM: up to 8977 doubles x hundreds of CTAs).
+static __global__ void __launch_bounds__(256)
+reduce_partials_kernel(const double* __restrict__ partials, int S, int G, double* __restrict__ out,
+                       const double* __restrict__ ctrl) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    if (ctrl && ctrl[5] != 0.0) return;          // frozen fit: the producer kernel did not run
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int b = 0;
+    for (; b + 3 < G; b += 4) {
+        a0 += partials[(size_t)b * S + s];
+        a1 += partials[(size_t)(b + 1) * S + s];
+        a2 += partials[(size_t)(b + 2) * S + s];
+        a3 += partials[(size_t)(b + 3) * S + s];
+    }
+    for (; b < G; ++b) a0 += partials[(size_t)b * S + s];
+    out[s] = (a0 + a1) + (a2 + a3);
 }
 
 __device__ __forceinline__ float round_dec5(float x) {

@@ -19,6 +19,31 @@ constexpr int kMaxDecGrid = 2048;      // persistent DEC grids never exceed this
 constexpr int kMaxGmmGrid = 512;
 constexpr size_t kWorkspaceHeader = 256;   // counters live in front of the partial slots
 
+enum { MODE_KL = 0, MODE_GENERIC = 1 };
+
+struct DecArgs {
+    const float* z;
+    int64_t n;
+    const float* mu;
+    int K;
+    float alpha;
+    int round5;
+    // assign
+    float* q;
+    int32_t* labels;
+    const int32_t* labels_prev;
+    // grad
+    const float* p;
+    const double* f_cols;
+    const float* grad_q;
+    float scale;
+    float* dz;
+    // reduction
+    double* stats;
+    double* partials;
+    unsigned int* counter;
+};
+
 void set_cuda_error(cudaError_t e, const char* what, int line);
 
 // Cached per-kernel launch configuration: opts the kernel into `smem` bytes of dynamic shared
