@@ -141,6 +141,21 @@ int scc_dec_backward(const float* z, int64_t n, int d,
                      const float* grad_q, float* dz, double* stats,
                      void* workspace, size_t workspace_bytes, scc_stream_t stream);
 
+/*
+ * One Lloyd (k-means) step: nearest-centre labels, per-cluster counts, centre
+ * shifts and the inertia — the scan KMeans(n_init=100, max_iter=1000) repeats
+ * inside Cluster/models.py:386-394 (seeding of gmm()) and models.py:565-574.
+ *   stats [K*d + 2 + K] float64 out: inertia = sum_i min_j ||z_i - c_j||^2, 0,
+ *         shift[K*d] = sum_{i in j} (z_i - c_j)  (new centre = c_j + shift_j / count_j),
+ *         count[K]
+ *   labels  [n] int32 out or NULL;  mindist [n] float32 out or NULL (k-means++ sampling)
+ */
+#define SCC_KMEANS_STATS(K, d) ((K) * (d) + 2 + (K))
+int scc_kmeans_step(const float* z, int64_t n, int d,
+                    const float* centers, int K,
+                    int32_t* labels, float* mindist, double* stats,
+                    void* workspace, size_t workspace_bytes, scc_stream_t stream);
+
 /* ------------------------------------------------------------------------- *
  * GMM stage (full covariance)
  * ------------------------------------------------------------------------- */

@@ -203,4 +203,16 @@ int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float
     return dec_grad_dispatch(a, d, MODE_GENERIC, st);
 }
 
+int kmeans_step(const float* z, int64_t n, int d, const float* centers, int K, int32_t* labels, float* mindist,
+                double* stats, void* ws, size_t ws_bytes, cudaStream_t st) {
+    int rc = check_common(z, n, d, centers, K, 1.0f, stats, ws, ws_bytes);
+    if (rc != SCC_OK) return rc;
+    if (n == 0) { SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (K * d + 2 + K), st)); return SCC_OK; }
+    DecArgs a{};
+    a.z = z; a.n = n; a.mu = centers; a.K = K; a.alpha = 1.0f; a.scale = 1.f;
+    a.labels = labels; a.mindist = mindist; a.stats = stats;
+    fill_reduction(a, ws);
+    return dec_grad_dispatch(a, d, MODE_KMEANS, st);
+}
+
 }  // namespace scc

@@ -32,8 +32,9 @@ __host__ __device__ constexpr int dec_stages() { return RowLayout<D>::kDense ? 4
 template <int D, int KP, bool EXACT, bool ALPHA1>
 __device__ __forceinline__ void soft_assign_row(const float (&zr)[D], const float* __restrict__ mu_s, int K,
                                                 float inv_alpha, float expo, float (&u)[KP], float (&q)[KP],
-                                                int& label) {
-    float tsum = 0.f, best = 3.4e38f;
+                                                int& label, float& best) {
+    float tsum = 0.f;
+    best = 3.4e38f;
     label = 0;
 #pragma unroll
     for (int j = 0; j < KP; ++j) {
@@ -151,7 +152,8 @@ dec_assign_kernel(const DecArgs a) {
             const size_t i = (size_t)tile * kDecTile + threadIdx.x;
             float u[KP], q[KP];
             int label;
-            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label);
+            float best;
+            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label, best);
             if (round5) {
 #pragma unroll
                 for (int j = 0; j < KP; ++j) q[j] = round_dec5(q[j]);
@@ -177,12 +179,21 @@ dec_assign_kernel(const DecArgs a) {
 // dmu_j = -sum_i c_ij (z_i - mu_j).
 //   MODE_KL      : c_ij = scale (alpha+1)/alpha (p_ij - q_ij s_i) u_ij   (+ loss)
 //   MODE_GENERIC : c_ij = -(alpha+1)/alpha q_ij (G_ij - sum_j G_ij q_ij) u_ij
+//   MODE_KMEANS  : c_ij = [j == argmin_j ||z_i - mu_j||^2]  (Lloyd step: counts, centre shifts, inertia)
 // ---------------------------------------------------------------------------
 template <int KP, bool EXACT, int MODE>
 __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, int K, const float* __restrict__ inv_f,
                                                   const float (&u)[KP], const float (&q)[KP], float cscale,
+                                                  int label, float best,
                                                   float (&coef)[KP], float& loss, float& ssum) {
-    if constexpr (MODE == MODE_KL) {
+    if constexpr (MODE == MODE_KMEANS) {
+        // Lloyd statistics: one-hot coefficient on the nearest centre, "loss" = inertia
+#pragma unroll
+        for (int j = 0; j < KP; ++j) coef[j] = (j == label) ? 1.f : 0.f;
+        loss += best;
+        if (a.labels) a.labels[i] = label;
+        if (a.mindist) a.mindist[i] = best;
+    } else if constexpr (MODE == MODE_KL) {
         float p[KP];
         if (a.p) {
             load_krow<KP, EXACT>(a.p + i * K, K, p);
@@ -306,7 +317,7 @@ dec_grad_reg_kernel(const DecArgs a) {
     float* inv_f = c0_s + ((D + 3) & ~3);                                    // [KP]
     constexpr int SCR = NW * NV > kDecThreads ? NW * NV : kDecThreads;
     double* scratch = reinterpret_cast<double*>(inv_f + ((KP + 3) & ~3));    // [max(NW*NV, NT)]
-    double* cta_stats = scratch + SCR;                                       // [NV]
+    double* cta_stats = scratch + SCR;                                       // [NV]  (>= K*D + 2 + K)
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NV);
 
     const int K = EXACT ? KP : a.K;
@@ -341,8 +352,9 @@ dec_grad_reg_kernel(const DecArgs a) {
             const size_t i = (size_t)tile * kDecTile + threadIdx.x;
             float u[KP], q[KP], coef[KP];
             int label;
-            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label);
-            grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, coef, acc[0], acc[1]);
+            float best;
+            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label, best);
+            grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, label, best, coef, acc[0], acc[1]);
             float csum = 0.f;
 #pragma unroll
             for (int j = 0; j < KP; ++j) { acc[2 + j] += coef[j]; csum += coef[j]; }
@@ -368,17 +380,21 @@ dec_grad_reg_kernel(const DecArgs a) {
         }
         if (++stage == S) { stage = 0; ++use; }
     }
-    acc[0] *= a.scale;                   // loss = scale * sum p log(p/q)
+    if (MODE != MODE_KMEANS) acc[0] *= a.scale;        // loss = scale * sum p log(p/q)
     __syncthreads();
     cta_reduce<NV, kDecThreads>(acc, scratch, cta_stats);
     // dmu_jc = -(B_jc - W_j (mu_jc - c0_c)), compacted to [loss, sum s, dmu[K*D]]
-    double dmu = 0.0;
+    // (MODE_KMEANS: [inertia, 0, sum_{i in j} (z_i - mu_j) [K*D], counts[K]])
+    double dmu = 0.0, wj = 0.0;
     const int o = threadIdx.x;
     if (o < K * D) dmu = -(cta_stats[2 + KP + o] - cta_stats[2 + o / D] * (double)mc_s[o]);
+    if (o < K) wj = cta_stats[2 + o];
     __syncthreads();
-    if (o < K * D) cta_stats[2 + o] = dmu;
+    if (o < K * D) cta_stats[2 + o] = (MODE == MODE_KMEANS) ? -dmu : dmu;
+    if (MODE == MODE_KMEANS && o < K) cta_stats[2 + K * D + o] = wj;
     __syncthreads();
-    grid_publish<kDecThreads>(cta_stats, K * D + 2, a.partials, a.counter, a.stats, scratch);
+    grid_publish<kDecThreads>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials, a.counter, a.stats,
+                              scratch);
 }
 
 // ---------------------------------------------------------------------------
@@ -411,8 +427,8 @@ dec_grad_tiled_kernel(const DecArgs a) {
     float* inv_f = c0_s + D;                                 // [KP]
     double* scratch = reinterpret_cast<double*>(inv_f + KP); // [max(NW*NSM, NT)]
     double* small_s = scratch + (NW * NSM > kDecThreads ? NW * NSM : kDecThreads);   // [NSM]
-    double* cta_stats = small_s + NSM;                       // [NS]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NS);
+    double* cta_stats = small_s + NSM;                       // [NS + KP]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NS + KP);
 
     const int K = EXACT ? KP : a.K;
     load_grad_constants<D, KP>(a, K, mu_s, mc_s, c0_s, inv_f);
@@ -456,8 +472,9 @@ dec_grad_tiled_kernel(const DecArgs a) {
             const size_t i = (size_t)tile * kDecTile + threadIdx.x;
             float u[KP], q[KP];
             int label;
-            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label);
-            grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, coef, small[0], small[1]);
+            float best;
+            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label, best);
+            grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, label, best, coef, small[0], small[1]);
             float csum = 0.f;
 #pragma unroll
             for (int j = 0; j < KP; ++j) { small[2 + j] += coef[j]; csum += coef[j]; }
@@ -495,7 +512,7 @@ dec_grad_tiled_kernel(const DecArgs a) {
         if (++stage == S) { stage = 0; ++use; }
     }
     // ---- CTA reduction ----
-    small[0] *= a.scale;
+    if (MODE != MODE_KMEANS) small[0] *= a.scale;
     cta_reduce<NSM, kDecThreads>(small, scratch, small_s);
     // per-(warp, group) 4x4 partials -> shared (the ring buffer is free now), fixed-order sum
     double* part = reinterpret_cast<double*>(ring_buf);                      // [NW*G2][KP*D]
@@ -511,11 +528,14 @@ dec_grad_tiled_kernel(const DecArgs a) {
         double accd = 0.0;
 #pragma unroll
         for (int g = 0; g < NW * G2; ++g) accd += part[(size_t)g * (KP * D) + o];
-        cta_stats[2 + o] = -(accd - small_s[2 + o / D] * (double)mc_s[o]);
+        const double v = accd - small_s[2 + o / D] * (double)mc_s[o];
+        cta_stats[2 + o] = (MODE == MODE_KMEANS) ? v : -v;
     }
+    if (MODE == MODE_KMEANS && (int)threadIdx.x < K) cta_stats[2 + K * D + threadIdx.x] = small_s[2 + threadIdx.x];
     if (threadIdx.x == 0) { cta_stats[0] = small_s[0]; cta_stats[1] = small_s[1]; }
     __syncthreads();
-    grid_publish<kDecThreads>(cta_stats, K * D + 2, a.partials, a.counter, a.stats, scratch);
+    grid_publish<kDecThreads>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials, a.counter, a.stats,
+                              scratch);
 }
 
 // ---------------------------------------------------------------------------
@@ -548,7 +568,7 @@ constexpr size_t grad_tiled_smem() {
     constexpr int NSM = KP + 2;
     constexpr int scr = NW * NSM > kDecThreads ? NW * NSM : kDecThreads;
     size_t bytes = sizeof(float) * ((S + 1) * kDecTile * RowLayout<D>::LD + kDecTile * KP + 2 * KP * D + D + KP) +
-                   sizeof(double) * (scr + NSM + KP * D + 2) + sizeof(uint64_t) * S;
+                   sizeof(double) * (scr + NSM + KP * D + 2 + KP) + sizeof(uint64_t) * S;
     // the ring buffer is reused for the [NW*G2][KP*D] float64 partials at the end
     const size_t part = sizeof(double) * NW * G2 * KP * D;
     const size_t ring = sizeof(float) * S * kDecTile * RowLayout<D>::LD;

@@ -53,7 +53,7 @@ int persistent_grid(const void* kernel, int threads, size_t smem, int max_ctas_p
 
 size_t workspace_bytes(int d, int K) {
     if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return 0;
-    const size_t dec = (size_t)kMaxDecGrid * (size_t)(K * d + 2);
+    const size_t dec = (size_t)kMaxDecGrid * (size_t)(K * d + 2 + K);
     const size_t gmm = (size_t)kMaxGmmGrid * (size_t)SCC_GMM_STAT_DOUBLES(K, d);
     return kWorkspaceHeader + sizeof(double) * (dec > gmm ? dec : gmm);
 }
@@ -117,6 +117,12 @@ int scc_dec_backward(const float* z, int64_t n, int d, const float* mu, int K, f
                      float* dz, double* stats, void* workspace, size_t workspace_bytes, scc_stream_t stream) {
     return scc::dec_backward(z, n, d, mu, K, alpha, grad_q, dz, stats, workspace, workspace_bytes,
                              (cudaStream_t)stream);
+}
+
+int scc_kmeans_step(const float* z, int64_t n, int d, const float* centers, int K, int32_t* labels, float* mindist,
+                    double* stats, void* workspace, size_t workspace_bytes, scc_stream_t stream) {
+    return scc::kmeans_step(z, n, d, centers, K, labels, mindist, stats, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
 }
 
 int scc_gmm_em_step(const float* z, int64_t n, int d, int K, const float* params, double* stats, int32_t* labels,

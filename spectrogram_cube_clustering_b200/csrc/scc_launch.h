@@ -19,7 +19,7 @@ constexpr int kMaxDecGrid = 2048;      // persistent DEC grids never exceed this
 constexpr int kMaxGmmGrid = 512;
 constexpr size_t kWorkspaceHeader = 256;   // counters live in front of the partial slots
 
-enum { MODE_KL = 0, MODE_GENERIC = 1 };
+enum { MODE_KL = 0, MODE_GENERIC = 1, MODE_KMEANS = 2 };
 
 struct DecArgs {
     const float* z;
@@ -32,6 +32,7 @@ struct DecArgs {
     float* q;
     int32_t* labels;
     const int32_t* labels_prev;
+    float* mindist;            // MODE_KMEANS: squared distance to the nearest centre, or NULL
     // grad
     const float* p;
     const double* f_cols;
@@ -73,6 +74,8 @@ int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float 
                 void* ws, size_t ws_bytes, cudaStream_t st);
 int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* grad_q,
                  float* dz, double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
+int kmeans_step(const float* z, int64_t n, int d, const float* centers, int K, int32_t* labels, float* mindist,
+                double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
 
 int gmm_em_step(const float* z, int64_t n, int d, int K, const float* params, double* stats,
                 int32_t* labels, float* resp, const double* ctrl, int mode,

@@ -148,6 +148,20 @@ def dec_backward(z, mu, grad_q, alpha=1.0, want_dz=True):
     return dz, stats[2:].view(K, d)
 
 
+def kmeans_step(z, centers, labels=None, mindist=None, out_stats=None):
+    """One Lloyd step -> stats float64 [K*d+2+K] = (inertia, 0, shift[K,d], count[K]).  models.py:386-394."""
+    lib = _lib.load()
+    _require(z, "z"); _require(centers, "centers")
+    n, d = z.shape
+    K = centers.shape[0]
+    stats = out_stats if out_stats is not None else torch.empty(K * d + 2 + K, dtype=torch.float64, device=z.device)
+    ws = workspace(z.device, d, K)
+    rc = lib.scc_kmeans_step(z.data_ptr(), n, d, centers.data_ptr(), K, _ptr(labels), _ptr(mindist),
+                             stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "scc_kmeans_step")
+    return stats
+
+
 # --------------------------------------------------------------------------- GMM
 def gmm_param_floats(K, d):
     return K * d + K * (d * (d + 1) // 2) + K
