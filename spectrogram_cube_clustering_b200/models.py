@@ -145,7 +145,7 @@ class KMeans:
             shifts.append((step * step).sum())
             n_iter += 1
             if n_iter % poll == 0 or n_iter == self.max_iter:
-                if float(torch.stack(shifts[-poll:]).min().item()) <= thresh:
+                if float(shifts[-1].item()) <= thresh:        # sklearn: total centre shift <= tol * var
                     break
         labels = torch.empty(z.shape[0], dtype=torch.int32, device=z.device)
         ops.kmeans_step(z, centers, labels=labels, out_stats=stats)

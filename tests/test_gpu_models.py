@@ -1,0 +1,180 @@
+"""GPU tests of the reference-facing Python surface (networks.ClusteringLayer / DEC,
+models.target_distribution / gmm / kmeans / GaussianMixture, LatentBuffer)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err, DEC_CASES
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.mark.parametrize("case", DEC_CASES)
+def test_clustering_layer_matches_reference_layer(case):
+    """Same constructor / forward / autograd contract as Cluster.networks.ClusteringLayer, run the
+    way the reference runs it (float64 module), against the reference's own outputs."""
+    from spectrogram_cube_clustering_b200.networks import ClusteringLayer
+    g = load_golden("dec", case)
+    n, d = g["z"].shape
+    K = g["mu"].shape[0]
+    layer = ClusteringLayer(K, d, float(g["alpha"]), weights=torch.from_numpy(g["mu"]).double()).double().cuda()
+    assert layer.weights.dtype == torch.float64 and tuple(layer.weights.shape) == (K, d)
+    z = torch.from_numpy(g["z"]).double().cuda().requires_grad_(True)
+    q = layer(z)
+    assert q.dtype == torch.float64 and tuple(q.shape) == (n, K)
+    assert rel_err(q.detach().cpu().numpy(), g["q"]) < TOL
+    # the literal reference loss line: gamma * KLDivLoss('sum')(log q, p) / B   (models.py:1124-1125)
+    tar = torch.from_numpy(g["p"]).cuda()
+    loss = float(g["gamma"]) * torch.nn.KLDivLoss(reduction="sum")(torch.log(q), tar) / n
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 2 * TOL * abs(float(g["loss"]))
+    assert rel_err(z.grad.cpu().numpy(), g["dz"]) < 2 * TOL
+    assert rel_err(layer.weights.grad.cpu().numpy(), g["dmu"]) < 2 * TOL
+
+
+def test_clustering_layer_generic_grad_and_padding():
+    """d = 7 is not instantiated: the host zero-pads z and the centroids (exact)."""
+    from spectrogram_cube_clustering_b200.networks import ClusteringLayer
+    from oracle import dec as odec
+    rng = np.random.default_rng(3)
+    z = rng.normal(size=(333, 7)).astype(np.float32)
+    mu = rng.normal(size=(5, 7)).astype(np.float32)
+    G = rng.normal(size=(333, 5)).astype(np.float32)
+    layer = ClusteringLayer(5, 7, 1.0, weights=torch.from_numpy(mu)).cuda()
+    zt = torch.from_numpy(z).cuda().requires_grad_(True)
+    q = layer(zt)
+    q.backward(torch.from_numpy(G).cuda())
+    dz, dmu = odec.backward_generic(z, mu, G, 1.0)
+    assert rel_err(q.detach().cpu().numpy(), odec.soft_assign(z, mu)) < TOL
+    assert rel_err(zt.grad.cpu().numpy(), dz) < TOL and rel_err(layer.weights.grad.cpu().numpy(), dmu) < TOL
+
+
+def test_clustering_layer_rejects_cpu():
+    from spectrogram_cube_clustering_b200.networks import ClusteringLayer
+    from spectrogram_cube_clustering_b200._lib import SccError
+    with pytest.raises(SccError):
+        ClusteringLayer(8, 9)(torch.zeros(4, 9))
+
+
+def test_dec_module_state_dict_and_forward():
+    from spectrogram_cube_clustering_b200.networks import DEC
+    from spectrogram_cube_clustering_b200 import synth
+    model = DEC(n_clusters=5).cuda()
+    keys = set(model.state_dict())
+    assert "clustering.weights" in keys and "encoder.encoder.8.weight" in keys and "decoder.decoder.0.weight" in keys
+    assert "encoder.encoder.6.conv.weight" in keys
+    x = synth.spectrograms(32, device="cuda")
+    q, x_rec, z = model(x)
+    assert tuple(q.shape) == (32, 5) and tuple(z.shape) == (32, 9) and tuple(x_rec.shape) == (32, 1, 4, 101)
+    torch.testing.assert_close(q.sum(1), torch.ones(32, device="cuda"), atol=1e-5, rtol=0)
+    (q[:, 0].sum() + x_rec.mean()).backward()
+    assert model.clustering.weights.grad is not None and model.encoder.encoder[0].weight.grad is not None
+
+
+@pytest.mark.parametrize("case", ["c1", "k5", "tie"])
+def test_target_distribution_numpy_api(case):
+    from spectrogram_cube_clustering_b200.models import target_distribution
+    g = load_golden("dec", case)
+    p = target_distribution(g["q_round"])
+    assert isinstance(p, np.ndarray) and p.dtype == np.float64 and p.shape == g["p"].shape
+    d = np.abs(p - g["p"])
+    assert d.max() <= 1.01e-5 and (d > 1e-7).mean() < 0.03
+
+
+@pytest.mark.parametrize("case", ["c1", "k16", "relu"])
+def test_gaussian_mixture_front_end_matches_sklearn_fit(case):
+    from spectrogram_cube_clustering_b200.models import GaussianMixture
+    g = load_golden("gmm", case)
+    gm = GaussianMixture(g["mu0"].shape[0], max_iter=100, tol=float(g["tol"]), weights_init=g["w0"],
+                         means_init=g["mu0"], covariances_init=g["cov0"], poll_interval=4)
+    labels = gm.fit_predict(g["z"])
+    assert gm.n_iter_ == int(g["fit_n_iter"]) and gm.converged_ == bool(g["fit_converged"])
+    assert abs(gm.lower_bound_ - float(g["fit_lower_bound"])) < 1e-4 * abs(float(g["fit_lower_bound"]))
+    assert rel_err(gm.means_, g["fit_means"]) < 1e-4 and rel_err(gm.weights_, g["fit_weights"]) < 1e-4
+    assert labels.dtype == np.int64 and (labels != g["fit_labels"]).mean() < 2e-3
+
+
+def test_gaussian_mixture_errors():
+    from spectrogram_cube_clustering_b200.models import GaussianMixture, ConvergenceWarning
+    with pytest.raises(ValueError):                       # n_samples < n_components (sklearn _base.py:232-237)
+        GaussianMixture(8).fit(np.zeros((4, 9), dtype=np.float32))
+    z = np.ones((256, 9), dtype=np.float32)               # collapsed data, no regularisation -> not PD
+    with pytest.raises(ValueError):
+        GaussianMixture(2, reg_covar=0.0, means_init=np.ones((2, 9)),
+                        covariances_init=np.tile(np.eye(9), (2, 1, 1))).fit(z)
+    g = load_golden("gmm", "c1")
+    with pytest.warns(ConvergenceWarning):
+        GaussianMixture(8, max_iter=2, tol=0.0, weights_init=g["w0"], means_init=g["mu0"],
+                        covariances_init=g["cov0"]).fit(g["z"])
+
+
+def test_kmeans_lloyd_matches_sklearn_from_identical_centres():
+    from sklearn.cluster import KMeans as SkKMeans
+    from spectrogram_cube_clustering_b200.models import KMeans
+    g = load_golden("gmm", "c1")
+    z = g["z"]
+    init = g["mu0"].astype(np.float32)
+    sk = SkKMeans(n_clusters=8, init=init, n_init=1, max_iter=300, tol=1e-4, algorithm="lloyd").fit(z.astype(np.float64))
+    km = KMeans(8, max_iter=300, n_init=1, tol=1e-4).fit(z, init_centers=init)
+    assert (km.labels_ != sk.labels_).mean() < 5e-3
+    assert abs(km.inertia_ - sk.inertia_) < 1e-4 * sk.inertia_
+    assert rel_err(km.cluster_centers_, sk.cluster_centers_) < 1e-3
+
+
+def test_gmm_function_end_to_end():
+    """models.gmm(z, K): k-means++ seeding + EM, vs scikit-learn EM from the SAME seeds."""
+    from sklearn.mixture import GaussianMixture as SkGM
+    from spectrogram_cube_clustering_b200.models import gmm, KMeans
+    from spectrogram_cube_clustering_b200 import synth
+    from oracle import gmm as ogmm
+    z, _ = synth.latent_points(6000, 9, 5, rank=42)
+    z = z.numpy()
+    km = KMeans(5, n_init=3, random_state=2009).fit(z)
+    w0 = np.bincount(km.labels_, minlength=5) / z.shape[0]
+    labels, cent = gmm(z, 5, means_init=km.cluster_centers_, weights_init=w0)
+    assert labels.shape == (6000,) and labels.dtype == np.int64 and cent.shape == (5, 9)
+    X = z.astype(np.float64)
+    lab0 = np.argmin(((X[:, None] - km.cluster_centers_[None]) ** 2).sum(2), 1)
+    resp = np.zeros((6000, 5)); resp[np.arange(6000), lab0] = 1
+    with np.errstate(divide="ignore"):
+        _, _, cov0, _, _ = ogmm.m_step(X, np.log(resp))
+    sk = SkGM(5, max_iter=1000, weights_init=w0, means_init=km.cluster_centers_,
+              precisions_init=np.linalg.inv(cov0)).fit(X)
+    assert rel_err(cent, sk.means_) < 1e-3
+    assert (labels != sk.predict(X)).mean() < 5e-3
+    labels2, cent2 = gmm(z, 5)                      # full path with its own KMeans(n_init=100) seeding
+    assert labels2.shape == (6000,) and np.isfinite(cent2).all() and len(np.unique(labels2)) == 5
+
+
+def test_latent_buffer_dec_step_and_refine():
+    from spectrogram_cube_clustering_b200.latent_buffer import LatentBuffer
+    from spectrogram_cube_clustering_b200.models import dec_refine
+    from spectrogram_cube_clustering_b200 import synth
+    from oracle import dec as odec
+    z, mu = synth.latent_points(20000, 9, 8, rank=5)
+    buf = LatentBuffer.from_host(z.numpy(), "cuda")
+    res = buf.dec_step(mu.cuda(), 1.0, 1e-3, round_decimals=0)
+    ref = odec.dec_step(z.numpy(), mu.numpy(), 1.0, 1e-3, round_to=None)
+    assert abs(res.loss.item() - ref["loss"]) < TOL * abs(ref["loss"])
+    assert rel_err(res.dmu.cpu().numpy(), ref["dmu"]) < TOL and rel_err(res.f.cpu().numpy(), ref["f"]) < TOL
+    cent, hist = dec_refine(buf, mu, lr=1e-2, max_steps=30, tol=0.0)
+    assert cent.shape == (8, 9) and len(hist) == 30 and np.isfinite(cent).all()
+    assert hist[-1]["delta"] <= hist[1]["delta"] + 1e-3
+
+
+def test_batch_eval_matches_layerwise_eval():
+    from spectrogram_cube_clustering_b200.networks import DEC
+    from spectrogram_cube_clustering_b200.models import batch_eval
+    from spectrogram_cube_clustering_b200 import synth
+    torch.manual_seed(0)
+    model = DEC(n_clusters=5).cuda()
+    x = synth.spectrograms(1000)
+    loader = torch.utils.data.DataLoader(x, batch_size=128, shuffle=False)
+    q, labels, z = batch_eval(loader, model, "cuda")
+    assert q.shape == (1000, 5) and labels.shape == (1000,) and z.shape == (1000, 9)
+    with torch.no_grad():
+        qq, _, zz = model(x.cuda())
+    assert rel_err(z, zz.cpu().numpy()) < 1e-6
+    assert np.abs(q - np.round(qq.cpu().numpy().astype(np.float64), 5)).max() <= 1.01e-5
+    assert (labels != qq.argmax(1).cpu().numpy()).mean() < 2e-3
