@@ -253,19 +253,19 @@ def run_gpu(args):
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    # keep the same load running a little longer so NVML gets samples even for very short regions
-    t_end = time.perf_counter() + 0.15
-    i = 0
-    while time.perf_counter() < t_end:
-        run_step(i); i += 1
-        if i % 64 == 0:
-            torch.cuda.synchronize()
-    torch.cuda.synchronize()
-    sampler.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
+    # keep the same load running a little longer so NVML gets samples even for very short regions
+    # (a FIXED step count derived from the max-reduced time: every rank must issue the same collectives)
+    n_extra = max(8, min(20000, int(150.0 / max(ms_total / args.steps, 1e-3))))
+    for i in range(n_extra):
+        run_step(i)
+        if i % 64 == 63:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    sampler.stop()
     ms_per_step = ms_total / args.steps
     value = n_total / (ms_per_step * 1e-3)
 
