@@ -36,6 +36,11 @@ N_SETS = 4                      # distinct input/output sets cycled so no step r
 WORKLOAD = "DEC fwd/bwd + target distribution, N=1M latent points per GPU, d=9, K=8, alpha=1 (BASELINE configs[1])"
 
 
+def dbg(msg):
+    if os.environ.get("SCC_BENCH_DEBUG"):
+        print(f"[bench r{os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -200,11 +205,13 @@ def run_gpu(args):
     def step(s):
         k_assign(s); allreduce(s["st1"]); k_target(s); k_grad(s); allreduce(s["st2"])
 
+    dbg('inputs ready')
     # warm-up (eager): also creates workspaces and primes NCCL
     for w in range(max(args.warmup, 3)):
         step(sets[w % N_SETS])
     torch.cuda.synchronize()
 
+    dbg('eager warm-up done')
     # CUDA graphs: one per input set (pointers are baked in)
     graphs, use_graphs = [], not args.no_graphs
     if use_graphs:
@@ -234,6 +241,7 @@ def run_gpu(args):
         else:
             step(sets[i % N_SETS])
 
+    dbg(f'graphs={use_graphs}')
     for i in range(3):
         run_step(i)
     sampler = ClockSampler(local)
@@ -243,6 +251,7 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    dbg('timed region')
     # ---------------- timed region: EXACTLY `steps` steps ----------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -269,6 +278,7 @@ def run_gpu(args):
     ms_per_step = ms_total / args.steps
     value = n_total / (ms_per_step * 1e-3)
 
+    dbg('per-kernel pass')
     # ---------------- per-kernel durations (CUDA events, launch queue pre-loaded) ----------------
     # The stream is first blocked by a spin kernel so that all launches + event records are queued
     # before the GPU starts: consecutive events then bracket exactly one kernel.
@@ -299,6 +309,7 @@ def run_gpu(args):
                 "step_gbs": step_bytes * N_PER_GPU / (ms_per_step * 1e-3) / 1e9,
                 "step_frac": step_bytes * N_PER_GPU / (ms_per_step * 1e-3) / 1e9 / hbm_peak}
 
+    dbg('e2e pass')
     # ---------------- end to end: host buffers in, host results out, every step ----------------
     zh = [s["z"].cpu().pin_memory() for s in sets[:2]]
     mu_h = mu.cpu().pin_memory()
@@ -340,6 +351,7 @@ def run_gpu(args):
            "ms_per_step": e2e_ms, "api": "ops.dec_assign/dec_target/dec_kl_grad on a pinned host latent set; "
                                          "loss, dmu, f, label-change count read back", "loss": loss_h}
 
+    dbg('e2e done')
     extra = {}
     if world == 1 and not args.no_extra:
         extra = extra_benchmarks(torch, ops, synth, dev, hbm_peak)
@@ -366,8 +378,16 @@ def run_gpu(args):
             "cpu_baseline": cpu, "extra": extra,
         }
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
     if world > 1:
+        # CUDA graphs that captured NCCL kernels must die before the communicator does; a watchdog
+        # guarantees the process exits even if communicator teardown stalls.
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def extra_benchmarks(torch, ops, synth, dev, hbm_peak):
