@@ -26,13 +26,32 @@ template <int D>
 __host__ __device__ constexpr int dec_stages() { return RowLayout<D>::kDense ? 4 : 2; }
 
 // ---------------------------------------------------------------------------
+// Packed FP32 (sm_100 FFMA2 / FADD2 / FMUL2): two lanes of a float2 per instruction.  On B200 a
+// stream of 3-register scalar FFMAs issues at ~56 % of the FP32 peak (register-read bandwidth)
+// while FFMA2 reaches ~88 % (tools/ubench_fp32.cu), and the issue-slot count halves.
+// Rows are held as DP2 = ceil(D/2) float2 pairs; the pad lane of an odd D is kept at 0.
+// ---------------------------------------------------------------------------
+template <int D>
+struct Pairs { static constexpr int N = (D + 1) / 2; };
+
+__device__ __forceinline__ float2 splat2(float x) { return make_float2(x, x); }
+
+template <int D>
+__device__ __forceinline__ void pack_row(const float (&r)[D], float2 (&p)[Pairs<D>::N]) {
+#pragma unroll
+    for (int c = 0; c < Pairs<D>::N; ++c) p[c] = make_float2(r[2 * c], (2 * c + 1 < D) ? r[2 * c + 1] : 0.f);
+}
+
+// ---------------------------------------------------------------------------
 // q_i, u_i and the hard label of one point.  networks.py:279-288, models.py:92.
 // Distances use the exact difference form (z_c - mu_jc)^2: no cancellation.
+// nmu2_s holds the NEGATED centroids as float2 pairs [KP][DP2] (pad lane 0).
 // ---------------------------------------------------------------------------
 template <int D, int KP, bool EXACT, bool ALPHA1>
-__device__ __forceinline__ void soft_assign_row(const float (&zr)[D], const float* __restrict__ mu_s, int K,
-                                                float inv_alpha, float expo, float (&u)[KP], float (&q)[KP],
+__device__ __forceinline__ void soft_assign_row(const float2 (&z2)[Pairs<D>::N], const float2* __restrict__ nmu2_s,
+                                                int K, float inv_alpha, float expo, float (&u)[KP], float (&q)[KP],
                                                 int& label, float& best) {
+    constexpr int DP2 = Pairs<D>::N;
     float tsum = 0.f;
     best = 3.4e38f;
     label = 0;
@@ -40,12 +59,13 @@ __device__ __forceinline__ void soft_assign_row(const float (&zr)[D], const floa
     for (int j = 0; j < KP; ++j) {
         u[j] = 0.f; q[j] = 0.f;
         if (EXACT || j < K) {
-            float acc = 0.f;
+            float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int c = 0; c < D; ++c) {
-                const float df = zr[c] - mu_s[j * D + c];
-                acc = fmaf(df, df, acc);
+            for (int c = 0; c < DP2; ++c) {
+                const float2 df = __fadd2_rn(z2[c], nmu2_s[j * DP2 + c]);
+                acc2 = __ffma2_rn(df, df, acc2);
             }
+            const float acc = acc2.x + acc2.y;
             if (acc < best) { best = acc; label = j; }          // argmax q == argmin distance, first wins
             const float uu = __fdividef(1.f, ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f));
             const float t = ALPHA1 ? uu : __powf(uu, expo);
@@ -55,6 +75,17 @@ __device__ __forceinline__ void soft_assign_row(const float (&zr)[D], const floa
     const float inv = __fdividef(1.f, tsum);
 #pragma unroll
     for (int j = 0; j < KP; ++j) q[j] *= inv;
+}
+
+// negated centroids as pairs: nmu2_s[j][c] = -(mu[j][2c], mu[j][2c+1]); rows j >= K and pad lanes are 0
+template <int D, int KP>
+__device__ __forceinline__ void load_neg_centroid_pairs(const float* __restrict__ mu, int K, float2* nmu2_s) {
+    constexpr int DP2 = Pairs<D>::N;
+    float* flat = reinterpret_cast<float*>(nmu2_s);
+    for (int i = threadIdx.x; i < KP * DP2 * 2; i += kDecThreads) {
+        const int j = i / (2 * DP2), c = i - j * (2 * DP2);
+        flat[i] = (j < K && c < D) ? -mu[j * D + c] : 0.f;
+    }
 }
 
 template <int KP, bool EXACT>
@@ -116,13 +147,14 @@ dec_assign_kernel(const DecArgs a) {
     using Ring = ZRing<D, kDecTile, S, kDecThreads>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring_buf = reinterpret_cast<float*>(smem_raw);
-    float* mu_s = ring_buf + S * Ring::kTileFloats;                           // [KP*D]
-    double* scratch = reinterpret_cast<double*>(mu_s + ((KP * D + 3) & ~3));  // [max(NW*(KP+1), NT)]
+    constexpr int DP2 = Pairs<D>::N;
+    float2* nmu2_s = reinterpret_cast<float2*>(ring_buf + S * Ring::kTileFloats);      // [KP][DP2] (-mu pairs)
+    double* scratch = reinterpret_cast<double*>(nmu2_s + ((KP * DP2 + 1) & ~1));       // [max(NW*(KP+1), NT)]
     double* cta_stats = scratch + (NW * (KP + 1) > kDecThreads ? NW * (KP + 1) : kDecThreads);   // [KP+1]
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + (KP + 1));
 
     const int K = EXACT ? KP : a.K;
-    for (int i = threadIdx.x; i < KP * D; i += kDecThreads) mu_s[i] = (i < K * D) ? a.mu[i] : 0.f;
+    load_neg_centroid_pairs<D, KP>(a.mu, K, nmu2_s);
 
     Ring ring;
     ring.init(ring_buf, bars, a.z, a.n);
@@ -151,9 +183,11 @@ dec_assign_kernel(const DecArgs a) {
         if (active) {
             const size_t i = (size_t)tile * kDecTile + threadIdx.x;
             float u[KP], q[KP];
+            float2 z2[DP2];
+            pack_row<D>(zr, z2);
             int label;
             float best;
-            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label, best);
+            soft_assign_row<D, KP, EXACT, ALPHA1>(z2, nmu2_s, K, inv_alpha, expo, u, q, label, best);
             if (round5) {
 #pragma unroll
                 for (int j = 0; j < KP; ++j) q[j] = round_dec5(q[j]);
@@ -237,19 +271,26 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
 }
 
 // dz_c = (sum_j c_j) zc_c - sum_j c_j mc_jc  with zc = z - c0, mc = mu - c0 (algebraic form of
-// sum_j c_j (z_c - mu_jc): K*D FMAs instead of K*D (FADD + FMA)).
+// sum_j c_j (z_c - mu_jc): K*D/2 FFMA2 instead of K*D (FADD + FMA)).  nmc2_s = -(mu - c0) pairs.
 template <int D, int KP, bool EXACT>
-__device__ __forceinline__ void dz_from_coefficients(const float (&zc)[D], const float (&coef)[KP], float csum,
-                                                     const float* __restrict__ mc_s, int K, float (&dzr)[D]) {
+__device__ __forceinline__ void dz_from_coefficients(const float2 (&zc2)[Pairs<D>::N], const float (&coef)[KP],
+                                                     float csum, const float2* __restrict__ nmc2_s, int K,
+                                                     float (&dzr)[D]) {
+    constexpr int DP2 = Pairs<D>::N;
+    float2 dz2[DP2];
+    const float2 cs = splat2(csum);
 #pragma unroll
-    for (int c = 0; c < D; ++c) dzr[c] = csum * zc[c];
+    for (int c = 0; c < DP2; ++c) dz2[c] = __fmul2_rn(cs, zc2[c]);
 #pragma unroll
     for (int j = 0; j < KP; ++j) {
         if (EXACT || j < K) {
+            const float2 cj = splat2(coef[j]);
 #pragma unroll
-            for (int c = 0; c < D; ++c) dzr[c] = fmaf(-coef[j], mc_s[j * D + c], dzr[c]);
+            for (int c = 0; c < DP2; ++c) dz2[c] = __ffma2_rn(cj, nmc2_s[j * DP2 + c], dz2[c]);
         }
     }
+#pragma unroll
+    for (int c = 0; c < D; ++c) dzr[c] = (c & 1) ? dz2[c >> 1].y : dz2[c >> 1].x;
 }
 
 // Coalesced copy of a staged [np, D] tile (row stride LD) to global rows.
@@ -277,10 +318,11 @@ __device__ __forceinline__ void copy_tile_out(const float* __restrict__ tile, fl
     }
 }
 
-// Shared prologue of the gradient kernels: centroids, centred centroids, c0, 1/f.
+// Shared prologue of the gradient kernels: -mu pairs, -(mu - c0) pairs, c0, (mu - c0), 1/f.
 template <int D, int KP>
-__device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, float* mu_s, float* mc_s, float* c0_s,
-                                                    float* inv_f) {
+__device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, float2* nmu2_s, float2* nmc2_s,
+                                                    float* mc_s, float* c0_s, float* inv_f) {
+    constexpr int DP2 = Pairs<D>::N;
     if (threadIdx.x < D) {
         float m = 0.f;
         for (int j = 0; j < K; ++j) m += a.mu[j * D + threadIdx.x];
@@ -289,11 +331,16 @@ __device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, flo
     if (threadIdx.x < KP)
         inv_f[threadIdx.x] = (a.f_cols && (int)threadIdx.x < K) ? (float)(1.0 / a.f_cols[threadIdx.x]) : 0.f;
     __syncthreads();
-    for (int i = threadIdx.x; i < KP * D; i += kDecThreads) {
-        const float m = (i < K * D) ? a.mu[i] : 0.f;
-        mu_s[i] = m;
-        mc_s[i] = (i < K * D) ? m - c0_s[i % D] : 0.f;
+    float* nmu = reinterpret_cast<float*>(nmu2_s);
+    float* nmc = reinterpret_cast<float*>(nmc2_s);
+    for (int i = threadIdx.x; i < KP * DP2 * 2; i += kDecThreads) {
+        const int j = i / (2 * DP2), c = i - j * (2 * DP2);
+        const bool ok = (j < K && c < D);
+        const float m = ok ? a.mu[j * D + c] : 0.f;
+        nmu[i] = -m;
+        nmc[i] = ok ? -(m - c0_s[c]) : 0.f;
     }
+    for (int i = threadIdx.x; i < KP * D; i += kDecThreads) mc_s[i] = (i < K * D) ? a.mu[i] - c0_s[i % D] : 0.f;
 }
 
 // ---------------------------------------------------------------------------
@@ -302,26 +349,28 @@ __device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, flo
 // stats out: [loss, sum_i s_i, dmu[K*D]]
 // ---------------------------------------------------------------------------
 template <int D, int KP, bool EXACT, bool ALPHA1, int MODE>
-__global__ void __launch_bounds__(kDecThreads, (2 + KP + KP * D) <= 100 ? 2 : 1)
+__global__ void __launch_bounds__(kDecThreads, (2 + KP + 2 * KP * Pairs<D>::N) <= 100 ? 2 : 1)
 dec_grad_reg_kernel(const DecArgs a) {
     constexpr int S = dec_stages<D>();
     constexpr int NW = kDecThreads / 32;
+    constexpr int DP2 = Pairs<D>::N;
     using Ring = ZRing<D, kDecTile, S, kDecThreads>;
     constexpr int NV = 2 + KP + KP * D;
+    constexpr int SCR = NW * NV > kDecThreads ? NW * NV : kDecThreads;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring_buf = reinterpret_cast<float*>(smem_raw);
     float* out_tile = ring_buf + S * Ring::kTileFloats;                      // [TILE*LD]
-    float* mu_s = out_tile + Ring::kTileFloats;                              // [KP*D]
-    float* mc_s = mu_s + ((KP * D + 3) & ~3);                                // [KP*D]
+    float2* nmu2_s = reinterpret_cast<float2*>(out_tile + Ring::kTileFloats);  // [KP][DP2]
+    float2* nmc2_s = nmu2_s + ((KP * DP2 + 1) & ~1);                         // [KP][DP2]
+    float* mc_s = reinterpret_cast<float*>(nmc2_s + ((KP * DP2 + 1) & ~1));  // [KP*D]
     float* c0_s = mc_s + ((KP * D + 3) & ~3);                                // [D]
     float* inv_f = c0_s + ((D + 3) & ~3);                                    // [KP]
-    constexpr int SCR = NW * NV > kDecThreads ? NW * NV : kDecThreads;
     double* scratch = reinterpret_cast<double*>(inv_f + ((KP + 3) & ~3));    // [max(NW*NV, NT)]
     double* cta_stats = scratch + SCR;                                       // [NV]  (>= K*D + 2 + K)
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NV);
 
     const int K = EXACT ? KP : a.K;
-    load_grad_constants<D, KP>(a, K, mu_s, mc_s, c0_s, inv_f);
+    load_grad_constants<D, KP>(a, K, nmu2_s, nmc2_s, mc_s, c0_s, inv_f);
 
     Ring ring;
     ring.init(ring_buf, bars, a.z, a.n);
@@ -334,9 +383,16 @@ dec_grad_reg_kernel(const DecArgs a) {
     const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
     const float cscale = (MODE == MODE_KL ? a.scale : 1.f) * (a.alpha + 1.f) / a.alpha;
     const bool want_dz = a.dz != nullptr;
-    float acc[NV];
+    float sm[2 + KP];                     // loss, sum s, W_j
 #pragma unroll
-    for (int s = 0; s < NV; ++s) acc[s] = 0.f;
+    for (int s = 0; s < 2 + KP; ++s) sm[s] = 0.f;
+    float2 B2[KP * DP2];                  // B_jc = sum_i c_ij (z_ic - c0_c), as pairs
+#pragma unroll
+    for (int s = 0; s < KP * DP2; ++s) B2[s] = make_float2(0.f, 0.f);
+    float2 nc0[DP2];
+#pragma unroll
+    for (int c = 0; c < DP2; ++c)
+        nc0[c] = make_float2(-c0_s[2 * c], (2 * c + 1 < D) ? -c0_s[2 * c + 1] : 0.f);
 
     int stage = 0;
     uint32_t use = 0;
@@ -351,26 +407,28 @@ dec_grad_reg_kernel(const DecArgs a) {
         if (active) {
             const size_t i = (size_t)tile * kDecTile + threadIdx.x;
             float u[KP], q[KP], coef[KP];
+            float2 z2[DP2];
+            pack_row<D>(zr, z2);
             int label;
             float best;
-            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label, best);
-            grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, label, best, coef, acc[0], acc[1]);
+            soft_assign_row<D, KP, EXACT, ALPHA1>(z2, nmu2_s, K, inv_alpha, expo, u, q, label, best);
+            grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, label, best, coef, sm[0], sm[1]);
             float csum = 0.f;
 #pragma unroll
-            for (int j = 0; j < KP; ++j) { acc[2 + j] += coef[j]; csum += coef[j]; }
+            for (int j = 0; j < KP; ++j) { sm[2 + j] += coef[j]; csum += coef[j]; }
 #pragma unroll
-            for (int c = 0; c < D; ++c) zr[c] -= c0_s[c];
+            for (int c = 0; c < DP2; ++c) z2[c] = __fadd2_rn(z2[c], nc0[c]);       // centred point
 #pragma unroll
             for (int j = 0; j < KP; ++j) {
                 if (EXACT || j < K) {
+                    const float2 cj = splat2(coef[j]);
 #pragma unroll
-                    for (int c = 0; c < D; ++c)
-                        acc[2 + KP + j * D + c] = fmaf(coef[j], zr[c], acc[2 + KP + j * D + c]);
+                    for (int c = 0; c < DP2; ++c) B2[j * DP2 + c] = __ffma2_rn(cj, z2[c], B2[j * DP2 + c]);
                 }
             }
             if (want_dz) {
                 float dzr[D];
-                dz_from_coefficients<D, KP, EXACT>(zr, coef, csum, mc_s, K, dzr);
+                dz_from_coefficients<D, KP, EXACT>(z2, coef, csum, nmc2_s, K, dzr);
                 store_row<D>(out_tile, threadIdx.x, dzr);
             }
         }
@@ -380,7 +438,15 @@ dec_grad_reg_kernel(const DecArgs a) {
         }
         if (++stage == S) { stage = 0; ++use; }
     }
-    if (MODE != MODE_KMEANS) acc[0] *= a.scale;        // loss = scale * sum p log(p/q)
+    if (MODE != MODE_KMEANS) sm[0] *= a.scale;        // loss = scale * sum p log(p/q)
+    float acc[NV];
+#pragma unroll
+    for (int s = 0; s < 2 + KP; ++s) acc[s] = sm[s];
+#pragma unroll
+    for (int j = 0; j < KP; ++j)
+#pragma unroll
+        for (int c = 0; c < D; ++c)
+            acc[2 + KP + j * D + c] = (c & 1) ? B2[j * DP2 + (c >> 1)].y : B2[j * DP2 + (c >> 1)].x;
     __syncthreads();
     cta_reduce<NV, kDecThreads>(acc, scratch, cta_stats);
     // dmu_jc = -(B_jc - W_j (mu_jc - c0_c)), compacted to [loss, sum s, dmu[K*D]]
@@ -421,8 +487,10 @@ dec_grad_tiled_kernel(const DecArgs a) {
     float* ring_buf = reinterpret_cast<float*>(smem_raw);
     float* out_tile = ring_buf + S * Ring::kTileFloats;      // [TILE*LD] dz staging
     float* w_tile = out_tile + Ring::kTileFloats;            // [TILE*KP] coefficients
-    float* mu_s = w_tile + kDecTile * KP;                    // [KP*D]
-    float* mc_s = mu_s + KP * D;                             // [KP*D]
+    constexpr int DP2 = Pairs<D>::N;
+    float2* nmu2_s = reinterpret_cast<float2*>(w_tile + kDecTile * KP);      // [KP][DP2]
+    float2* nmc2_s = nmu2_s + KP * DP2;                      // [KP][DP2]
+    float* mc_s = reinterpret_cast<float*>(nmc2_s + KP * DP2);               // [KP*D]
     float* c0_s = mc_s + KP * D;                             // [D]
     float* inv_f = c0_s + D;                                 // [KP]
     double* scratch = reinterpret_cast<double*>(inv_f + KP); // [max(NW*NSM, NT)]
@@ -431,7 +499,7 @@ dec_grad_tiled_kernel(const DecArgs a) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NS + KP);
 
     const int K = EXACT ? KP : a.K;
-    load_grad_constants<D, KP>(a, K, mu_s, mc_s, c0_s, inv_f);
+    load_grad_constants<D, KP>(a, K, nmu2_s, nmc2_s, mc_s, c0_s, inv_f);
 
     Ring ring;
     ring.init(ring_buf, bars, a.z, a.n);
@@ -444,6 +512,9 @@ dec_grad_tiled_kernel(const DecArgs a) {
     const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
     const float cscale = (MODE == MODE_KL ? a.scale : 1.f) * (a.alpha + 1.f) / a.alpha;
     const bool want_dz = a.dz != nullptr;
+    float2 nc0[DP2];
+#pragma unroll
+    for (int c = 0; c < DP2; ++c) nc0[c] = make_float2(-c0_s[2 * c], -c0_s[2 * c + 1]);
     float small[NSM];
 #pragma unroll
     for (int s = 0; s < NSM; ++s) small[s] = 0.f;
@@ -471,19 +542,23 @@ dec_grad_tiled_kernel(const DecArgs a) {
             load_row<D>(ztile, threadIdx.x, zr);
             const size_t i = (size_t)tile * kDecTile + threadIdx.x;
             float u[KP], q[KP];
+            float2 z2[DP2];
+            pack_row<D>(zr, z2);
             int label;
             float best;
-            soft_assign_row<D, KP, EXACT, ALPHA1>(zr, mu_s, K, inv_alpha, expo, u, q, label, best);
+            soft_assign_row<D, KP, EXACT, ALPHA1>(z2, nmu2_s, K, inv_alpha, expo, u, q, label, best);
             grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, label, best, coef, small[0], small[1]);
             float csum = 0.f;
 #pragma unroll
             for (int j = 0; j < KP; ++j) { small[2 + j] += coef[j]; csum += coef[j]; }
 #pragma unroll
-            for (int c = 0; c < D; ++c) zr[c] -= c0_s[c];
+            for (int c = 0; c < DP2; ++c) z2[c] = __fadd2_rn(z2[c], nc0[c]);
+#pragma unroll
+            for (int c = 0; c < D; ++c) zr[c] = (c & 1) ? z2[c >> 1].y : z2[c >> 1].x;
             store_row<D>(ztile, threadIdx.x, zr);     // own row, centred, for phase 2
             if (want_dz) {
                 float dzr[D];
-                dz_from_coefficients<D, KP, EXACT>(zr, coef, csum, mc_s, K, dzr);
+                dz_from_coefficients<D, KP, EXACT>(z2, coef, csum, nmc2_s, K, dzr);
                 store_row<D>(out_tile, threadIdx.x, dzr);
             }
         }
@@ -546,7 +621,7 @@ constexpr size_t assign_smem() {
     constexpr int S = dec_stages<D>();
     constexpr int NW = kDecThreads / 32;
     constexpr int scr = NW * (KP + 1) > kDecThreads ? NW * (KP + 1) : kDecThreads;
-    return sizeof(float) * (S * kDecTile * RowLayout<D>::LD + ((KP * D + 3) & ~3)) +
+    return sizeof(float) * (S * kDecTile * RowLayout<D>::LD + 2 * ((KP * Pairs<D>::N + 1) & ~1)) +
            sizeof(double) * (scr + (KP + 1)) + sizeof(uint64_t) * S;
 }
 template <int D, int KP>
@@ -555,8 +630,8 @@ constexpr size_t grad_reg_smem() {
     constexpr int NV = 2 + KP + KP * D;
     constexpr int NW = kDecThreads / 32;
     constexpr int SCR = NW * NV > kDecThreads ? NW * NV : kDecThreads;
-    return sizeof(float) * ((S + 1) * kDecTile * RowLayout<D>::LD + 2 * ((KP * D + 3) & ~3) + ((D + 3) & ~3) +
-                            ((KP + 3) & ~3)) +
+    return sizeof(float) * ((S + 1) * kDecTile * RowLayout<D>::LD + 4 * ((KP * Pairs<D>::N + 1) & ~1) +
+                            ((KP * D + 3) & ~3) + ((D + 3) & ~3) + ((KP + 3) & ~3)) +
            sizeof(double) * (SCR + NV) + sizeof(uint64_t) * S;
 }
 template <int D, int KP>
@@ -567,7 +642,8 @@ constexpr size_t grad_tiled_smem() {
     constexpr int NW = kDecThreads / 32;
     constexpr int NSM = KP + 2;
     constexpr int scr = NW * NSM > kDecThreads ? NW * NSM : kDecThreads;
-    size_t bytes = sizeof(float) * ((S + 1) * kDecTile * RowLayout<D>::LD + kDecTile * KP + 2 * KP * D + D + KP) +
+    size_t bytes = sizeof(float) * ((S + 1) * kDecTile * RowLayout<D>::LD + kDecTile * KP + 4 * KP * Pairs<D>::N +
+                                    KP * D + D + KP) +
                    sizeof(double) * (scr + NSM + KP * D + 2 + KP) + sizeof(uint64_t) * S;
     // the ring buffer is reused for the [NW*G2][KP*D] float64 partials at the end
     const size_t part = sizeof(double) * NW * G2 * KP * D;
