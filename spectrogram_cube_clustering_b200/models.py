@@ -324,6 +324,88 @@ def gmm(z_array, n_clusters, means_init=None, weights_init=None):
     return labels, gm.means_
 
 
+# ----------------------------------------------------------------------------- DEC training loop
+def DEC_training(model, dataloader, optimizer, n_epochs, gamma=1e-3, tol=3e-3, update_interval_cfg=-1,
+                 device=None, labels_prev=None, fused_loss=True, log_every=0):
+    """DEC fine-tuning loop with the reference's cadence (``models.py:929-1231``) and none of its
+    host round trips:
+
+    * ``batch_eval`` fills a device latent buffer; q, labels and the label-change count come from one
+      fused pass, ``target_distribution`` runs on the device and p STAYS on the device (the reference
+      copies q to numpy, computes p there and re-uploads it slice by slice: ``models.py:89,1113-1114``);
+    * every ``update_interval = ceil(M / (2B))`` batches p is refreshed and the stop rule
+      ``delta_label < tol`` is evaluated (``models.py:985-989, 1093-1111``);
+    * per batch: ``loss = MSE(x_rec, x) + gamma * KL(p_batch || q) / B``, backward, optimizer step
+      (``models.py:1121-1128``).  ``fused_loss=True`` takes loss + dL/dz + dL/dmu from one
+      ``dec_kl_grad`` launch; ``False`` runs the literal ``KLDivLoss(log q, p)`` line through autograd;
+    * losses are accumulated on the device and read back once per epoch (the reference syncs three
+      scalars per batch: ``models.py:1131-1133``).
+
+    The dataloader must not shuffle (p is indexed by running offset, as in the reference).
+    Returns a history dict (per-epoch MSE / KLD / loss, deltas, whether the stop rule fired).
+    """
+    from .networks import dec_kl_loss
+    device = _device(device)
+    bsz = dataloader.batch_size
+    M = len(dataloader.dataset)
+    upd = int(np.ceil(M / (bsz * 2))) if update_interval_cfg == -1 else int(np.ceil(M / (bsz * update_interval_cfg)))
+    mse = torch.nn.MSELoss(reduction="mean")
+    kld = torch.nn.KLDivLoss(reduction="sum")
+    alpha = float(model.clustering.alpha)
+
+    def refresh():
+        buf, q, labels = batch_eval(dataloader, model, device, return_buffer=True)
+        p = ops.dec_target(q, ops.colsum(q), 5)
+        return p, labels
+
+    p, labels = refresh()
+    if labels_prev is None:
+        labels_prev = labels.clone()
+    else:
+        labels_prev = torch.as_tensor(labels_prev).to(device=device, dtype=torch.int32)
+    hist = dict(mse=[], kld=[], loss=[], deltas=[], finished=False, update_interval=upd)
+    finished = False
+    for epoch in range(n_epochs):
+        sums = torch.zeros(3, dtype=torch.float64, device=device)
+        running = 0
+        for batch_num, batch in enumerate(dataloader):
+            x = batch[0] if isinstance(batch, (list, tuple)) else batch
+            x = x.to(device, non_blocking=True)
+            if (batch_num % upd == 0) and not (batch_num == 0 and epoch == 0):
+                p, labels = refresh()
+                delta = float((labels != labels_prev).sum().item()) / labels.shape[0]
+                hist["deltas"].append(delta)
+                labels_prev = labels.clone()
+                if delta < tol:
+                    finished = True
+                    break
+            B = x.shape[0]
+            tar = p[running:running + B]
+            model.train()
+            optimizer.zero_grad(set_to_none=True)
+            z = model.encoder(x)
+            x_rec = model.decoder(z)
+            loss_rec = mse(x_rec, x)
+            if fused_loss:
+                loss_clust = dec_kl_loss(z, model.clustering.weights, tar, alpha, gamma / B)
+            else:
+                loss_clust = gamma * kld(torch.log(model.clustering(z)), tar) / B
+            loss = loss_rec + loss_clust
+            loss.backward()
+            optimizer.step()
+            running += B
+            sums += torch.stack([loss_rec.detach(), loss_clust.detach(), loss.detach()]).double() * B
+        if running:
+            tot = (sums / running).cpu().numpy()
+            hist["mse"].append(float(tot[0])); hist["kld"].append(float(tot[1])); hist["loss"].append(float(tot[2]))
+        if log_every and (epoch + 1) % log_every == 0:
+            print(f"epoch {epoch + 1}/{n_epochs}: " + ", ".join(f"{k}={hist[k][-1]:.4e}" for k in ("mse", "kld", "loss")))
+        if finished:
+            break
+    hist["finished"] = finished
+    return hist
+
+
 # ----------------------------------------------------------------------------- DEC refinement
 def dec_refine(buf: LatentBuffer, centroids, alpha=1.0, gamma=1e-3, lr=1e-3, tol=3e-3, max_steps=1000,
                round_decimals=5, update_every=1, betas=(0.9, 0.999), eps=1e-8):

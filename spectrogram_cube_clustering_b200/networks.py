@@ -51,6 +51,38 @@ class _SoftAssign(torch.autograd.Function):
         return gx, gw, None
 
 
+class _FusedKLLoss(torch.autograd.Function):
+    """scale * KL(p || softassign(z, weights)) with loss, dL/dz and dL/dweights from ONE launch
+    (``scc_dec_kl_grad``) — the fused form of ``gamma * KLDivLoss('sum')(log q, p) / B`` + backward
+    (``models.py:1124-1127``)."""
+
+    @staticmethod
+    def forward(ctx, z, weights, p, alpha, scale):
+        if not z.is_cuda:
+            raise SccError("dec_kl_loss needs CUDA tensors: the B200 path has no CPU fallback")
+        d = z.shape[1]
+        dp = ops.padded_dim(d)
+        z32 = _pad_cols(z.detach().to(torch.float32), dp).contiguous()
+        w32 = _pad_cols(weights.detach().to(device=z.device, dtype=torch.float32), dp).contiguous()
+        p32 = p.detach().to(device=z.device, dtype=torch.float32).contiguous()
+        stats, dz = ops.dec_kl_grad(z32, w32, alpha, p=p32, scale=scale, want_dz=True)
+        K = w32.shape[0]
+        ctx.save_for_backward(dz[:, :d].to(z.dtype), stats[2:].view(K, dp)[:, :d].to(weights.dtype))
+        return stats[0].to(z.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dz, dmu = ctx.saved_tensors
+        return grad_out * dz, grad_out * dmu, None, None, None
+
+
+def dec_kl_loss(z, weights, p, alpha=1.0, scale=1.0):
+    """Fused clustering loss: ``scale * sum_ij p_ij (log p_ij - log q_ij)`` with q recomputed from
+    (z, weights); differentiable w.r.t. z and weights.  ``scale = gamma / batch_size`` reproduces
+    ``models.py:1124-1125``."""
+    return _FusedKLLoss.apply(z, weights, p, float(alpha), float(scale))
+
+
 class ClusteringLayer(nn.Module):
     """Student's-t soft assignment (drop-in for ``Cluster.networks.ClusteringLayer``).
 

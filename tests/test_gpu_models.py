@@ -180,3 +180,67 @@ def test_batch_eval_matches_layerwise_eval():
     assert rel_err(z, zz.cpu().numpy()) < 1e-6
     assert np.abs(q - np.round(qq.cpu().numpy().astype(np.float64), 5)).max() <= 1.01e-5
     assert (labels != qq.argmax(1).cpu().numpy()).mean() < 2e-3
+
+
+def _reference_style_epoch(model, x, bsz, gamma, opt):
+    """The reference loop verbatim in torch (models.py:1015-1016, 1089-1128) for one epoch without
+    p refreshes: q via the layer, p on the host with numpy, literal KLDivLoss line."""
+    from oracle import dec as odec
+    dev = next(model.parameters()).device
+    model.eval()
+    with torch.no_grad():
+        q = torch.cat([model(x[i:i + bsz].to(dev))[0] for i in range(0, len(x), bsz)]).cpu().numpy()
+    p = odec.target_distribution(np.round(q.astype(np.float64), 5))
+    out = []
+    for i in range(0, len(x), bsz):
+        xb = x[i:i + bsz].to(dev)
+        tar = torch.from_numpy(p[i:i + bsz]).to(dev, torch.float32)
+        model.train(); opt.zero_grad()
+        qb, x_rec, _ = model(xb)
+        loss = torch.nn.MSELoss()(x_rec, xb) + gamma * torch.nn.KLDivLoss(reduction="sum")(torch.log(qb), tar) / xb.shape[0]
+        loss.backward(); opt.step()
+        out.append(loss.item())
+    return out
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_dec_training_epoch_matches_reference_style_loop(fused):
+    import copy
+    from spectrogram_cube_clustering_b200.networks import DEC
+    from spectrogram_cube_clustering_b200.models import DEC_training
+    from spectrogram_cube_clustering_b200 import synth
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(1)
+        model = DEC(n_clusters=5).cuda()
+        with torch.no_grad():
+            model.clustering.weights.mul_(0.3).add_(0.1)
+        ref_model = copy.deepcopy(model)
+        x = synth.spectrograms(2048)
+        bsz, gamma = 256, 1e-1
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        ref_opt = torch.optim.Adam(ref_model.parameters(), lr=1e-3)
+        loader = torch.utils.data.DataLoader(x, batch_size=bsz, shuffle=False)
+        hist = DEC_training(model, loader, opt, n_epochs=1, gamma=gamma, tol=0.0, update_interval_cfg=1,
+                            fused_loss=fused)           # update_interval = M/B batches: no refresh inside the epoch
+        ref_losses = _reference_style_epoch(ref_model, x, bsz, gamma, ref_opt)
+        assert hist["update_interval"] == 8 and len(hist["loss"]) == 1
+        assert abs(hist["loss"][0] - np.mean(ref_losses)) < 2e-4 * abs(np.mean(ref_losses))
+        w, wr = model.clustering.weights.detach().cpu().numpy(), ref_model.clustering.weights.detach().cpu().numpy()
+        assert rel_err(w, wr) < 2e-3                       # Adam amplifies 1e-6 gradient differences
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_fused_kl_loss_matches_literal_line():
+    from spectrogram_cube_clustering_b200.networks import ClusteringLayer, dec_kl_loss
+    g = load_golden("dec", "c1")
+    n = g["z"].shape[0]
+    z = torch.from_numpy(g["z"]).cuda().requires_grad_(True)
+    w = torch.nn.Parameter(torch.from_numpy(g["mu"]).cuda())
+    tar = torch.from_numpy(g["p"]).float().cuda()
+    loss = dec_kl_loss(z, w, tar, 1.0, float(g["gamma"]) / n) * 3.0
+    loss.backward()
+    assert abs(loss.item() / 3.0 - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    assert rel_err(z.grad.cpu().numpy() / 3.0, g["dz"]) < 1e-5 and rel_err(w.grad.cpu().numpy() / 3.0, g["dmu"]) < 1e-5
