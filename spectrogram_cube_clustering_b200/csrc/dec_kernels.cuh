@@ -34,8 +34,6 @@ __host__ __device__ constexpr int dec_stages() { return RowLayout<D>::kDense ? 4
 template <int D>
 struct Pairs { static constexpr int N = (D + 1) / 2; };
 
-__device__ __forceinline__ float2 splat2(float x) { return make_float2(x, x); }
-
 template <int D>
 __device__ __forceinline__ void pack_row(const float (&r)[D], float2 (&p)[Pairs<D>::N]) {
 #pragma unroll

@@ -1,0 +1,202 @@
+// gmm_api.cu — GMM entry points: finalize / pack kernels (dimension independent, float64) and the
+// per-dimension dispatch of the fused EM pass.
+#include "gmm_kernels.cuh"
+
+namespace scc {
+
+#define SCC_FOR_EACH_GMM_DIM(M) M(4) M(8) M(9) M(10) M(12) M(16) M(20) M(24) M(32)
+#define SCC_DECL(D_) int gmm_em_dim##D_(const GmmArgs& a, cudaStream_t st);
+SCC_FOR_EACH_GMM_DIM(SCC_DECL)
+#undef SCC_DECL
+
+// ---------------------------------------------------------------------------
+// finalize / pack: one CTA, warp k owns component k.  float64 throughout.
+// ---------------------------------------------------------------------------
+struct FinArgs {
+    const double* stats;       // FROM_STATS
+    const double* weights_in;  // !FROM_STATS
+    const double* cov_in;      // !FROM_STATS
+    double n_total, reg_covar, nk_add, tol;
+    int d, K;
+    double* means;             // in/out
+    double* weights;           // out (may be NULL in pack mode)
+    double* covariances;       // out (may be NULL in pack mode)
+    double* prec_chol;         // out, may be NULL
+    float* params;             // out
+    double* ctrl;
+};
+
+template <bool FROM_STATS>
+__global__ void __launch_bounds__(512, 1)
+gmm_finalize_kernel(const FinArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int d = a.d, K = a.K, LDA = d + 1, TRI = tri(d);
+    double* mats = reinterpret_cast<double*>(smem_raw);       // [K][d*LDA]  L below, Y^T above
+    __shared__ double nk_s[SCC_MAX_K];
+    __shared__ double logdet_s[SCC_MAX_K];
+    __shared__ int bad_s;
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    double* ctrl = a.ctrl;
+    if (FROM_STATS && ctrl[5] != 0.0) return;
+    if (threadIdx.x == 0) bad_s = 0;
+    __syncthreads();
+
+    if (k < K) {
+        double* A = mats + (size_t)k * d * LDA;
+        const int i = lane;                         // row owned by this lane
+        if constexpr (FROM_STATS) {
+            const double* N = a.stats + 1;
+            const double* S1 = a.stats + 1 + K;
+            const double* S2 = a.stats + 1 + K + (size_t)K * d;
+            const double nk = N[k] + a.nk_add;
+            if (lane == 0) nk_s[k] = nk;
+            if (i < d) {
+                const double di = S1[k * d + i] / nk;
+                for (int c = 0; c < d; ++c) {
+                    const double dc = S1[k * d + c] / nk;
+                    const int lo = i < c ? i : c, hi = i < c ? c : i;
+                    double v = S2[(size_t)k * TRI + tri(hi) + lo] / nk - di * dc;
+                    if (c == i) v += a.reg_covar;
+                    A[i * LDA + c] = v;
+                    a.covariances[((size_t)k * d + i) * d + c] = v;
+                }
+                a.means[k * d + i] += di;
+            }
+        } else {
+            if (lane == 0) nk_s[k] = a.weights_in[k];
+            if (i < d)
+                for (int c = 0; c < d; ++c) A[i * LDA + c] = a.cov_in[((size_t)k * d + i) * d + c];
+        }
+        __syncwarp();
+        // Cholesky, lower, in place (left-looking; lane i owns row i)
+        bool ok = true;
+        for (int j = 0; j < d; ++j) {
+            double s = 0.0;
+            if (i >= j && i < d) {
+                s = A[i * LDA + j];
+                for (int c = 0; c < j; ++c) s -= A[i * LDA + c] * A[j * LDA + c];
+            }
+            const double piv = __shfl_sync(0xffffffffu, s, j);
+            if (!(piv > 0.0)) { ok = false; break; }
+            const double root = sqrt(piv);
+            if (i == j) A[i * LDA + j] = root;
+            else if (i > j && i < d) A[i * LDA + j] = s / root;
+            __syncwarp();
+        }
+        if (!ok) {
+            if (lane == 0) atomicMax(&bad_s, k + 1);
+        } else {
+            // Y = L^-1 (lower triangular), lane c owns column c (forward substitution).  Y[r][c], r > c,
+            // is parked in the strict UPPER triangle at A[c][r]; Y[c][c] = 1 / L[c][c].  The upper
+            // triangle of A with the diagonal inverted is then exactly U = L^-T.
+            const int c = lane;
+            if (c < d) {
+                const double ycc = 1.0 / A[c * LDA + c];
+                for (int r = c + 1; r < d; ++r) {
+                    double acc = A[r * LDA + c] * ycc;
+                    for (int m = c + 1; m < r; ++m) acc += A[r * LDA + m] * A[c * LDA + m];
+                    A[c * LDA + r] = -acc / A[r * LDA + r];
+                }
+            }
+            __syncwarp();
+            double ld = (i < d) ? -log(A[i * LDA + i]) : 0.0;          // log det U = -sum log L_ii
+            ld = warp_sum(ld);
+            if (lane == 0) logdet_s[k] = ld;
+            if (i < d) {
+                for (int b = 0; b < d; ++b) {
+                    const double u = (i < b) ? A[i * LDA + b] : ((i == b) ? 1.0 / A[i * LDA + i] : 0.0);   // U[i][b]
+                    if (a.prec_chol) a.prec_chol[((size_t)k * d + i) * d + b] = u;
+                    if (i <= b) a.params[(size_t)K * d + (size_t)k * TRI + tri(b) + i] = (float)u;
+                }
+                a.params[k * d + i] = (float)a.means[k * d + i];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int j = 0; j < K; ++j) tot += nk_s[j];
+        if (bad_s == 0) {
+            for (int j = 0; j < K; ++j) {
+                const double w = nk_s[j] / tot;
+                if (a.weights) a.weights[j] = w;
+                a.params[(size_t)K * d + (size_t)K * TRI + j] =
+                    (float)(logdet_s[j] + log(w) - 0.5 * d * 1.8378770664093453 /* log(2 pi) */);
+            }
+        }
+        if constexpr (FROM_STATS) {
+            const double lower = a.stats[0] / a.n_total;
+            const double prev = ctrl[0];
+            ctrl[1] = prev; ctrl[0] = lower; ctrl[2] += 1.0;
+            if (bad_s) { ctrl[4] = (double)bad_s; ctrl[5] = 1.0; }
+            else if (fabs(lower - prev) < a.tol) { ctrl[3] = 1.0; ctrl[5] = 1.0; }
+        } else {
+            ctrl[0] = -INFINITY; ctrl[1] = -INFINITY; ctrl[2] = 0.0; ctrl[3] = 0.0;
+            ctrl[4] = (double)bad_s; ctrl[5] = bad_s ? 1.0 : 0.0; ctrl[6] = 0.0; ctrl[7] = 0.0;
+        }
+    }
+}
+
+
+bool gmm_supported(int d, int K) {
+    if (K < 1 || K > SCC_MAX_K) return false;
+#define SCC_SUP(D_) if (d == D_) return true;
+    SCC_FOR_EACH_GMM_DIM(SCC_SUP)
+#undef SCC_SUP
+    return false;
+}
+
+int gmm_em_step(const float* z, int64_t n, int d, int K, const float* params, double* stats,
+                int32_t* labels, float* resp, const double* ctrl, int mode,
+                void* ws, size_t ws_bytes, cudaStream_t st) {
+    if ((!z && n > 0) || !params || !stats || n < 0) return SCC_ERR_INVALID;
+    if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return SCC_ERR_INVALID;
+    if (mode < 0 || mode > 2) return SCC_ERR_INVALID;
+    if (!gmm_supported(d, K)) return SCC_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(z) & 15u) != 0) return SCC_ERR_MISALIGNED;
+    if (!ws || ws_bytes < workspace_bytes(d, K)) return SCC_ERR_WORKSPACE;
+    if (n == 0) { SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * SCC_GMM_STAT_DOUBLES(K, d), st)); return SCC_OK; }
+    GmmArgs a{};
+    a.z = z; a.n = n; a.K = K; a.params = params; a.labels = labels; a.resp = resp; a.ctrl = ctrl;
+    a.accumulate = mode; a.stats = stats;
+    a.counter = reinterpret_cast<unsigned int*>(ws);
+    a.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + kWorkspaceHeader);
+#define SCC_CASE(D_) if (d == D_) return gmm_em_dim##D_(a, st);
+    SCC_FOR_EACH_GMM_DIM(SCC_CASE)
+#undef SCC_CASE
+    return SCC_ERR_UNSUPPORTED;
+}
+
+static size_t finalize_smem(int d, int K) { return sizeof(double) * (size_t)K * d * (d + 1); }
+
+int gmm_finalize(const double* stats, double n_total, int d, int K, double reg_covar, double nk_eps, double tol,
+                 double* means, double* weights, double* covariances, double* prec_chol, float* params,
+                 double* ctrl, cudaStream_t st) {
+    if (!stats || !means || !weights || !covariances || !params || !ctrl) return SCC_ERR_INVALID;
+    if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K || !(n_total > 0)) return SCC_ERR_INVALID;
+    FinArgs a{};
+    a.stats = stats; a.n_total = n_total; a.reg_covar = reg_covar; a.nk_add = nk_eps; a.tol = tol;
+    a.d = d; a.K = K; a.means = means; a.weights = weights; a.covariances = covariances;
+    a.prec_chol = prec_chol; a.params = params; a.ctrl = ctrl;
+    const size_t smem = finalize_smem(d, K);
+    SCC_CUDA(cudaFuncSetAttribute(gmm_finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gmm_finalize_kernel<true><<<1, 512, smem, st>>>(a);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
+
+int gmm_pack_params(const double* weights, const double* means, const double* covariances, int d, int K,
+                    double* prec_chol, float* params, double* ctrl, cudaStream_t st) {
+    if (!weights || !means || !covariances || !params || !ctrl) return SCC_ERR_INVALID;
+    if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return SCC_ERR_INVALID;
+    FinArgs a{};
+    a.weights_in = weights; a.cov_in = covariances; a.d = d; a.K = K;
+    a.means = const_cast<double*>(means); a.prec_chol = prec_chol; a.params = params; a.ctrl = ctrl;
+    const size_t smem = finalize_smem(d, K);
+    SCC_CUDA(cudaFuncSetAttribute(gmm_finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gmm_finalize_kernel<false><<<1, 512, smem, st>>>(a);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
+
+}  // namespace scc

@@ -1,0 +1,487 @@
+// gmm_kernels.cuh — fused full-covariance EM pass for sm_100a (FP32 CUDA cores).
+//
+//   gmm_em_full_kernel<D,KP>   one read of z per EM iteration                     (d <= 12)
+//       phase 1: one thread per point — Cholesky log-likelihoods for all K components
+//                (sklearn _gaussian_mixture.py:490-553), log-sum-exp responsibilities
+//                (_base.py:552-582), labels; r_ik parked in shared memory
+//       phase 2: one warp per component — the lanes sweep the tile's points and keep the
+//                1 + d + d(d+1)/2 moments of "their" component in registers, centred on
+//                the current mean (sklearn _gaussian_mixture.py:282-320,168-197)
+//
+// FP32-FMA-bound, not HBM-bound: ~K(d^2+4d) FMA per point against 4d bytes.
+// (A constant-bank + FFMA2 E-step was tried in round 1 and measured 27 % SLOWER at d=9, K=16 —
+//  LDCU parameter loads take the same issue slots the shared-memory broadcasts did and the pair
+//  accumulators spill under the 128-register cap of a 512-thread CTA)
+#pragma once
+
+#include "scc_common.cuh"
+#include "scc_launch.h"
+
+namespace scc {
+
+struct GmmArgs {
+    const float* z;
+    int64_t n;
+    int K;
+    const float* params;       // mu[K*D], U[K*TRI], cst[K]
+    int32_t* labels;
+    float* resp;
+    const double* ctrl;
+    int accumulate;            // 0 E-step only, 1 soft EM, 2 hard (one-hot) responsibilities
+    double* stats;
+    double* partials;
+    unsigned int* counter;
+};
+
+__host__ __device__ constexpr int tri(int d) { return d * (d + 1) / 2; }
+
+// ---------------------------------------------------------------------------
+// FULL variant
+// ---------------------------------------------------------------------------
+template <int D, int KP>
+__global__ void __launch_bounds__(32 * KP, 1)
+gmm_em_full_kernel(const GmmArgs a) {
+    constexpr int NT = 32 * KP;
+    constexpr int TILE = NT;
+    constexpr int S = 3;
+    constexpr int TRI = tri(D);
+    constexpr int NM = 1 + D + TRI;                      // moments per component
+    constexpr int FLUSH = 16;                            // tiles between float -> double flushes
+    using Ring = ZRing<D, TILE, S, NT>;
+    using L = RowLayout<D>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring_buf = reinterpret_cast<float*>(smem_raw);
+    float* r_s = ring_buf + S * Ring::kTileFloats;       // [KP][TILE]
+    float* mu_s = r_s + KP * TILE;                       // [KP*D]
+    float* u_s = mu_s + ((KP * D + 3) & ~3);             // [KP*TRI]
+    float* cst_s = u_s + ((KP * TRI + 3) & ~3);          // [KP]
+    double* mom_s = reinterpret_cast<double*>(cst_s + ((KP + 3) & ~3));   // [KP][NM]
+    double* ll_s = mom_s + KP * NM;                      // [KP] per-warp log-likelihood
+    double* cta_stats = ll_s + KP;                       // [1 + K + K*D + K*TRI]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + 1 + KP * NM);
+
+    if (a.ctrl && a.ctrl[5] != 0.0) return;              // frozen fit: converged or failed earlier
+
+    const int K = a.K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < KP * D; i += NT) mu_s[i] = (i < K * D) ? a.params[i] : 0.f;
+    for (int i = threadIdx.x; i < KP * TRI; i += NT) u_s[i] = (i < K * TRI) ? a.params[K * D + i] : 0.f;
+    if (threadIdx.x < KP) cst_s[threadIdx.x] = ((int)threadIdx.x < K) ? a.params[K * D + K * TRI + threadIdx.x] : 0.f;
+    for (int i = threadIdx.x; i < KP * NM; i += NT) mom_s[i] = 0.0;
+
+    Ring ring;
+    ring.init(ring_buf, bars, a.z, a.n);
+    __syncthreads();
+    const int G = gridDim.x;
+    for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
+    __syncthreads();
+
+    // phase-2 state of this warp's component
+    const int kc = warp;
+    float muk[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) muk[c] = mu_s[kc * D + c];
+    float mom[NM];
+#pragma unroll
+    for (int s = 0; s < NM; ++s) mom[s] = 0.f;
+    float loglik = 0.f;
+
+    auto flush = [&]() {
+        if (kc < K) {
+#pragma unroll
+            for (int s = 0; s < NM; ++s) {
+                const float w = warp_sum(mom[s]);
+                if (lane == 0) mom_s[kc * NM + s] += (double)w;
+                mom[s] = 0.f;
+            }
+        }
+    };
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G, ++it) {
+        const int stage = it % S;
+        ring.wait(stage, tile, (uint32_t)(it / S));
+        const int np = ring.points(tile);
+        const float* ztile = ring.stage_ptr(stage);
+        // ---------------- phase 1: E-step for point threadIdx.x ----------------
+        {
+            const bool active = (int)threadIdx.x < np;
+            float lp[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) lp[k] = 0.f;
+            float lse = 0.f;
+            int label = 0;
+            if (active) {
+                float x[D];
+                load_row<D>(ztile, threadIdx.x, x);
+                float best = -3.4e38f;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    lp[k] = -3.4e38f;
+                    if (k < K) {
+                        float df[D];
+#pragma unroll
+                        for (int c = 0; c < D; ++c) df[c] = x[c] - mu_s[k * D + c];
+                        float m = 0.f;
+#pragma unroll
+                        for (int b = 0; b < D; ++b) {
+                            float y = 0.f;
+#pragma unroll
+                            for (int c = 0; c <= b; ++c) y = fmaf(df[c], u_s[k * TRI + tri(b) + c], y);
+                            m = fmaf(y, y, m);
+                        }
+                        lp[k] = fmaf(-0.5f, m, cst_s[k]);
+                        if (lp[k] > best) { best = lp[k]; label = k; }
+                    }
+                }
+                float se = 0.f;
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (k < K) se += expf(lp[k] - best);
+                lse = best + logf(se);
+                loglik += lse;
+            }
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                float r = (active && k < K) ? expf(lp[k] - lse) : 0.f;
+                if (a.accumulate == SCC_GMM_HARD) r = (active && k == label) ? 1.f : 0.f;
+                r_s[k * TILE + threadIdx.x] = r;
+                lp[k] = r;
+            }
+            if (active) {
+                const size_t i = (size_t)tile * TILE + threadIdx.x;
+                if (a.labels) a.labels[i] = label;
+                if (a.resp) {
+#pragma unroll
+                    for (int k = 0; k < KP; ++k)
+                        if (k < K) a.resp[i * K + k] = lp[k];
+                }
+            }
+        }
+        __syncthreads();
+        // ---------------- phase 2: moments of component kc over the tile ----------------
+        if (a.accumulate && kc < K) {
+            for (int t = lane; t < np; t += 32) {
+                const float r = r_s[kc * TILE + t];
+                float df[D];
+                load_row<D>(ztile, t, df);
+#pragma unroll
+                for (int c = 0; c < D; ++c) df[c] -= muk[c];
+                mom[0] += r;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    const float w = r * df[c];
+                    mom[1 + c] += w;
+#pragma unroll
+                    for (int b = c; b < D; ++b)                      // S2[c][b], c <= b, column-packed
+                        mom[1 + D + tri(b) + c] = fmaf(w, df[b], mom[1 + D + tri(b) + c]);
+                }
+            }
+            if ((it + 1) % FLUSH == 0) flush();
+        }
+        __syncthreads();
+        ring.issue(stage, tile + S * G);
+    }
+    if (a.accumulate) flush();
+    {
+        const float w = warp_sum(loglik);
+        if (lane == 0) ll_s[warp] = (double)w;
+    }
+    __syncthreads();
+    // pack CTA statistics with the true K: [ll, N_k[K], S1[K*D], S2[K*TRI]]
+    const int NS = 1 + K * NM;
+    for (int s = threadIdx.x; s < NS; s += NT) {
+        double v;
+        if (s == 0) {
+            v = 0.0;
+            for (int w = 0; w < KP; ++w) v += ll_s[w];
+        } else if (s < 1 + K) {
+            v = mom_s[(s - 1) * NM];
+        } else if (s < 1 + K + K * D) {
+            const int o = s - 1 - K, k = o / D, c = o - k * D;
+            v = mom_s[k * NM + 1 + c];
+        } else {
+            const int o = s - 1 - K - K * D, k = o / TRI, e = o - k * TRI;
+            v = mom_s[k * NM + 1 + D + e];
+        }
+        cta_stats[s] = v;
+    }
+    __syncthreads();
+    // per-CTA slot; the host-side launcher follows up with reduce_partials_kernel (fixed order)
+    for (int s = threadIdx.x; s < NS; s += NT) a.partials[(size_t)blockIdx.x * NS + s] = cta_stats[s];
+}
+
+template <int D, int KP>
+constexpr size_t gmm_full_smem() {
+    constexpr int NT = 32 * KP, TILE = NT, S = 3, TRI = tri(D), NM = 1 + D + TRI;
+    return sizeof(float) * (S * TILE * RowLayout<D>::LD + KP * TILE + ((KP * D + 3) & ~3) + ((KP * TRI + 3) & ~3) +
+                            ((KP + 3) & ~3)) +
+           sizeof(double) * (KP * NM + KP + 1 + KP * NM) + sizeof(uint64_t) * S;
+}
+
+template <int D, int KP>
+static int launch_gmm_full(const GmmArgs& a, cudaStream_t st) {
+    constexpr int NT = 32 * KP;
+    auto kern = gmm_em_full_kernel<D, KP>;
+    const size_t smem = gmm_full_smem<D, KP>();
+    const int64_t tiles = (a.n + NT - 1) / NT;
+    int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), NT, smem, 2);
+    if (grid < 0) return (int)grid;
+    if (grid > kMaxGmmGrid) grid = kMaxGmmGrid;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, NT, smem, st>>>(a);
+    SCC_CUDA(cudaGetLastError());
+    const int NS = SCC_GMM_STAT_DOUBLES(a.K, D);
+    reduce_partials_kernel<<<(NS + 255) / 256, 256, 0, st>>>(a.partials, NS, (int)grid, a.stats, a.ctrl);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// BLOCK variant (d % 4 == 0, d >= 16): the 1 + d + d(d+1)/2 moments of a component no longer fit
+// one thread's registers, so phase 2 tiles the symmetric second moment into 4x4 register blocks:
+// a "unit" is (component k, row block ab, column block bb >= ab); the K * NB2 units are dealt to
+// the CTA's threads and every thread sweeps ALL points of the tile for its units (r broadcast,
+// two LDS.128 of the centred point, 4 FMUL + 16 FMA).  Diagonal units also carry S1 (and unit
+// (0,0) S0).  Partials are flushed from fp32 registers straight into the CTA's float64 slot.
+// ---------------------------------------------------------------------------
+template <int D, int KP>
+struct GmmBlock {
+    static constexpr int NT = 256, TILE = 256, S = 2;
+    static constexpr int NBLK = D / 4;
+    static constexpr int NB2 = NBLK * (NBLK + 1) / 2;
+    static constexpr int MAXU = (KP * NB2 + NT - 1) / NT;      // units per thread
+    static constexpr int TRI = D * (D + 1) / 2;
+    static constexpr int NM = 1 + D + TRI;
+};
+
+template <int D, int KP>
+__global__ void __launch_bounds__(256, 1)
+gmm_em_block_kernel(const GmmArgs a) {
+    using B = GmmBlock<D, KP>;
+    using L = RowLayout<D>;
+    constexpr int NT = B::NT, TILE = B::TILE, S = B::S, TRI = B::TRI, NM = B::NM, NBLK = B::NBLK, NB2 = B::NB2;
+    constexpr int MAXU = B::MAXU;
+    constexpr int FLUSH = 8;
+    using Ring = ZRing<D, TILE, S, NT>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring_buf = reinterpret_cast<float*>(smem_raw);
+    float* r_s = ring_buf + S * Ring::kTileFloats;       // [TILE][KP]
+    float* mu_s = r_s + TILE * KP;                       // [KP*D]
+    float* u_s = mu_s + KP * D;                          // [KP*TRI]
+    float* cst_s = u_s + ((KP * TRI + 3) & ~3);          // [KP]
+    double* ll_s = reinterpret_cast<double*>(cst_s + ((KP + 3) & ~3));   // [NT/32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ll_s + NT / 32);
+
+    if (a.ctrl && a.ctrl[5] != 0.0) return;
+
+    const int K = a.K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < KP * D; i += NT) mu_s[i] = (i < K * D) ? a.params[i] : 0.f;
+    for (int i = threadIdx.x; i < KP * TRI; i += NT) u_s[i] = (i < K * TRI) ? a.params[K * D + i] : 0.f;
+    if (threadIdx.x < KP) cst_s[threadIdx.x] = ((int)threadIdx.x < K) ? a.params[K * D + K * TRI + threadIdx.x] : 0.f;
+    const int NS = 1 + K * NM;
+    double* slot = a.partials + (size_t)blockIdx.x * NS;
+    for (int i = threadIdx.x; i < NS; i += NT) slot[i] = 0.0;
+
+    Ring ring;
+    ring.init(ring_buf, bars, a.z, a.n);
+    __syncthreads();
+    const int G = gridDim.x;
+#pragma unroll
+    for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
+    __syncthreads();
+
+    // this thread's units
+    int uk[MAXU], ua[MAXU], ub[MAXU];
+    float mua[MAXU][4], mub[MAXU][4];
+    float acc[MAXU][16], s1[MAXU][4], s0[MAXU];
+    const int nunits = K * NB2;
+#pragma unroll
+    for (int m = 0; m < MAXU; ++m) {
+        const int u = threadIdx.x + m * NT;
+        int k = -1, ab = 0, bb = 0;
+        if (u < nunits) {
+            k = u / NB2;
+            int e = u - k * NB2;                       // row-major over the upper block triangle
+            while (e >= NBLK - ab) { e -= NBLK - ab; ++ab; }
+            bb = ab + e;
+        }
+        uk[m] = k; ua[m] = ab; ub[m] = bb;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            mua[m][c] = (k >= 0) ? mu_s[k * D + 4 * ab + c] : 0.f;
+            mub[m][c] = (k >= 0) ? mu_s[k * D + 4 * bb + c] : 0.f;
+            s1[m][c] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[m][e] = 0.f;
+        s0[m] = 0.f;
+    }
+    float loglik = 0.f;
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int m = 0; m < MAXU; ++m) {
+            if (uk[m] >= 0) {
+                double* dst = slot + 1;                 // [N_k[K] | S1[K*D] | S2[K*TRI]]
+                const int k = uk[m], ab = ua[m], bb = ub[m];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int ra = 4 * ab + r, cb = 4 * bb + c;
+                        if (ra <= cb) dst[K + K * D + k * TRI + cb * (cb + 1) / 2 + ra] += (double)acc[m][4 * r + c];
+                        acc[m][4 * r + c] = 0.f;
+                    }
+                if (ab == bb) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { dst[K + k * D + 4 * ab + r] += (double)s1[m][r]; s1[m][r] = 0.f; }
+                    if (ab == 0) { dst[k] += (double)s0[m]; s0[m] = 0.f; }
+                }
+            }
+        }
+    };
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G, ++it) {
+        const int stage = it % S;
+        ring.wait(stage, tile, (uint32_t)(it / S));
+        const int np = ring.points(tile);
+        const float* ztile = ring.stage_ptr(stage);
+        // ---------------- phase 1: E-step for point threadIdx.x ----------------
+        {
+            const bool active = (int)threadIdx.x < np;
+            float lp[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) lp[k] = 0.f;
+            float lse = 0.f;
+            int label = 0;
+            if (active) {
+                float x[D];
+                load_row<D>(ztile, threadIdx.x, x);
+                float best = -3.4e38f;
+#pragma unroll 1
+                for (int k = 0; k < K; ++k) {
+                    float df[D];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) df[c] = x[c] - mu_s[k * D + c];
+                    const float* uk_s = u_s + k * TRI;
+                    float m = 0.f;
+#pragma unroll
+                    for (int b = 0; b < D; ++b) {
+                        float y = 0.f;
+#pragma unroll
+                        for (int c = 0; c <= b; ++c) y = fmaf(df[c], uk_s[tri(b) + c], y);
+                        m = fmaf(y, y, m);
+                    }
+                    const float v = fmaf(-0.5f, m, cst_s[k]);
+                    r_s[threadIdx.x * KP + k] = v;             // park log-probabilities (dynamic k)
+                    if (v > best) { best = v; label = k; }
+                }
+#pragma unroll
+                for (int k = 0; k < KP; ++k) lp[k] = (k < K) ? r_s[threadIdx.x * KP + k] : -3.4e38f;
+                float se = 0.f;
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (k < K) se += expf(lp[k] - best);
+                lse = best + logf(se);
+                loglik += lse;
+            }
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                float r = (active && k < K) ? expf(lp[k] - lse) : 0.f;
+                if (a.accumulate == SCC_GMM_HARD) r = (active && k == label) ? 1.f : 0.f;
+                lp[k] = r;
+            }
+#pragma unroll
+            for (int k = 0; k < KP; k += 4)
+                *reinterpret_cast<float4*>(r_s + threadIdx.x * KP + k) = make_float4(lp[k], lp[k + 1], lp[k + 2], lp[k + 3]);
+            if (active) {
+                const size_t i = (size_t)tile * TILE + threadIdx.x;
+                if (a.labels) a.labels[i] = label;
+                if (a.resp) {
+#pragma unroll
+                    for (int k = 0; k < KP; ++k)
+                        if (k < K) a.resp[i * K + k] = lp[k];
+                }
+            }
+        }
+        __syncthreads();
+        // ---------------- phase 2: 4x4 moment blocks over all points of the tile ----------------
+        if (a.accumulate) {
+            for (int t = 0; t < np; ++t) {
+                const float* row = ztile + t * L::LD;
+#pragma unroll
+                for (int m = 0; m < MAXU; ++m) {
+                    if (uk[m] >= 0) {
+                        const float r = r_s[t * KP + uk[m]];
+                        const float4 xa = *reinterpret_cast<const float4*>(row + 4 * ua[m]);
+                        const float4 xb = *reinterpret_cast<const float4*>(row + 4 * ub[m]);
+                        const float da[4] = {xa.x - mua[m][0], xa.y - mua[m][1], xa.z - mua[m][2], xa.w - mua[m][3]};
+                        const float db[4] = {xb.x - mub[m][0], xb.y - mub[m][1], xb.z - mub[m][2], xb.w - mub[m][3]};
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const float w = r * da[rr];
+                            s1[m][rr] += w;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) acc[m][4 * rr + c] = fmaf(w, db[c], acc[m][4 * rr + c]);
+                        }
+                        s0[m] += r;
+                    }
+                }
+            }
+            if ((it + 1) % FLUSH == 0) flush();
+        }
+        __syncthreads();
+        ring.issue(stage, tile + S * G);
+    }
+    if (a.accumulate) flush();
+    {
+        const float w = warp_sum(loglik);
+        if (lane == 0) ll_s[warp] = (double)w;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < NT / 32; ++w) v += ll_s[w];
+        slot[0] = v;
+    }
+}
+
+template <int D, int KP>
+constexpr size_t gmm_block_smem() {
+    using B = GmmBlock<D, KP>;
+    return sizeof(float) * (B::S * B::TILE * RowLayout<D>::LD + B::TILE * KP + KP * D + ((KP * B::TRI + 3) & ~3) +
+                            ((KP + 3) & ~3)) +
+           sizeof(double) * (B::NT / 32) + sizeof(uint64_t) * B::S;
+}
+
+template <int D, int KP>
+static int launch_gmm_block(const GmmArgs& a, cudaStream_t st) {
+    using B = GmmBlock<D, KP>;
+    auto kern = gmm_em_block_kernel<D, KP>;
+    constexpr size_t smem = gmm_block_smem<D, KP>();
+    const int64_t tiles = (a.n + B::TILE - 1) / B::TILE;
+    int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), B::NT, smem, 1);
+    if (grid < 0) return (int)grid;
+    if (grid > kMaxGmmGrid) grid = kMaxGmmGrid;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, B::NT, smem, st>>>(a);
+    SCC_CUDA(cudaGetLastError());
+    const int NS = SCC_GMM_STAT_DOUBLES(a.K, D);
+    reduce_partials_kernel<<<(NS + 255) / 256, 256, 0, st>>>(a.partials, NS, (int)grid, a.stats, a.ctrl);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
+
+template <int D, int KP>
+static int launch_gmm(const GmmArgs& a, cudaStream_t st) {
+    if constexpr (D <= 12) return launch_gmm_full<D, KP>(a, st);
+    else return launch_gmm_block<D, KP>(a, st);
+}
+
+}  // namespace scc

@@ -55,7 +55,7 @@ size_t workspace_bytes(int d, int K) {
     if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return 0;
     const size_t dec = (size_t)kMaxDecGrid * (size_t)(K * d + 2 + K);
     const size_t gmm = (size_t)kMaxGmmGrid * (size_t)SCC_GMM_STAT_DOUBLES(K, d);
-    return kWorkspaceHeader + sizeof(double) * (dec > gmm ? dec : gmm);
+    return kWorkspaceHeader + sizeof(double) * (dec > gmm ? dec : gmm) + (size_t)(64 << 10);   // + staged GMM params
 }
 
 }  // namespace scc

@@ -283,6 +283,8 @@ reduce_partials_kernel(const double* __restrict__ partials, int S, int G, double
     out[s] = (a0 + a1) + (a2 + a3);
 }
 
+__device__ __forceinline__ float2 splat2(float x) { return make_float2(x, x); }
+
 __device__ __forceinline__ float round_dec5(float x) {
     // np.round(x, 5): rint (half-to-even) of x * 1e5, scaled back.
     return rintf(x * 100000.0f) * 1.0e-5f;
