@@ -227,20 +227,24 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
     __threadfence();
     const int G = gridDim.x;
     if (S <= NT) {
+        // 16 independent loads in flight per thread (the chain is L2-latency bound), summed in a
+        // fixed order
         const int R = NT / S;
         const int s = tid % S, r = tid / S;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double acc = 0.0;
         if (r < R) {
-            int b = r;
-            for (; b + 3 * R < G; b += 4 * R) {
-                a0 += __ldcg(partials + (size_t)b * S + s);
-                a1 += __ldcg(partials + (size_t)(b + R) * S + s);
-                a2 += __ldcg(partials + (size_t)(b + 2 * R) * S + s);
-                a3 += __ldcg(partials + (size_t)(b + 3 * R) * S + s);
+            for (int b = r; b < G; b += 16 * R) {
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int bb = b + u * R;
+                    v[u] = (bb < G) ? __ldcg(partials + (size_t)bb * S + s) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc += v[u];
             }
-            for (; b < G; b += R) a0 += __ldcg(partials + (size_t)b * S + s);
         }
-        scratch[tid] = (a0 + a1) + (a2 + a3);
+        scratch[tid] = acc;
         __syncthreads();
         if (tid < S) {
             double t = 0.0;
@@ -249,14 +253,15 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
         }
     } else {
         for (int s = tid; s < S; s += NT) {
-            double a0 = 0.0, a1 = 0.0;
-            int b = 0;
-            for (; b + 1 < G; b += 2) {
-                a0 += __ldcg(partials + (size_t)b * S + s);
-                a1 += __ldcg(partials + (size_t)(b + 1) * S + s);
+            double acc = 0.0;
+            for (int b = 0; b < G; b += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (b + u < G) ? __ldcg(partials + (size_t)(b + u) * S + s) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += v[u];
             }
-            if (b < G) a0 += __ldcg(partials + (size_t)b * S + s);
-            out[s] = a0 + a1;
+            out[s] = acc;
         }
     }
     if (tid == 0) *counter = 0u;
