@@ -189,9 +189,27 @@ def run_gpu(args):
                          st2=torch.empty(K * D + 2, dtype=torch.float64, device=dev)))
     scale = GAMMA / n_total
 
+    exchange = None
+    if world > 1 and not args.nccl:
+        try:
+            from spectrogram_cube_clustering_b200.latent_buffer import PeerExchange
+            exchange = PeerExchange(group, dev, 1 + 16 + 16 * D + 16 * (D * (D + 1) // 2))
+            chk = torch.arange(K * D + 2, dtype=torch.float64, device=dev) * (rank + 1)
+            ref = chk.clone(); dist.all_reduce(ref, group=group)
+            exchange.all_reduce(chk)
+            torch.cuda.synchronize()
+            assert torch.equal(chk, ref), "peer exchange disagrees with NCCL"
+            dbg("peer exchange verified against NCCL")
+        except Exception as exc:
+            print(f"[bench] peer-memory exchange unavailable ({exc!r}); using NCCL all_reduce", file=sys.stderr)
+            exchange = None
+
     def allreduce(t):
         if world > 1:
-            dist.all_reduce(t, group=group)
+            if exchange is not None:
+                exchange.all_reduce(t)
+            else:
+                dist.all_reduce(t, group=group)
 
     def k_assign(s):
         ops.dec_assign(s["z"], mu, ALPHA, 5, out_q=s["q"], out_labels=s["labels"], out_stats=s["st1"])
@@ -368,13 +386,15 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_points_per_gpu": N_PER_GPU, "n_points_total": n_total, "d": D,
                        "K": K, "alpha": ALPHA, "gamma": GAMMA, "round_decimals": 5,
-                       "parallelism": f"latent points sharded over {world} GPU(s); packed f64 stat all-reduce x2/step"
+                       "parallelism": (f"latent points sharded over {world} GPU(s); packed f64 stat all-reduce x2/step via "
+                                       + ("one-shot NVLink peer-memory exchange kernel" if exchange is not None else "NCCL"))
                                       if world > 1 else "single GPU",
                        "launch": "CUDA graph replay per step" if use_graphs else "eager launches",
                        "l2": f"inputs/outputs rotate over {N_SETS} sets ({N_SETS * 140} MB) > 126 MB L2",
                        "timing": "CUDA events around the K steps, max over ranks; per-kernel durations from "
                                  "CUDA events in a second pass with the launch queue pre-loaded"},
-            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": 3 * args.steps, "roofline": roofline,
+            "clocks": sampler.summary(), "e2e": e2e,
+            "gpu_launches": (3 + (2 if exchange is not None else 0)) * args.steps, "roofline": roofline,
             "cpu_baseline": cpu, "extra": extra,
         }
         print(json.dumps(line), flush=True)
@@ -468,6 +488,7 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="use NCCL all_reduce instead of the peer-memory exchange")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -233,6 +233,25 @@ int scc_gmm_pack_params(const double* weights, const double* means,
                         double* prec_chol, float* params, double* ctrl,
                         scc_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * Multi-GPU exchange of the packed statistics (one process per GPU, one NVSwitch box)
+ * ------------------------------------------------------------------------- */
+
+/*
+ * One-shot all-reduce(sum) of a float64 vector over NVLink peer memory, in one small kernel
+ * (the reference has no multi-GPU path; this is the exchange step SURVEY.md 8e names: f_j,
+ * loss + dL/dmu, N_k / sum r z / sum r zz^T).
+ *   peer_windows: DEVICE array of `world` pointers, entry r = rank r's exchange window mapped into
+ *                 this process (symmetric allocation of scc_peer_window_bytes(max_len) bytes,
+ *                 zero-filled once before first use, same max_len on every rank).
+ *   Every rank must call with the same len in the same order; the result (summed in rank order)
+ *   is bit-identical on all ranks.  local and out may alias.
+ */
+size_t scc_peer_window_bytes(int max_len);
+int scc_peer_allreduce(const double* local, int len, double* out,
+                       void* const* peer_windows, int rank, int world, int max_len,
+                       scc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,8 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "scc_kmeans_step": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_size_t, c_void_p]),
+    "scc_peer_window_bytes": (c_size_t, [c_int]),
+    "scc_peer_allreduce": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "scc_gmm_em_step": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "scc_gmm_finalize": (c_int, [c_void_p, c_double, c_int, c_int, c_double, c_double, c_double, c_void_p,

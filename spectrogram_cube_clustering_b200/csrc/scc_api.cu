@@ -125,6 +125,13 @@ int scc_kmeans_step(const float* z, int64_t n, int d, const float* centers, int 
                             (cudaStream_t)stream);
 }
 
+size_t scc_peer_window_bytes(int max_len) { return scc::peer_window_bytes(max_len); }
+
+int scc_peer_allreduce(const double* local, int len, double* out, void* const* peer_windows, int rank, int world,
+                       int max_len, scc_stream_t stream) {
+    return scc::peer_allreduce(local, len, out, peer_windows, rank, world, max_len, (cudaStream_t)stream);
+}
+
 int scc_gmm_em_step(const float* z, int64_t n, int d, int K, const float* params, double* stats, int32_t* labels,
                     float* resp, const double* ctrl, int mode, void* workspace,
                     size_t workspace_bytes, scc_stream_t stream) {

@@ -77,6 +77,10 @@ int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float
 int kmeans_step(const float* z, int64_t n, int d, const float* centers, int K, int32_t* labels, float* mindist,
                 double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t peer_window_bytes(int max_len);
+int peer_allreduce(const double* local, int len, double* out, void* const* windows_dev, int rank, int world,
+                   int max_len, cudaStream_t st);
+
 int gmm_em_step(const float* z, int64_t n, int d, int K, const float* params, double* stats,
                 int32_t* labels, float* resp, const double* ctrl, int mode,
                 void* ws, size_t ws_bytes, cudaStream_t st);

@@ -218,6 +218,21 @@ def gmm_finalize(stats, n_total, means, weights, covariances, prec_chol, params,
     _lib.check(rc, "scc_gmm_finalize")
 
 
+# --------------------------------------------------------------------------- multi-GPU exchange
+def peer_window_bytes(max_len: int) -> int:
+    return int(_lib.load().scc_peer_window_bytes(int(max_len)))
+
+
+def peer_allreduce(t: torch.Tensor, windows: torch.Tensor, rank: int, world: int, max_len: int) -> torch.Tensor:
+    """In-place one-shot all-reduce(sum) of a float64 vector over NVLink peer memory."""
+    lib = _lib.load()
+    _require(t, "t", torch.float64)
+    rc = lib.scc_peer_allreduce(t.data_ptr(), t.numel(), t.data_ptr(), windows.data_ptr(), int(rank), int(world),
+                                int(max_len), _stream())
+    _lib.check(rc, "scc_peer_allreduce")
+    return t
+
+
 # --------------------------------------------------------------------------- torch.library registration
 def _register_custom_ops():
     """Expose the launches as PyTorch custom ops (torch.ops.scc_b200.*)."""
