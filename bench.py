@@ -319,8 +319,19 @@ def run_gpu(args):
     dominant = max(kavg, key=kavg.get)
     achieved = alg_bytes[dominant] * N_PER_GPU / (kavg[dominant] * 1e-3) / 1e9
     step_bytes = sum(alg_bytes.values())
+    traffic = None
+    try:          # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)
+        traffic = tr.get({"dec_assign": "dec_assign_kernel", "dec_target": "dec_target_kernel",
+                          "dec_kl_grad": "dec_grad_reg_kernel"}[dominant])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic,
+                "traffic_note": "ncu cold-cache capture (profiles/r01_ncu_dec.txt); dz/p written by the kernel are still "
+                                "in the 126 MB L2 when it ends, so DRAM writes are below the algorithmic store bytes",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_point": alg_bytes[dominant],
                 "kernels_ms": kavg,
                 "kernels_gbs": {k: alg_bytes[k] * N_PER_GPU / (kavg[k] * 1e-3) / 1e9 for k in kavg},
