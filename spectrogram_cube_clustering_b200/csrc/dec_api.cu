@@ -134,7 +134,7 @@ static int check_common(const float* z, int64_t n, int d, const float* mu, int K
                         void* ws, size_t ws_bytes) {
     if ((!z && n > 0) || !mu || !stats || n < 0 || !(alpha > 0.f)) return SCC_ERR_INVALID;
     if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return SCC_ERR_INVALID;
-    if (n > (int64_t)kDecTile * 2147483647LL) return SCC_ERR_INVALID;
+    if (n > (int64_t)kDecTile * 1000000000LL) return SCC_ERR_INVALID;
     if (!dec_supported(d, K)) return SCC_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(z) & 15u) != 0) return SCC_ERR_MISALIGNED;
     if (!ws || ws_bytes < workspace_bytes(d, K)) return SCC_ERR_WORKSPACE;

@@ -23,7 +23,7 @@ constexpr int kDecThreads = 256;
 constexpr int kDecTile = 256;
 
 template <int D>
-__host__ __device__ constexpr int dec_stages() { return RowLayout<D>::kDense ? 4 : 2; }
+__host__ __device__ constexpr int dec_stages() { return RowLayout<D>::kDense ? 4 : (RowLayout<D>::kVec4 ? 3 : 2); }
 
 // ---------------------------------------------------------------------------
 // Packed FP32 (sm_100 FFMA2 / FADD2 / FMUL2): two lanes of a float2 per instruction.  On B200 a
@@ -135,14 +135,72 @@ __device__ __forceinline__ void cta_reduce(const float (&v)[NV], double* scratch
 }
 
 // ---------------------------------------------------------------------------
+// P rows per thread sharing every centroid load: the centroid broadcasts (one LDS.64/128 per pair)
+// are what saturates first at large K*d (LSU pipe: 1 wavefront/clk/SM against 4 FP32 warp-instr/clk),
+// so register-blocking P = 2 points halves the shared-memory traffic per point.
+// ---------------------------------------------------------------------------
+template <int D, int KP, bool EXACT, bool ALPHA1, int P>
+__device__ __forceinline__ void soft_assign_rows(const float2 (&z2)[P][Pairs<D>::N], const float2* __restrict__ nmu2_s,
+                                                 int K, float inv_alpha, float expo, float (&u)[P][KP],
+                                                 float (&q)[P][KP], int (&label)[P], float (&best)[P]) {
+    constexpr int DP2 = Pairs<D>::N;
+    float tsum[P];
+#pragma unroll
+    for (int r = 0; r < P; ++r) { tsum[r] = 0.f; best[r] = 3.4e38f; label[r] = 0; }
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+#pragma unroll
+        for (int r = 0; r < P; ++r) { u[r][j] = 0.f; q[r][j] = 0.f; }
+        if (EXACT || j < K) {
+            float2 acc2[P];
+#pragma unroll
+            for (int r = 0; r < P; ++r) acc2[r] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < DP2; ++c) {
+                const float2 m = nmu2_s[j * DP2 + c];
+#pragma unroll
+                for (int r = 0; r < P; ++r) {
+                    const float2 df = __fadd2_rn(z2[r][c], m);
+                    acc2[r] = __ffma2_rn(df, df, acc2[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < P; ++r) {
+                const float acc = acc2[r].x + acc2[r].y;
+                if (acc < best[r]) { best[r] = acc; label[r] = j; }
+                const float uu = __fdividef(1.f, ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f));
+                const float t = ALPHA1 ? uu : __powf(uu, expo);
+                u[r][j] = uu; q[r][j] = t; tsum[r] += t;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < P; ++r) {
+        const float inv = __fdividef(1.f, tsum[r]);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) q[r][j] *= inv;
+    }
+}
+
+// points per thread of the assign pass (tile = 256 * P points)
+template <int D, int KP>
+__host__ __device__ constexpr int assign_ppt() { return (KP * D <= 96) ? 2 : 1; }
+template <int D, int KP>
+__host__ __device__ constexpr int assign_stages() {
+    return RowLayout<D>::kDense ? (assign_ppt<D, KP>() == 2 ? 3 : 4) : (RowLayout<D>::kVec4 ? 3 : 2);
+}
+
+// ---------------------------------------------------------------------------
 // dec_assign
 // ---------------------------------------------------------------------------
 template <int D, int KP, bool EXACT, bool ALPHA1>
 __global__ void __launch_bounds__(kDecThreads)
 dec_assign_kernel(const DecArgs a) {
-    constexpr int S = dec_stages<D>();
+    constexpr int P = assign_ppt<D, KP>();
+    constexpr int TILE = kDecTile * P;
+    constexpr int S = assign_stages<D, KP>();
     constexpr int NW = kDecThreads / 32;
-    using Ring = ZRing<D, kDecTile, S, kDecThreads>;
+    using Ring = ZRing<D, TILE, S, kDecThreads>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring_buf = reinterpret_cast<float*>(smem_raw);
     constexpr int DP2 = Pairs<D>::N;
@@ -173,28 +231,40 @@ dec_assign_kernel(const DecArgs a) {
     for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
         ring.wait(stage, tile, use);
         const int np = ring.points(tile);
-        const bool active = (int)threadIdx.x < np;
-        float zr[D];
-        if (active) load_row<D>(ring.stage_ptr(stage), threadIdx.x, zr);
+        float2 z2[P][DP2];
+        bool active[P];
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+            const int t = threadIdx.x + r * kDecThreads;
+            active[r] = t < np;
+            float zr[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) zr[c] = 0.f;
+            if (active[r]) load_row<D>(ring.stage_ptr(stage), t, zr);
+            pack_row<D>(zr, z2[r]);
+        }
         __syncthreads();
         ring.issue(stage, tile + S * G);
-        if (active) {
-            const size_t i = (size_t)tile * kDecTile + threadIdx.x;
-            float u[KP], q[KP];
-            float2 z2[DP2];
-            pack_row<D>(zr, z2);
-            int label;
-            float best;
-            soft_assign_row<D, KP, EXACT, ALPHA1>(z2, nmu2_s, K, inv_alpha, expo, u, q, label, best);
-            if (round5) {
+        if (active[0]) {
+            float u[P][KP], q[P][KP];
+            int label[P];
+            float best[P];
+            soft_assign_rows<D, KP, EXACT, ALPHA1, P>(z2, nmu2_s, K, inv_alpha, expo, u, q, label, best);
 #pragma unroll
-                for (int j = 0; j < KP; ++j) q[j] = round_dec5(q[j]);
+            for (int r = 0; r < P; ++r) {
+                if (active[r]) {
+                    const size_t i = (size_t)tile * TILE + threadIdx.x + r * kDecThreads;
+                    if (round5) {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) q[r][j] = round_dec5(q[r][j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) facc[j] += q[r][j];
+                    if (a.q) store_krow<KP, EXACT>(a.q + i * K, K, q[r]);
+                    if (a.labels) a.labels[i] = label[r];
+                    if (a.labels_prev) facc[KP] += (a.labels_prev[i] != label[r]) ? 1.f : 0.f;
+                }
             }
-#pragma unroll
-            for (int j = 0; j < KP; ++j) facc[j] += q[j];
-            if (a.q) store_krow<KP, EXACT>(a.q + i * K, K, q);
-            if (a.labels) a.labels[i] = label;
-            if (a.labels_prev) facc[KP] += (a.labels_prev[i] != label) ? 1.f : 0.f;
         }
         if (++stage == S) { stage = 0; ++use; }
     }
@@ -616,10 +686,10 @@ dec_grad_tiled_kernel(const DecArgs a) {
 // ---------------------------------------------------------------------------
 template <int D, int KP>
 constexpr size_t assign_smem() {
-    constexpr int S = dec_stages<D>();
+    constexpr int S = assign_stages<D, KP>();
     constexpr int NW = kDecThreads / 32;
     constexpr int scr = NW * (KP + 1) > kDecThreads ? NW * (KP + 1) : kDecThreads;
-    return sizeof(float) * (S * kDecTile * RowLayout<D>::LD + 2 * ((KP * Pairs<D>::N + 1) & ~1)) +
+    return sizeof(float) * (S * kDecTile * assign_ppt<D, KP>() * RowLayout<D>::LD + 2 * ((KP * Pairs<D>::N + 1) & ~1)) +
            sizeof(double) * (scr + (KP + 1)) + sizeof(uint64_t) * S;
 }
 template <int D, int KP>
@@ -651,8 +721,8 @@ constexpr size_t grad_tiled_smem() {
 }
 
 template <typename Kern>
-static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t stream) {
-    const int64_t num_tiles = (args.n + kDecTile - 1) / kDecTile;
+static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t stream, int tile_points = kDecTile) {
+    const int64_t num_tiles = (args.n + tile_points - 1) / tile_points;
     int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), kDecThreads, smem, kMaxCtasPerSm);
     if (grid < 0) return (int)grid;
     if (grid > kMaxDecGrid) grid = kMaxDecGrid;
@@ -668,10 +738,11 @@ struct DecOps {
     static int assign(const DecArgs& a, cudaStream_t st) {
         const bool exact = a.K == KP, a1 = a.alpha == 1.0f;
         constexpr size_t smem = assign_smem<D, KP>();
-        if (exact && a1) return launch_dec(dec_assign_kernel<D, KP, true, true>, a, smem, st);
-        if (exact) return launch_dec(dec_assign_kernel<D, KP, true, false>, a, smem, st);
-        if (a1) return launch_dec(dec_assign_kernel<D, KP, false, true>, a, smem, st);
-        return launch_dec(dec_assign_kernel<D, KP, false, false>, a, smem, st);
+        constexpr int tp = kDecTile * assign_ppt<D, KP>();
+        if (exact && a1) return launch_dec(dec_assign_kernel<D, KP, true, true>, a, smem, st, tp);
+        if (exact) return launch_dec(dec_assign_kernel<D, KP, true, false>, a, smem, st, tp);
+        if (a1) return launch_dec(dec_assign_kernel<D, KP, false, true>, a, smem, st, tp);
+        return launch_dec(dec_assign_kernel<D, KP, false, false>, a, smem, st, tp);
     }
     template <int MODE, bool EXACT, bool A1>
     static int grad_inst(const DecArgs& a, cudaStream_t st) {

@@ -105,6 +105,15 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// Ampere-style asynchronous 16-byte global -> shared copy (LDGSTS), used for the padded row layouts
+// that a dense TMA bulk copy cannot produce.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -154,35 +163,47 @@ struct ZRing {
     __device__ __forceinline__ int points(int tile) const { return tile == num_tiles - 1 ? last_points : TILE; }
     __device__ __forceinline__ float* stage_ptr(int stage) const { return buf + stage * kTileFloats; }
 
+    // padded float4 layouts are filled with cp.async (one commit group per issue() call per thread)
+    static constexpr bool kCpAsync = L::kVec4 && !L::kDense;
+
     // Called by ALL threads at the same program point.
     __device__ __forceinline__ void issue(int stage, int tile) {
-        if (tile >= num_tiles) return;
-        float* dst = stage_ptr(stage);
-        const float* src = z + (size_t)tile * (TILE * D);
-        const int np = points(tile);
-        if (L::kDense && np == TILE) {
-            if (threadIdx.x == 0) {
-                mbar_expect_tx(&bar[stage], kTileBytes);
-                bulk_g2s(dst, src, kTileBytes, &bar[stage]);
-            }
-        } else if constexpr (L::kVec4) {
-            const int nvec = np * (D / 4);
-            const float4* src4 = reinterpret_cast<const float4*>(src);
-            for (int v = threadIdx.x; v < nvec; v += NT) {
-                const int row = v / (D / 4), c4 = v - row * (D / 4);
-                *reinterpret_cast<float4*>(dst + row * L::LD + 4 * c4) = ldg_stream4(src4 + v);
-            }
-        } else {
-            const int nf = np * D;
-            for (int f = threadIdx.x; f < nf; f += NT) {
-                const int row = f / D, c = f - row * D;
-                dst[row * L::LD + c] = ldg_stream(src + f);
+        if (tile < num_tiles) {
+            float* dst = stage_ptr(stage);
+            const float* src = z + (size_t)tile * (TILE * D);
+            const int np = points(tile);
+            if (L::kDense && np == TILE) {
+                if (threadIdx.x == 0) {
+                    mbar_expect_tx(&bar[stage], kTileBytes);
+                    bulk_g2s(dst, src, kTileBytes, &bar[stage]);
+                }
+            } else if constexpr (L::kVec4) {
+                const int nvec = np * (D / 4);
+                const float4* src4 = reinterpret_cast<const float4*>(src);
+                for (int v = threadIdx.x; v < nvec; v += NT) {
+                    const int row = v / (D / 4), c4 = v - row * (D / 4);
+                    if constexpr (kCpAsync) cp_async16(dst + row * L::LD + 4 * c4, src4 + v);
+                    else *reinterpret_cast<float4*>(dst + row * L::LD + 4 * c4) = ldg_stream4(src4 + v);
+                }
+            } else {
+                const int nf = np * D;
+                for (int f = threadIdx.x; f < nf; f += NT) {
+                    const int row = f / D, c = f - row * D;
+                    dst[row * L::LD + c] = ldg_stream(src + f);
+                }
             }
         }
+        if constexpr (kCpAsync) cp_async_commit();        // empty groups keep the per-thread count aligned
     }
     // use_index = how many times this stage has been consumed before (i / STAGES).
+    // After wait() returns, every thread may read any row of the stage.
     __device__ __forceinline__ void wait(int stage, int tile, uint32_t use_index) {
-        if (L::kDense && points(tile) == TILE) mbar_wait(&bar[stage], use_index & 1u);
+        if constexpr (kCpAsync) {
+            cp_async_wait<STAGES - 1>();                  // this thread's copies of the oldest stage landed
+            __syncthreads();                              // ... and everybody else's
+        } else {
+            if (L::kDense && points(tile) == TILE) mbar_wait(&bar[stage], use_index & 1u);
+        }
     }
 };
 
