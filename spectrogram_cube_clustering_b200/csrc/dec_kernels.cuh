@@ -50,7 +50,7 @@ __device__ __forceinline__ void soft_assign_row(const float2 (&z2)[Pairs<D>::N],
                                                 int K, float inv_alpha, float expo, float (&u)[KP], float (&q)[KP],
                                                 int& label, float& best) {
     constexpr int DP2 = Pairs<D>::N;
-    float tsum = 0.f;
+    float tsum[2] = {0.f, 0.f};               // two chains: short serial dependencies matter at 4 warps/scheduler
     best = 3.4e38f;
     label = 0;
 #pragma unroll
@@ -67,10 +67,10 @@ __device__ __forceinline__ void soft_assign_row(const float2 (&z2)[Pairs<D>::N],
             if (acc < best) { best = acc; label = j; }          // argmax q == argmin distance, first wins
             const float uu = __fdividef(1.f, ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f));
             const float t = ALPHA1 ? uu : __powf(uu, expo);
-            u[j] = uu; q[j] = t; tsum += t;
+            u[j] = uu; q[j] = t; tsum[j & 1] += t;
         }
     }
-    const float inv = __fdividef(1.f, tsum);
+    const float inv = __fdividef(1.f, tsum[0] + tsum[1]);
 #pragma unroll
     for (int j = 0; j < KP; ++j) q[j] *= inv;
 }
@@ -314,16 +314,17 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
                 if (a.round5) p[j] = round_dec5(p[j]);
             }
         }
-        float s = 0.f, l = 0.f;
+        float s2[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
             if (EXACT || j < K) {
-                s += p[j];
+                s2[j & 1] += p[j];
                 // xlogy(p,p) - p log q ; 0 when p == 0 (torch KLDivLoss); NaN targets still propagate
                 const float term = p[j] * __log2f(__fdividef(p[j], q[j]));
-                l += (p[j] == 0.f) ? 0.f : term;
+                l2[j & 1] += (p[j] == 0.f) ? 0.f : term;
             }
         }
+        const float s = s2[0] + s2[1], l = l2[0] + l2[1];
 #pragma unroll
         for (int j = 0; j < KP; ++j) coef[j] = (EXACT || j < K) ? (p[j] - q[j] * s) * u[j] * cscale : 0.f;
         loss = fmaf(l, 0.693147180559945f, loss); ssum += s;
@@ -481,9 +482,10 @@ dec_grad_reg_kernel(const DecArgs a) {
             float best;
             soft_assign_row<D, KP, EXACT, ALPHA1>(z2, nmu2_s, K, inv_alpha, expo, u, q, label, best);
             grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, label, best, coef, sm[0], sm[1]);
-            float csum = 0.f;
+            float cs2[2] = {0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < KP; ++j) { sm[2 + j] += coef[j]; csum += coef[j]; }
+            for (int j = 0; j < KP; ++j) { sm[2 + j] += coef[j]; cs2[j & 1] += coef[j]; }
+            const float csum = cs2[0] + cs2[1];
 #pragma unroll
             for (int c = 0; c < DP2; ++c) z2[c] = __fadd2_rn(z2[c], nc0[c]);       // centred point
 #pragma unroll
