@@ -1,0 +1,72 @@
+"""Property tests of the CUDA path: invariants that hold at any size, checked at the
+BASELINE configs' full sizes where no oracle run is affordable."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from spectrogram_cube_clustering_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("n,d,K", [(1_000_000, 9, 8), (2_000_003, 32, 16), (300_001, 16, 5)])
+def test_full_size_invariants(ops, n, d, K):
+    from spectrogram_cube_clustering_b200 import synth
+    z, mu = synth.latent_points(n, d, K, device="cuda", rank=11)
+    q, labels, st = ops.dec_assign(z, mu, 1.0, 0)
+    # rows of q sum to 1; f is the column sum of q; labels are the arg max
+    torch.testing.assert_close(q.sum(1), torch.ones(n, device="cuda"), atol=2e-6, rtol=0)
+    torch.testing.assert_close(st[:K], q.double().sum(0), rtol=1e-7, atol=0)   # per-thread fp32 partial sums
+    assert torch.equal(labels.long(), q.argmax(1)) or (labels.long() != q.argmax(1)).float().mean() < 1e-5
+    p = ops.dec_target(q, st, 0)
+    torch.testing.assert_close(p.sum(1), torch.ones(n, device="cuda"), atol=2e-6, rtol=0)
+    stats, dz = ops.dec_kl_grad(z, mu, 1.0, p=p, scale=1e-3 / n)
+    dmu = stats[2:].view(K, d)
+    # translation invariance of the loss: sum_i dL/dz_i = - sum_j dL/dmu_j
+    lhs, rhs = dz.double().sum(0), -dmu.sum(0)
+    assert (lhs - rhs).abs().max() <= 1e-4 * dmu.abs().max() * K
+    assert stats[0].item() >= -1e-12 and abs(stats[1].item() - n) < 1e-4 * n     # KL >= 0, sum_i s_i = N
+    # API mode (p from global memory) and fused mode (p rebuilt from f) agree
+    stats_f, dz_f = ops.dec_kl_grad(z, mu, 1.0, f=st, scale=1e-3 / n)
+    assert abs(stats_f[0].item() - stats[0].item()) <= 1e-5 * abs(stats[0].item())
+    assert (stats_f[2:] - stats[2:]).abs().max() <= 1e-5 * stats[2:].abs().max()
+    assert (dz_f - dz).abs().max() <= 1e-5 * dz.abs().max()
+    # determinism: a second launch reproduces every statistic bit for bit
+    _, _, st2 = ops.dec_assign(z, mu, 1.0, 0, want_q=False, want_labels=False)
+    assert torch.equal(st[:K], st2[:K])
+
+
+def test_cluster_permutation_equivariance(ops):
+    from spectrogram_cube_clustering_b200 import synth
+    z, mu = synth.latent_points(50_000, 9, 8, device="cuda", rank=12)
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4], device="cuda")
+    q, lab, st = ops.dec_assign(z, mu, 1.0, 0)
+    qp, labp, stp = ops.dec_assign(z, mu[perm].contiguous(), 1.0, 0)
+    torch.testing.assert_close(qp, q[:, perm], atol=1e-7, rtol=1e-6)
+    torch.testing.assert_close(stp[:8], st[:8][perm], rtol=1e-7, atol=0)
+    inv = torch.empty_like(perm); inv[perm] = torch.arange(8, device="cuda")
+    assert (inv[lab.long()] != labp.long()).float().mean() < 1e-4
+
+
+def test_gmm_statistics_invariants_full_size(ops):
+    """N_k sum to N, sum_k S1-weighted means are consistent, lower bound increases over EM iterations."""
+    from spectrogram_cube_clustering_b200 import synth
+    n, d, K = 2_000_000, 9, 16
+    z, _ = synth.latent_points(n, d, K, device="cuda", rank=13)
+    w0, mu0, cov0 = synth.gmm_initial_state(d, K, "cuda")
+    params, pchol, ctrl = ops.gmm_pack_params(w0, mu0, cov0)
+    means, weights, cov = mu0.clone(), w0.clone(), cov0.clone()
+    lbs = []
+    for _ in range(6):
+        stats = ops.gmm_em_step(z, K, params, ctrl=ctrl)
+        assert abs(stats[1:1 + K].sum().item() - n) < 1e-6 * n
+        ops.gmm_finalize(stats, n, means, weights, cov, pchol, params, ctrl, tol=0.0)
+        lbs.append(ctrl[0].item())
+    assert abs(weights.sum().item() - 1.0) < 1e-12
+    assert all(b >= a - 1e-6 for a, b in zip(lbs, lbs[1:])), lbs          # EM never decreases the bound
+    evals = torch.linalg.eigvalsh(cov)
+    assert (evals > 0).all()
