@@ -220,10 +220,28 @@ def run_gpu(args):
     def k_grad(s):
         ops.dec_kl_grad(s["z"], mu, ALPHA, p=s["p"], scale=scale, out_dz=s["dz"], out_stats=s["st2"])
 
+    fused_ex = exchange is not None and not args.unfused_exchange
+
     def step(s):
-        k_assign(s); allreduce(s["st1"]); k_target(s); k_grad(s); allreduce(s["st2"])
+        if fused_ex:        # collectives ride on the kernels: push in the producers' tails, pull in the consumers
+            ex = exchange.desc
+            ops.dec_assign(s["z"], mu, ALPHA, 5, out_q=s["q"], out_labels=s["labels"], out_stats=s["st1"], push=ex)
+            ops.dec_target(s["q"], s["st1"], 5, out=s["p"], pull=ex)
+            ops.dec_kl_grad(s["z"], mu, ALPHA, p=s["p"], scale=scale, out_dz=s["dz"], out_stats=s["st2"], push=ex)
+            ops.peer_finish(s["st2"], ex)
+        else:
+            k_assign(s); allreduce(s["st1"]); k_target(s); k_grad(s); allreduce(s["st2"])
 
     dbg('inputs ready')
+    if fused_ex:            # one fused step must reproduce the NCCL-reduced statistics
+        s0 = sets[0]
+        k_assign(s0); f_ref = s0["st1"].clone(); dist.all_reduce(f_ref, group=group)
+        ops.dec_target(s0["q"], f_ref, 5, out=s0["p"]); k_grad(s0); g_ref = s0["st2"].clone(); dist.all_reduce(g_ref, group=group)
+        step(s0)
+        torch.cuda.synchronize()
+        assert torch.equal(s0["st1"], f_ref), "fused exchange: column sums differ from NCCL"
+        assert torch.allclose(s0["st2"], g_ref, rtol=1e-12, atol=0), "fused exchange: gradient statistics differ from NCCL"
+        dbg("fused exchange verified against NCCL")
     # warm-up (eager): also creates workspaces and primes NCCL
     for w in range(max(args.warmup, 3)):
         step(sets[w % N_SETS])
@@ -350,11 +368,18 @@ def run_gpu(args):
     def e2e_step(i):
         zd.copy_(zh[i % 2], non_blocking=True)
         mud.copy_(mu_h, non_blocking=True)
-        ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"])
-        allreduce(sd["st1"])
-        ops.dec_target(sd["q"], sd["st1"], 5, out=sd["p"])
-        ops.dec_kl_grad(zd, mud, ALPHA, p=sd["p"], scale=scale, out_dz=sd["dz"], out_stats=sd["st2"])
-        allreduce(sd["st2"])
+        if fused_ex:
+            ex = exchange.desc
+            ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"], push=ex)
+            ops.dec_target(sd["q"], sd["st1"], 5, out=sd["p"], pull=ex)
+            ops.dec_kl_grad(zd, mud, ALPHA, p=sd["p"], scale=scale, out_dz=sd["dz"], out_stats=sd["st2"], push=ex)
+            ops.peer_finish(sd["st2"], ex)
+        else:
+            ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"])
+            allreduce(sd["st1"])
+            ops.dec_target(sd["q"], sd["st1"], 5, out=sd["p"])
+            ops.dec_kl_grad(zd, mud, ALPHA, p=sd["p"], scale=scale, out_dz=sd["dz"], out_stats=sd["st2"])
+            allreduce(sd["st2"])
         res_h[:K * D + 2].copy_(sd["st2"], non_blocking=True)
         res_h[K * D + 2:].copy_(sd["st1"], non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the caller reads loss / dmu on the host
@@ -398,14 +423,16 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "n_points_per_gpu": N_PER_GPU, "n_points_total": n_total, "d": D,
                        "K": K, "alpha": ALPHA, "gamma": GAMMA, "round_decimals": 5,
                        "parallelism": (f"latent points sharded over {world} GPU(s); packed f64 stat all-reduce x2/step via "
-                                       + ("one-shot NVLink peer-memory exchange kernel" if exchange is not None else "NCCL"))
+                                       + (("NVLink peer-memory exchange fused into the kernels (push in the producer's "
+                                           "last CTA, pull in the consumer's prologue)" if fused_ex else
+                                           "one-shot NVLink peer-memory exchange kernel") if exchange is not None else "NCCL"))
                                       if world > 1 else "single GPU",
                        "launch": "CUDA graph replay per step" if use_graphs else "eager launches",
                        "l2": f"inputs/outputs rotate over {N_SETS} sets ({N_SETS * 140} MB) > 126 MB L2",
                        "timing": "CUDA events around the K steps, max over ranks; per-kernel durations from "
                                  "CUDA events in a second pass with the launch queue pre-loaded"},
             "clocks": sampler.summary(), "e2e": e2e,
-            "gpu_launches": (3 + (2 if exchange is not None else 0)) * args.steps, "roofline": roofline,
+            "gpu_launches": (3 + ((1 if fused_ex else 2) if exchange is not None else 0)) * args.steps, "roofline": roofline,
             "cpu_baseline": cpu, "extra": extra,
         }
         print(json.dumps(line), flush=True)
@@ -500,6 +527,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nccl", action="store_true", help="use NCCL all_reduce instead of the peer-memory exchange")
+    ap.add_argument("--unfused-exchange", action="store_true", help="stand-alone exchange kernels instead of fused push/pull")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

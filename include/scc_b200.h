@@ -248,6 +248,32 @@ int scc_gmm_pack_params(const double* weights, const double* means,
  *   is bit-identical on all ranks.  local and out may alias.
  */
 size_t scc_peer_window_bytes(int max_len);
+
+/*
+ * Fused form: the exchange rides on the kernels that produce / consume the statistics, so a sharded
+ * DEC step is  assign_ex(push) -> target_ex(pull) -> kl_grad_ex(push) -> peer_finish  — four launches,
+ * no separate collective.  `push`: the LAST thread block of the statistics kernel ships the reduced
+ * vector to every rank's window and raises the sequence flag (peer stores over NVLink in the same
+ * kernel as the compute).  `pull`: the consuming kernel waits for the world's flags in its prologue
+ * and sums the slots in rank order.  Every push must be matched by exactly one pull (target_ex /
+ * kl_grad_ex with pull_f / scc_peer_finish) on every rank before the next-but-one push.
+ */
+typedef struct scc_exchange {
+    void* const* windows;   /* DEVICE array of `world` window pointers (see scc_peer_allreduce) */
+    int rank, world, max_len;
+} scc_exchange;
+
+int scc_dec_assign_ex(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
+                      float* q, int32_t* labels, const int32_t* labels_prev, double* stats,
+                      void* workspace, size_t workspace_bytes, const scc_exchange* push, scc_stream_t stream);
+/* f [K+1] receives the all-reduced column sums and label-change count when `pull` is given */
+int scc_dec_target_ex(const float* q, int64_t n, int K, double* f, int round_decimals, float* p,
+                      const scc_exchange* pull, scc_stream_t stream);
+int scc_dec_kl_grad_ex(const float* z, int64_t n, int d, const float* mu, int K, float alpha,
+                       const float* p, const double* f_cols, int round_decimals, float scale, float* dz,
+                       double* stats, void* workspace, size_t workspace_bytes,
+                       const scc_exchange* pull_f, const scc_exchange* push, scc_stream_t stream);
+int scc_peer_finish(double* out, int len, const scc_exchange* ex, scc_stream_t stream);
 int scc_peer_allreduce(const double* local, int len, double* out,
                        void* const* peer_windows, int rank, int world, int max_len,
                        scc_stream_t stream);

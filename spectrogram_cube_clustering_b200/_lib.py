@@ -41,6 +41,11 @@ _FP = POINTER(c_float)
 _DP = POINTER(c_double)
 _IP = POINTER(c_int32)
 
+class SccExchange(ctypes.Structure):
+    """Mirror of ``scc_exchange`` (include/scc_b200.h)."""
+    _fields_ = [("windows", c_void_p), ("rank", c_int), ("world", c_int), ("max_len", c_int)]
+
+
 _SIGNATURES = {
     "scc_abi_version": (c_int, []),
     "scc_status_string": (c_char_p, [c_int]),
@@ -59,6 +64,12 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "scc_kmeans_step": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_size_t, c_void_p]),
+    "scc_dec_assign_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "scc_dec_target_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "scc_dec_kl_grad_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int,
+                                   c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "scc_peer_finish": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "scc_peer_window_bytes": (c_size_t, [c_int]),
     "scc_peer_allreduce": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "scc_gmm_em_step": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -17,10 +17,17 @@ SCC_FOR_EACH_DIM(SCC_DECL_DIM, 0)
 // ---------------------------------------------------------------------------
 template <int LPR>
 __global__ void __launch_bounds__(256)
-dec_target_kernel(const float* __restrict__ q, int64_t n, int K, const double* __restrict__ f,
-                  int round5, float* __restrict__ p) {
+dec_target_kernel(const float* __restrict__ q, int64_t n, int K, double* __restrict__ f,
+                  int round5, float* __restrict__ p, PeerCtx pull) {
     __shared__ float inv_f[SCC_MAX_K];
-    if (threadIdx.x < K) inv_f[threadIdx.x] = (float)(1.0 / f[threadIdx.x]);
+    if (pull.windows) {                 // f comes from the exchange pushed by the preceding assign kernel
+        __shared__ double f_pull[SCC_MAX_K + 1];
+        peer_pull(pull, f_pull, K + 1);
+        if (threadIdx.x < K) inv_f[threadIdx.x] = (float)(1.0 / f_pull[threadIdx.x]);
+        if (blockIdx.x == 0 && (int)threadIdx.x <= K) f[threadIdx.x] = f_pull[threadIdx.x];   // publish the sums
+    } else if (threadIdx.x < K) {
+        inv_f[threadIdx.x] = (float)(1.0 / f[threadIdx.x]);
+    }
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     if constexpr (LPR > 0) {
@@ -99,7 +106,8 @@ int colsum(const float* q, int64_t n, int K, double* f, void* ws, size_t ws_byte
 }
 
 
-int dec_target(const float* q, int64_t n, int K, const double* f, int round_decimals, float* p, cudaStream_t st) {
+int dec_target(const float* q, int64_t n, int K, double* f, int round_decimals, float* p, cudaStream_t st,
+               const ExchangeDesc* pull) {
     if (!q || !f || !p || n < 0 || K < 1 || K > SCC_MAX_K) return SCC_ERR_INVALID;
     if (round_decimals != 0 && round_decimals != 5) return SCC_ERR_INVALID;
     if (n == 0) return SCC_OK;
@@ -113,10 +121,12 @@ int dec_target(const float* q, int64_t n, int K, const double* f, int round_deci
     const int64_t cap = (int64_t)sms * 8;
     if (grid > cap) grid = cap;
     const int r5 = round_decimals == 5;
-    if (vec && K == 4) dec_target_kernel<1><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p);
-    else if (vec && K == 8) dec_target_kernel<2><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p);
-    else if (vec && K == 16) dec_target_kernel<4><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p);
-    else dec_target_kernel<0><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p);
+    PeerCtx px{nullptr, 0, 1, 0};
+    if (pull && pull->windows) px = PeerCtx{reinterpret_cast<unsigned char* const*>(pull->windows), pull->rank, pull->world, pull->max_len};
+    if (vec && K == 4) dec_target_kernel<1><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p, px);
+    else if (vec && K == 8) dec_target_kernel<2><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p, px);
+    else if (vec && K == 16) dec_target_kernel<4><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p, px);
+    else dec_target_kernel<0><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p, px);
     SCC_CUDA(cudaGetLastError());
     return SCC_OK;
 }
@@ -141,6 +151,15 @@ static int check_common(const float* z, int64_t n, int d, const float* mu, int K
     return SCC_OK;
 }
 
+static void fill_exchange(DecArgs& a, const ExchangeDesc* push, int do_push, const ExchangeDesc* pull_f) {
+    const ExchangeDesc* e = (push && push->windows) ? push : ((pull_f && pull_f->windows) ? pull_f : nullptr);
+    if (!e) return;
+    a.ex_windows = reinterpret_cast<unsigned char* const*>(e->windows);
+    a.ex_rank = e->rank; a.ex_world = e->world; a.ex_max_len = e->max_len;
+    a.ex_push = (push && push->windows && do_push) ? 1 : 0;
+    a.ex_pull_f = (pull_f && pull_f->windows) ? 1 : 0;
+}
+
 static void fill_reduction(DecArgs& a, void* ws) {
     a.counter = reinterpret_cast<unsigned int*>(ws);
     a.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + kWorkspaceHeader);
@@ -148,16 +167,21 @@ static void fill_reduction(DecArgs& a, void* ws) {
 
 int dec_assign(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
                float* q, int32_t* labels, const int32_t* labels_prev, double* stats,
-               void* ws, size_t ws_bytes, cudaStream_t st) {
+               void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* push) {
     int rc = check_common(z, n, d, mu, K, alpha, stats, ws, ws_bytes);
     if (rc != SCC_OK) return rc;
     if (round_decimals != 0 && round_decimals != 5) return SCC_ERR_INVALID;
     if (q && (K % 4 == 0) && (reinterpret_cast<uintptr_t>(q) & 15u)) return SCC_ERR_MISALIGNED;
-    if (n == 0) { SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (K + 1), st)); return SCC_OK; }
+    if (n == 0) {
+        SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (K + 1), st));
+        if (push && push->windows) return peer_push_only(stats, K + 1, push->windows, push->rank, push->world, push->max_len, st);
+        return SCC_OK;
+    }
     DecArgs a{};
     a.z = z; a.n = n; a.mu = mu; a.K = K; a.alpha = alpha; a.round5 = round_decimals == 5;
     a.q = q; a.labels = labels; a.labels_prev = labels_prev; a.stats = stats;
     fill_reduction(a, ws);
+    fill_exchange(a, push, /*push=*/1, nullptr);
 #define SCC_CASE(D_, X) if (d == D_) return dec_assign_dim##D_(a, st);
     SCC_FOR_EACH_DIM(SCC_CASE, 0)
 #undef SCC_CASE
@@ -173,18 +197,23 @@ static int dec_grad_dispatch(const DecArgs& a, int d, int mode, cudaStream_t st)
 
 int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* p,
                 const double* f_cols, int round_decimals, float scale, float* dz, double* stats,
-                void* ws, size_t ws_bytes, cudaStream_t st) {
+                void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* pull_f, const ExchangeDesc* push) {
     int rc = check_common(z, n, d, mu, K, alpha, stats, ws, ws_bytes);
     if (rc != SCC_OK) return rc;
-    if (!p && !f_cols) return SCC_ERR_INVALID;
+    if (!p && !f_cols && !(pull_f && pull_f->windows)) return SCC_ERR_INVALID;
     if (round_decimals != 0 && round_decimals != 5) return SCC_ERR_INVALID;
     if (p && (K % 4 == 0) && (reinterpret_cast<uintptr_t>(p) & 15u)) return SCC_ERR_MISALIGNED;
     if (dz && (reinterpret_cast<uintptr_t>(dz) & 15u)) return SCC_ERR_MISALIGNED;
-    if (n == 0) { SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (K * d + 2), st)); return SCC_OK; }
+    if (n == 0) {
+        SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (K * d + 2), st));
+        if (push && push->windows) return peer_push_only(stats, K * d + 2, push->windows, push->rank, push->world, push->max_len, st);
+        return SCC_OK;
+    }
     DecArgs a{};
     a.z = z; a.n = n; a.mu = mu; a.K = K; a.alpha = alpha; a.round5 = round_decimals == 5;
     a.p = p; a.f_cols = f_cols; a.scale = scale; a.dz = dz; a.stats = stats;
     fill_reduction(a, ws);
+    fill_exchange(a, push, 1, p ? nullptr : pull_f);
     return dec_grad_dispatch(a, d, MODE_KL, st);
 }
 

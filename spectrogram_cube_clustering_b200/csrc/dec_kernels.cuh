@@ -273,7 +273,8 @@ dec_assign_kernel(const DecArgs a) {
         if (threadIdx.x == 0 && K < KP) cta_stats[K] = cta_stats[KP];
         __syncthreads();
     }
-    grid_publish<kDecThreads>(cta_stats, K + 1, a.partials, a.counter, a.stats, scratch);
+    const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
+    grid_publish<kDecThreads>(cta_stats, K + 1, a.partials, a.counter, a.stats, scratch, &push);
 }
 
 // ---------------------------------------------------------------------------
@@ -397,8 +398,14 @@ __device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, flo
         for (int j = 0; j < K; ++j) m += a.mu[j * D + threadIdx.x];
         c0_s[threadIdx.x] = m / (float)K;
     }
-    if (threadIdx.x < KP)
+    if (a.ex_pull_f && a.ex_windows) {          // column sums arrive through the fused exchange
+        __shared__ double f_pull[SCC_MAX_K + 1];
+        const PeerCtx ex{a.ex_windows, a.ex_rank, a.ex_world, a.ex_max_len};
+        peer_pull(ex, f_pull, K + 1);
+        if (threadIdx.x < KP) inv_f[threadIdx.x] = ((int)threadIdx.x < K) ? (float)(1.0 / f_pull[threadIdx.x]) : 0.f;
+    } else if (threadIdx.x < KP) {
         inv_f[threadIdx.x] = (a.f_cols && (int)threadIdx.x < K) ? (float)(1.0 / a.f_cols[threadIdx.x]) : 0.f;
+    }
     __syncthreads();
     float* nmu = reinterpret_cast<float*>(nmu2_s);
     float* nmc = reinterpret_cast<float*>(nmc2_s);
@@ -529,8 +536,9 @@ dec_grad_reg_kernel(const DecArgs a) {
     if (o < K * D) cta_stats[2 + o] = (MODE == MODE_KMEANS) ? -dmu : dmu;
     if (MODE == MODE_KMEANS && o < K) cta_stats[2 + K * D + o] = wj;
     __syncthreads();
+    const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
     grid_publish<kDecThreads>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials, a.counter, a.stats,
-                              scratch);
+                              scratch, &push);
 }
 
 // ---------------------------------------------------------------------------
@@ -679,8 +687,9 @@ dec_grad_tiled_kernel(const DecArgs a) {
     if (MODE == MODE_KMEANS && (int)threadIdx.x < K) cta_stats[2 + K * D + threadIdx.x] = small_s[2 + threadIdx.x];
     if (threadIdx.x == 0) { cta_stats[0] = small_s[0]; cta_stats[1] = small_s[1]; }
     __syncthreads();
+    const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
     grid_publish<kDecThreads>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials, a.counter, a.stats,
-                              scratch);
+                              scratch, &push);
 }
 
 // ---------------------------------------------------------------------------

@@ -12,28 +12,10 @@
 // can run at most one exchange ahead of the slowest without overwriting unread data):
 //   uint32 seq; uint32 flags[2][16]; double slots[2][16][max_len]
 // One process per GPU: kernels of different ranks run on different devices, so the spin-wait is safe.
+#include "scc_common.cuh"
 #include "scc_launch.h"
 
 namespace scc {
-
-constexpr int kPeerMaxWorld = 16;
-constexpr size_t kPeerHeaderBytes = 512;       // seq + flags, padded
-
-struct PeerHeader {
-    unsigned int seq;
-    unsigned int pad[31];
-    unsigned int flags[2][kPeerMaxWorld];
-};
-static_assert(sizeof(PeerHeader) <= kPeerHeaderBytes, "header too large");
-
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 __global__ void __launch_bounds__(256)
 peer_allreduce_kernel(const double* __restrict__ local, int len, double* __restrict__ out,
@@ -67,6 +49,20 @@ peer_allreduce_kernel(const double* __restrict__ local, int len, double* __restr
     if (threadIdx.x == 0) me->seq = seq;
 }
 
+// Second half of a fused exchange: the producing kernel's last CTA already pushed (grid_publish with a
+// PeerCtx); wait for the world and write the rank-ordered sum.
+__global__ void __launch_bounds__(256)
+peer_finish_kernel(double* __restrict__ out, int len, PeerCtx ex) {
+    peer_pull(ex, out, len);
+}
+
+// Push-only half for a rank whose shard is empty (its statistics are all zero but it must still take
+// part in the exchange).
+__global__ void __launch_bounds__(256)
+peer_push_kernel(const double* __restrict__ local, int len, PeerCtx ex) {
+    peer_push(ex, ((int)threadIdx.x < len) ? local[threadIdx.x] : 0.0, len);
+}
+
 size_t peer_window_bytes(int max_len) {
     if (max_len < 1) return 0;
     return kPeerHeaderBytes + sizeof(double) * 2 * kPeerMaxWorld * (size_t)max_len;
@@ -78,6 +74,24 @@ int peer_allreduce(const double* local, int len, double* out, void* const* windo
     if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world) return SCC_ERR_INVALID;
     peer_allreduce_kernel<<<1, 256, 0, st>>>(local, len, out, reinterpret_cast<unsigned char* const*>(windows_dev),
                                              rank, world, max_len);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
+
+int peer_push_only(const double* local, int len, void* const* windows_dev, int rank, int world, int max_len,
+                   cudaStream_t st) {
+    if (!local || !windows_dev || len < 1 || len > 256 || len > max_len) return SCC_ERR_INVALID;
+    PeerCtx ex{reinterpret_cast<unsigned char* const*>(windows_dev), rank, world, max_len};
+    peer_push_kernel<<<1, 256, 0, st>>>(local, len, ex);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
+
+int peer_finish(double* out, int len, void* const* windows_dev, int rank, int world, int max_len, cudaStream_t st) {
+    if (!out || !windows_dev || len < 1 || len > max_len) return SCC_ERR_INVALID;
+    if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world) return SCC_ERR_INVALID;
+    PeerCtx ex{reinterpret_cast<unsigned char* const*>(windows_dev), rank, world, max_len};
+    peer_finish_kernel<<<1, 256, 0, st>>>(out, len, ex);
     SCC_CUDA(cudaGetLastError());
     return SCC_OK;
 }

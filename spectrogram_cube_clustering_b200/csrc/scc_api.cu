@@ -98,7 +98,7 @@ int scc_dec_assign(const float* z, int64_t n, int d, const float* mu, int K, flo
 
 int scc_dec_target(const float* q, int64_t n, int K, const double* f, int round_decimals, float* p,
                    scc_stream_t stream) {
-    return scc::dec_target(q, n, K, f, round_decimals, p, (cudaStream_t)stream);
+    return scc::dec_target(q, n, K, const_cast<double*>(f), round_decimals, p, (cudaStream_t)stream);
 }
 
 int scc_colsum(const float* q, int64_t n, int K, double* f, void* workspace, size_t workspace_bytes,
@@ -123,6 +123,40 @@ int scc_kmeans_step(const float* z, int64_t n, int d, const float* centers, int 
                     double* stats, void* workspace, size_t workspace_bytes, scc_stream_t stream) {
     return scc::kmeans_step(z, n, d, centers, K, labels, mindist, stats, workspace, workspace_bytes,
                             (cudaStream_t)stream);
+}
+
+static const scc::ExchangeDesc* as_desc(const scc_exchange* e, scc::ExchangeDesc* tmp) {
+    if (!e || !e->windows) return nullptr;
+    tmp->windows = e->windows; tmp->rank = e->rank; tmp->world = e->world; tmp->max_len = e->max_len;
+    return tmp;
+}
+
+int scc_dec_assign_ex(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
+                      float* q, int32_t* labels, const int32_t* labels_prev, double* stats, void* workspace,
+                      size_t workspace_bytes, const scc_exchange* push, scc_stream_t stream) {
+    scc::ExchangeDesc t;
+    return scc::dec_assign(z, n, d, mu, K, alpha, round_decimals, q, labels, labels_prev, stats, workspace,
+                           workspace_bytes, (cudaStream_t)stream, as_desc(push, &t));
+}
+
+int scc_dec_target_ex(const float* q, int64_t n, int K, double* f, int round_decimals, float* p,
+                      const scc_exchange* pull, scc_stream_t stream) {
+    scc::ExchangeDesc t;
+    return scc::dec_target(q, n, K, f, round_decimals, p, (cudaStream_t)stream, as_desc(pull, &t));
+}
+
+int scc_dec_kl_grad_ex(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* p,
+                       const double* f_cols, int round_decimals, float scale, float* dz, double* stats,
+                       void* workspace, size_t workspace_bytes, const scc_exchange* pull_f,
+                       const scc_exchange* push, scc_stream_t stream) {
+    scc::ExchangeDesc t1, t2;
+    return scc::dec_kl_grad(z, n, d, mu, K, alpha, p, f_cols, round_decimals, scale, dz, stats, workspace,
+                            workspace_bytes, (cudaStream_t)stream, as_desc(pull_f, &t1), as_desc(push, &t2));
+}
+
+int scc_peer_finish(double* out, int len, const scc_exchange* ex, scc_stream_t stream) {
+    if (!ex || !ex->windows) return SCC_ERR_INVALID;
+    return scc::peer_finish(out, len, ex->windows, ex->rank, ex->world, ex->max_len, (cudaStream_t)stream);
 }
 
 size_t scc_peer_window_bytes(int max_len) { return scc::peer_window_bytes(max_len); }

@@ -208,6 +208,67 @@ struct ZRing {
 };
 
 // ----------------------------------------------------------------------------
+// Peer-memory exchange window (see peer_exchange.cu): header {seq, flags[2][16]} then
+// slots[2][16][max_len] float64.  `push` runs in the LAST CTA of a statistics kernel (fused into
+// its tail), `pull` in the prologue of the kernel that consumes the all-reduced vector.
+// ----------------------------------------------------------------------------
+constexpr int kPeerMaxWorld = 16;
+constexpr size_t kPeerHeaderBytes = 512;
+struct PeerHeader {
+    unsigned int seq;
+    unsigned int pad[31];
+    unsigned int flags[2][kPeerMaxWorld];
+};
+struct PeerCtx {                    // by value inside kernel argument structs
+    unsigned char* const* windows;  // device array of `world` window base pointers (nullptr = no exchange)
+    int rank, world, max_len;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double* peer_slot(unsigned char* window, int parity, int src_rank, int max_len) {
+    return reinterpret_cast<double*>(window + kPeerHeaderBytes) + ((size_t)parity * kPeerMaxWorld + src_rank) * max_len;
+}
+
+// All threads of ONE CTA: push vals[0..len) (thread tid holds element tid, len <= blockDim) to every
+// rank's window and publish the sequence flag.  Advances the local sequence number.
+__device__ __forceinline__ void peer_push(const PeerCtx& ex, double my_val, int len) {
+    PeerHeader* me = reinterpret_cast<PeerHeader*>(ex.windows[ex.rank]);
+    const unsigned int seq = me->seq + 1u;
+    const int parity = seq & 1u;
+    if ((int)threadIdx.x < len)
+        for (int r = 0; r < ex.world; ++r) peer_slot(ex.windows[r], parity, ex.rank, ex.max_len)[threadIdx.x] = my_val;
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < ex.world)
+        st_release_sys(&reinterpret_cast<PeerHeader*>(ex.windows[threadIdx.x])->flags[parity][ex.rank], seq);
+    if (threadIdx.x == 0) me->seq = seq;
+}
+
+// All threads of a CTA: wait for the exchange most recently pushed by the preceding kernel and write
+// the rank-ordered sum of the `len` doubles to dst (shared or global).  Ends with __syncthreads().
+__device__ __forceinline__ void peer_pull(const PeerCtx& ex, double* dst, int len) {
+    const PeerHeader* me = reinterpret_cast<const PeerHeader*>(ex.windows[ex.rank]);
+    const unsigned int seq = me->seq;
+    const int parity = seq & 1u;
+    if ((int)threadIdx.x < ex.world)
+        while (ld_acquire_sys(&me->flags[parity][threadIdx.x]) != seq) {}
+    __syncthreads();
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < ex.world; ++r) acc += __ldcv(peer_slot(ex.windows[ex.rank], parity, r, ex.max_len) + i);
+        dst[i] = acc;
+    }
+    __syncthreads();
+}
+
+// ----------------------------------------------------------------------------
 // Reductions.
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -230,7 +291,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Returns true in the CTA that arrived last (after `out` is complete).
 template <int NT>
 __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, double* partials,
-                                             unsigned int* counter, double* out, double* scratch) {
+                                             unsigned int* counter, double* out, double* scratch,
+                                             const PeerCtx* push = nullptr) {
     __shared__ int s_last;
     const int tid = threadIdx.x;
     double* mine = partials + (size_t)blockIdx.x * S;
@@ -267,11 +329,12 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
         }
         scratch[tid] = acc;
         __syncthreads();
+        double t = 0.0;
         if (tid < S) {
-            double t = 0.0;
             for (int rr = 0; rr < R; ++rr) t += scratch[rr * S + tid];
             out[tid] = t;
         }
+        if (push && push->windows) peer_push(*push, t, S);      // fused tail: ship the vector to every rank
     } else {
         for (int s = tid; s < S; s += NT) {
             double acc = 0.0;

@@ -43,6 +43,16 @@ struct DecArgs {
     double* stats;
     double* partials;
     unsigned int* counter;
+    // optional fused multi-GPU exchange (windows == nullptr: none)
+    unsigned char* const* ex_windows;
+    int ex_rank, ex_world, ex_max_len;
+    int ex_push;               // last CTA pushes the reduced stats to every rank's window
+    int ex_pull_f;             // f_cols are pulled from the exchange pushed by the preceding assign kernel
+};
+
+struct ExchangeDesc {          // host-side mirror of scc_exchange
+    void* const* windows;
+    int rank, world, max_len;
 };
 
 void set_cuda_error(cudaError_t e, const char* what, int line);
@@ -66,12 +76,17 @@ bool gmm_supported(int d, int K);
 
 int dec_assign(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
                float* q, int32_t* labels, const int32_t* labels_prev, double* stats,
-               void* ws, size_t ws_bytes, cudaStream_t st);
-int dec_target(const float* q, int64_t n, int K, const double* f, int round_decimals, float* p, cudaStream_t st);
+               void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* push = nullptr);
+int dec_target(const float* q, int64_t n, int K, double* f, int round_decimals, float* p, cudaStream_t st,
+               const ExchangeDesc* pull = nullptr);
+int peer_finish(double* out, int len, void* const* windows_dev, int rank, int world, int max_len, cudaStream_t st);
+int peer_push_only(const double* local, int len, void* const* windows_dev, int rank, int world, int max_len,
+                   cudaStream_t st);
 int colsum(const float* q, int64_t n, int K, double* f, void* ws, size_t ws_bytes, cudaStream_t st);
 int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* p,
                 const double* f_cols, int round_decimals, float scale, float* dz, double* stats,
-                void* ws, size_t ws_bytes, cudaStream_t st);
+                void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* pull_f = nullptr,
+                const ExchangeDesc* push = nullptr);
 int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* grad_q,
                  float* dz, double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
 int kmeans_step(const float* z, int64_t n, int d, const float* centers, int K, int32_t* labels, float* mindist,

@@ -56,6 +56,8 @@ class PeerExchange:
         torch.cuda.synchronize(device)
         dist.barrier(group)
         self.ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        from ._lib import SccExchange
+        self.desc = SccExchange(self.ptrs.data_ptr(), self.rank, self.world, self.max_len)   # for the *_ex entry points
 
     def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
         if t.numel() > self.max_len:
@@ -151,10 +153,28 @@ class LatentBuffer:
 
     def dec_step(self, mu: torch.Tensor, alpha: float = 1.0, gamma: float = 1e-3, round_decimals: int = 0,
                  want_dz: bool = False) -> DecStepResult:
-        """Fused latent-buffer DEC step: assign -> (allreduce f) -> KL gradients -> (allreduce dmu)."""
+        """Fused latent-buffer DEC step: assign -> (allreduce f) -> KL gradients -> (allreduce dmu).
+        With a peer exchange the collectives ride on the kernels: the assign kernel's last CTA pushes f
+        to every rank, the gradient kernel pulls it in its prologue and pushes its own statistics, and
+        one small finish kernel collects them — three launches per step, no separate collective."""
+        K = mu.shape[0]
+        if self.exchange is not None and self.world > 1:
+            ex = self.exchange.desc
+            prev = self.labels
+            out_labels = self._labels_spare if self._labels_spare is not None else torch.empty(
+                self.n_local, dtype=torch.int32, device=self.z.device)
+            _, labels, st = ops.dec_assign(self.z, mu, alpha, round_decimals, want_q=False, want_labels=True,
+                                           labels_prev=prev, out_labels=out_labels, push=ex)
+            self._labels_spare, self.labels = self.labels, labels
+            stats, dz = ops.dec_kl_grad(self.z, mu, alpha, round_decimals=round_decimals,
+                                        scale=gamma / self.n_total, want_dz=want_dz, pull_f=ex, push=ex)
+            ops.peer_finish(stats, ex)
+            # st holds only this shard's f; the all-reduced f is not needed by the caller of a fused step,
+            # the label-change count is: exchange it with the (tiny) standalone kernel
+            self.exchange.all_reduce(st)
+            return DecStepResult(loss=stats[0], dmu=stats[2:].view(K, self.d), f=st[:K], n_changed=st[K], dz=dz)
         _, st = self.dec_assign(mu, alpha, round_decimals)
         stats, dz = self.dec_grad(mu, st, alpha, gamma, round_decimals, want_dz=want_dz)
-        K = mu.shape[0]
         return DecStepResult(loss=stats[0], dmu=stats[2:].view(K, self.d), f=st[:K], n_changed=st[K], dz=dz)
 
     def delta_label(self, assign_stats: torch.Tensor) -> float:

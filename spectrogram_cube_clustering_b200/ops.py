@@ -22,6 +22,12 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _ex(desc):
+    """ctypes pointer to an ``scc_exchange`` descriptor (or NULL)."""
+    import ctypes
+    return None if desc is None else ctypes.addressof(desc)
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -61,7 +67,7 @@ def padded_dim(d: int) -> int:
 
 # --------------------------------------------------------------------------- DEC
 def dec_assign(z, mu, alpha=1.0, round_decimals=0, want_q=True, want_labels=True, labels_prev=None,
-               out_q=None, out_labels=None, out_stats=None):
+               out_q=None, out_labels=None, out_stats=None, push=None):
     """z [n,d], mu [K,d] -> (q [n,K] | None, labels int32 [n] | None, stats float64 [K+1]).
 
     stats = (f_0..f_{K-1}, number of labels != labels_prev).  networks.py:279-288,
@@ -80,19 +86,23 @@ def dec_assign(z, mu, alpha=1.0, round_decimals=0, want_q=True, want_labels=True
         _require(labels_prev, "labels_prev", torch.int32)
     stats = out_stats if out_stats is not None else torch.empty(K + 1, dtype=torch.float64, device=z.device)
     ws = workspace(z.device, d, K)
-    rc = lib.scc_dec_assign(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), int(round_decimals), _ptr(q),
-                            _ptr(labels), _ptr(labels_prev), stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    rc = lib.scc_dec_assign_ex(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), int(round_decimals), _ptr(q),
+                               _ptr(labels), _ptr(labels_prev), stats.data_ptr(), ws.data_ptr(), ws.numel(),
+                               _ex(push), _stream())
     _lib.check(rc, "scc_dec_assign")
     return q, labels, stats
 
 
-def dec_target(q, f, round_decimals=0, out=None):
-    """q [n,K], f float64 [>=K] -> p [n,K].  models.py:1320-1322."""
+def dec_target(q, f, round_decimals=0, out=None, pull=None):
+    """q [n,K], f float64 [>=K] -> p [n,K].  models.py:1320-1322.  With ``pull`` (an exchange
+    descriptor) f [K+1] is first filled with the all-reduced sums pushed by the preceding
+    ``dec_assign(push=...)`` on every rank."""
     lib = _lib.load()
     _require(q, "q"); _require(f, "f", torch.float64)
     n, K = q.shape
     p = out if out is not None else torch.empty_like(q)
-    rc = lib.scc_dec_target(q.data_ptr(), n, K, f.data_ptr(), int(round_decimals), p.data_ptr(), _stream())
+    rc = lib.scc_dec_target_ex(q.data_ptr(), n, K, f.data_ptr(), int(round_decimals), p.data_ptr(), _ex(pull),
+                               _stream())
     _lib.check(rc, "scc_dec_target")
     return p
 
@@ -109,7 +119,7 @@ def colsum(q):
 
 
 def dec_kl_grad(z, mu, alpha=1.0, p=None, f=None, round_decimals=0, scale=1.0, want_dz=True,
-                out_dz=None, out_stats=None):
+                out_dz=None, out_stats=None, pull_f=None, push=None):
     """-> (stats float64 [K*d+2] = (loss, sum_i s_i, dmu[K,d]), dz [n,d] | None).  models.py:1124-1127."""
     lib = _lib.load()
     _require(z, "z"); _require(mu, "mu")
@@ -121,14 +131,14 @@ def dec_kl_grad(z, mu, alpha=1.0, p=None, f=None, round_decimals=0, scale=1.0, w
             raise ValueError("p must be [n, K]")
     if f is not None:
         _require(f, "f", torch.float64)
-    if p is None and f is None:
+    if p is None and f is None and pull_f is None:
         raise ValueError("need the target p or the column sums f")
     dz = out_dz if out_dz is not None else (torch.empty_like(z) if want_dz else None)
     stats = out_stats if out_stats is not None else torch.empty(K * d + 2, dtype=torch.float64, device=z.device)
     ws = workspace(z.device, d, K)
-    rc = lib.scc_dec_kl_grad(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), _ptr(p), _ptr(f),
-                             int(round_decimals), float(scale), _ptr(dz), stats.data_ptr(), ws.data_ptr(),
-                             ws.numel(), _stream())
+    rc = lib.scc_dec_kl_grad_ex(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), _ptr(p), _ptr(f),
+                                int(round_decimals), float(scale), _ptr(dz), stats.data_ptr(), ws.data_ptr(),
+                                ws.numel(), _ex(pull_f), _ex(push), _stream())
     _lib.check(rc, "scc_dec_kl_grad")
     return stats, dz
 
@@ -230,6 +240,14 @@ def peer_allreduce(t: torch.Tensor, windows: torch.Tensor, rank: int, world: int
     rc = lib.scc_peer_allreduce(t.data_ptr(), t.numel(), t.data_ptr(), windows.data_ptr(), int(rank), int(world),
                                 int(max_len), _stream())
     _lib.check(rc, "scc_peer_allreduce")
+    return t
+
+
+def peer_finish(t: torch.Tensor, desc) -> torch.Tensor:
+    """Completes a fused exchange: waits for every rank's push and writes the rank-ordered sum to t."""
+    lib = _lib.load()
+    _require(t, "t", torch.float64)
+    _lib.check(lib.scc_peer_finish(t.data_ptr(), t.numel(), _ex(desc), _stream()), "scc_peer_finish")
     return t
 
 
