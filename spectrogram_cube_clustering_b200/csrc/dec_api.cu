@@ -15,16 +15,21 @@ SCC_FOR_EACH_DIM(SCC_DECL_DIM, 0)
 // LPR lanes cooperate on one row (K = 4*LPR) so that global accesses are
 // 128-bit and fully coalesced; LPR = 0 is the scalar thread-per-row fallback.
 // ---------------------------------------------------------------------------
+// kept out of line so that the exchange prologue does not inflate the streaming loop's registers
+static __device__ __noinline__ void target_pull_f(const PeerCtx& pull, int K, double* f, float* inv_f) {
+    __shared__ double f_pull[SCC_MAX_K + 1];
+    peer_pull(pull, f_pull, K + 1);
+    if ((int)threadIdx.x < K) inv_f[threadIdx.x] = (float)(1.0 / f_pull[threadIdx.x]);
+    if (blockIdx.x == 0 && (int)threadIdx.x <= K) f[threadIdx.x] = f_pull[threadIdx.x];   // publish the sums
+}
+
 template <int LPR>
 __global__ void __launch_bounds__(256)
 dec_target_kernel(const float* __restrict__ q, int64_t n, int K, double* __restrict__ f,
                   int round5, float* __restrict__ p, PeerCtx pull) {
     __shared__ float inv_f[SCC_MAX_K];
     if (pull.windows) {                 // f comes from the exchange pushed by the preceding assign kernel
-        __shared__ double f_pull[SCC_MAX_K + 1];
-        peer_pull(pull, f_pull, K + 1);
-        if (threadIdx.x < K) inv_f[threadIdx.x] = (float)(1.0 / f_pull[threadIdx.x]);
-        if (blockIdx.x == 0 && (int)threadIdx.x <= K) f[threadIdx.x] = f_pull[threadIdx.x];   // publish the sums
+        target_pull_f(pull, K, f, inv_f);
     } else if (threadIdx.x < K) {
         inv_f[threadIdx.x] = (float)(1.0 / f[threadIdx.x]);
     }
