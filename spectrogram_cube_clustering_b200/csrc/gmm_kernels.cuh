@@ -14,6 +14,8 @@
 //  accumulators spill under the 128-register cap of a 512-thread CTA)
 #pragma once
 
+#include <stdlib.h>
+
 #include "scc_common.cuh"
 #include "scc_launch.h"
 
@@ -238,6 +240,273 @@ static int launch_gmm_full(const GmmArgs& a, cudaStream_t st) {
     return SCC_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// PACKED variant of the d <= 12 kernel: same two phases, inner loops in packed FP32 (FFMA2/FADD2).
+//   E-step:  y_{2bp}, y_{2bp+1} = sum_c df_c * {U[c][2bp], U[c][2bp+1]}  (U stored as zero-padded
+//            pairs in shared memory, df_c splat is free: FFMA2 R, R.F32, R.F32x2, R.F32x2)
+//   M-step:  S2[c][2bp..2bp+1] += w_c * {df_2bp, df_2bp+1},  bp >= c/2  (aligned pairs; the one
+//            redundant lower-triangle lane of odd rows is discarded at flush time)
+// ---------------------------------------------------------------------------
+template <int D>
+struct GmmPairs {
+    static constexpr int DP2 = (D + 1) / 2;
+    __host__ __device__ static constexpr int rows(int bp) { return (2 * bp + 2 < D) ? 2 * bp + 2 : D; }
+    __host__ __device__ static constexpr int uoff(int bp) { int n = 0; for (int b = 0; b < bp; ++b) n += rows(b); return n; }
+    static constexpr int NU2 = uoff(DP2);                       // U pairs per component
+    __host__ __device__ static constexpr int moff(int c) { int n = 0; for (int r = 0; r < c; ++r) n += DP2 - r / 2; return n; }
+    static constexpr int NP = moff(D);                          // S2 pairs per component
+    static constexpr int NPAIR = 1 + DP2 + NP;                  // {S0,-}, S1 pairs, S2 pairs
+};
+
+template <int D, int KP>
+__global__ void __launch_bounds__(32 * KP, 1)
+gmm_em_packed_kernel(const GmmArgs a) {
+    constexpr int NT = 32 * KP;
+    constexpr int TILE = NT;
+    constexpr int S = 3;
+    constexpr int TRI = tri(D);
+    constexpr int NM = 1 + D + TRI;
+    constexpr int FLUSH = 16;
+    using Ring = ZRing<D, TILE, S, NT>;
+    using P = GmmPairs<D>;
+    constexpr int DP2 = P::DP2, NU2 = P::NU2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring_buf = reinterpret_cast<float*>(smem_raw);
+    float* r_s = ring_buf + S * Ring::kTileFloats;                       // [KP][TILE]
+    float2* nmu2_s = reinterpret_cast<float2*>(r_s + KP * TILE);         // [KP][DP2]   -mu pairs
+    float2* u2_s = nmu2_s + ((KP * DP2 + 1) & ~1);                       // [KP][NU2]   U pairs
+    float* cst_s = reinterpret_cast<float*>(u2_s + ((KP * NU2 + 1) & ~1));   // [KP]
+    double* mom_s = reinterpret_cast<double*>(cst_s + ((KP + 3) & ~3));  // [KP][NM]
+    double* ll_s = mom_s + KP * NM;
+    double* cta_stats = ll_s + KP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + 1 + KP * NM);
+
+    if (a.ctrl && a.ctrl[5] != 0.0) return;
+
+    const int K = a.K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {   // parameters -> pair layouts
+        float* nmu = reinterpret_cast<float*>(nmu2_s);
+        for (int i = threadIdx.x; i < KP * DP2 * 2; i += NT) {
+            const int k = i / (2 * DP2), c = i - k * (2 * DP2);
+            nmu[i] = (k < K && c < D) ? -a.params[k * D + c] : 0.f;
+        }
+        float* u2 = reinterpret_cast<float*>(u2_s);
+        for (int i = threadIdx.x; i < KP * NU2 * 2; i += NT) {
+            const int k = i / (2 * NU2), e = i - k * (2 * NU2), pair = e >> 1, ln = e & 1;
+            int bp = 0, base = 0;
+            while (base + P::rows(bp) <= pair) { base += P::rows(bp); ++bp; }
+            const int c = pair - base, b = 2 * bp + ln;
+            u2[i] = (k < K && b < D && c <= b) ? a.params[K * D + k * TRI + tri(b) + c] : 0.f;
+        }
+        if (threadIdx.x < KP) cst_s[threadIdx.x] = ((int)threadIdx.x < K) ? a.params[K * D + K * TRI + threadIdx.x] : 0.f;
+        for (int i = threadIdx.x; i < KP * NM; i += NT) mom_s[i] = 0.0;
+    }
+
+    Ring ring;
+    ring.init(ring_buf, bars, a.z, a.n);
+    __syncthreads();
+    const int G = gridDim.x;
+#pragma unroll
+    for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
+    __syncthreads();
+
+    const int kc = warp;
+    float2 nmuk[DP2];
+#pragma unroll
+    for (int c = 0; c < DP2; ++c) nmuk[c] = nmu2_s[kc * DP2 + c];
+    float2 mom2[P::NPAIR];
+#pragma unroll
+    for (int s = 0; s < P::NPAIR; ++s) mom2[s] = make_float2(0.f, 0.f);
+    float loglik = 0.f;
+
+    auto flush = [&]() {
+        if (kc < K) {
+            double* dst = mom_s + kc * NM;
+            { const float w = warp_sum(mom2[0].x); if (lane == 0) dst[0] += (double)w; }
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const float v = (c & 1) ? mom2[1 + (c >> 1)].y : mom2[1 + (c >> 1)].x;
+                const float w = warp_sum(v);
+                if (lane == 0) dst[1 + c] += (double)w;
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+#pragma unroll
+                for (int b = c; b < D; ++b) {
+                    const int pr = 1 + DP2 + P::moff(c) + (b >> 1) - (c >> 1);
+                    const float v = (b & 1) ? mom2[pr].y : mom2[pr].x;
+                    const float w = warp_sum(v);
+                    if (lane == 0) dst[1 + D + tri(b) + c] += (double)w;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < P::NPAIR; ++s) mom2[s] = make_float2(0.f, 0.f);
+        }
+    };
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G, ++it) {
+        const int stage = it % S;
+        ring.wait(stage, tile, (uint32_t)(it / S));
+        const int np = ring.points(tile);
+        const float* ztile = ring.stage_ptr(stage);
+        // ---------------- phase 1 ----------------
+        {
+            const bool active = (int)threadIdx.x < np;
+            float lp[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) lp[k] = 0.f;
+            float lse = 0.f;
+            int label = 0;
+            if (active) {
+                float xr[D];
+                load_row<D>(ztile, threadIdx.x, xr);
+                float2 x2[DP2];
+#pragma unroll
+                for (int c = 0; c < DP2; ++c) x2[c] = make_float2(xr[2 * c], (2 * c + 1 < D) ? xr[2 * c + 1] : 0.f);
+                float best = -3.4e38f;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    lp[k] = -3.4e38f;
+                    if (k < K) {
+                        float2 df2[DP2];
+#pragma unroll
+                        for (int c = 0; c < DP2; ++c) df2[c] = __fadd2_rn(x2[c], nmu2_s[k * DP2 + c]);
+                        float2 m2 = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int bp = 0; bp < DP2; ++bp) {
+                            float2 y2 = make_float2(0.f, 0.f);
+#pragma unroll
+                            for (int c = 0; c < P::rows(bp); ++c) {
+                                const float dc = (c & 1) ? df2[c >> 1].y : df2[c >> 1].x;
+                                y2 = __ffma2_rn(make_float2(dc, dc), u2_s[k * NU2 + P::uoff(bp) + c], y2);
+                            }
+                            m2 = __ffma2_rn(y2, y2, m2);
+                        }
+                        lp[k] = fmaf(-0.5f, m2.x + m2.y, cst_s[k]);
+                        if (lp[k] > best) { best = lp[k]; label = k; }
+                    }
+                }
+                float se = 0.f;
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (k < K) se += expf(lp[k] - best);
+                lse = best + logf(se);
+                loglik += lse;
+            }
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                float r = (active && k < K) ? expf(lp[k] - lse) : 0.f;
+                if (a.accumulate == SCC_GMM_HARD) r = (active && k == label) ? 1.f : 0.f;
+                r_s[k * TILE + threadIdx.x] = r;
+                lp[k] = r;
+            }
+            if (active) {
+                const size_t i = (size_t)tile * TILE + threadIdx.x;
+                if (a.labels) a.labels[i] = label;
+                if (a.resp) {
+#pragma unroll
+                    for (int k = 0; k < KP; ++k)
+                        if (k < K) a.resp[i * K + k] = lp[k];
+                }
+            }
+        }
+        __syncthreads();
+        // ---------------- phase 2 ----------------
+        if (a.accumulate && kc < K) {
+            for (int t = lane; t < np; t += 32) {
+                const float r = r_s[kc * TILE + t];
+                float xr[D];
+                load_row<D>(ztile, t, xr);
+                float2 df2[DP2], w2[DP2];
+                const float2 r2 = splat2(r);
+#pragma unroll
+                for (int c = 0; c < DP2; ++c) {
+                    df2[c] = __fadd2_rn(make_float2(xr[2 * c], (2 * c + 1 < D) ? xr[2 * c + 1] : 0.f), nmuk[c]);
+                    w2[c] = __fmul2_rn(r2, df2[c]);
+                    mom2[1 + c] = __fadd2_rn(mom2[1 + c], w2[c]);
+                }
+                mom2[0].x += r;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    const float wc = (c & 1) ? w2[c >> 1].y : w2[c >> 1].x;
+#pragma unroll
+                    for (int bp = c >> 1; bp < DP2; ++bp) {
+                        const int pr = 1 + DP2 + P::moff(c) + bp - (c >> 1);
+                        mom2[pr] = __ffma2_rn(make_float2(wc, wc), df2[bp], mom2[pr]);
+                    }
+                }
+            }
+            if ((it + 1) % FLUSH == 0) flush();
+        }
+        __syncthreads();
+        ring.issue(stage, tile + S * G);
+    }
+    if (a.accumulate) flush();
+    {
+        const float w = warp_sum(loglik);
+        if (lane == 0) ll_s[warp] = (double)w;
+    }
+    __syncthreads();
+    const int NS = 1 + K * NM;
+    for (int s = threadIdx.x; s < NS; s += NT) {
+        double v;
+        if (s == 0) {
+            v = 0.0;
+            for (int w = 0; w < KP; ++w) v += ll_s[w];
+        } else if (s < 1 + K) {
+            v = mom_s[(s - 1) * NM];
+        } else if (s < 1 + K + K * D) {
+            const int o = s - 1 - K, k = o / D, c = o - k * D;
+            v = mom_s[k * NM + 1 + c];
+        } else {
+            const int o = s - 1 - K - K * D, k = o / TRI, e = o - k * TRI;
+            v = mom_s[k * NM + 1 + D + e];
+        }
+        cta_stats[s] = v;
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < NS; s += NT) a.partials[(size_t)blockIdx.x * NS + s] = cta_stats[s];
+}
+
+template <int D, int KP>
+constexpr size_t gmm_packed_smem() {
+    constexpr int NT = 32 * KP, TILE = NT, S = 3, TRI = tri(D), NM = 1 + D + TRI;
+    using P = GmmPairs<D>;
+    return sizeof(float) * (S * TILE * RowLayout<D>::LD + KP * TILE + 2 * ((KP * P::DP2 + 1) & ~1) + 2 * ((KP * P::NU2 + 1) & ~1) +
+                            ((KP + 3) & ~3)) +
+           sizeof(double) * (KP * NM + KP + 1 + KP * NM) + sizeof(uint64_t) * S;
+}
+
+// which d <= 12 kernel to run (set from measurements; SCC_GMM_FORCE_SCALAR / _PACKED override for A/B runs)
+template <int D, int KP>
+static int launch_gmm_small(const GmmArgs& a, cudaStream_t st) {
+    constexpr int NT = 32 * KP;
+    static const int force = []() {
+        const char* e = getenv("SCC_GMM_VARIANT");
+        return e ? (e[0] == 'p' ? 1 : (e[0] == 's' ? 2 : 0)) : 0;
+    }();
+    // measured (tools/gmm_ab.py, N=4M): packed wins only for even d (d=12: 477 vs 522 us, d=4: 153 vs 160 us);
+    // at the reference's d=9 the pad lane and half-pair splats make it 30 % slower (534 vs 403 us, K=8)
+    const bool packed = force ? (force == 1) : (KP <= 8 && D % 2 == 0);
+    if (!packed) return launch_gmm_full<D, KP>(a, st);
+    auto kern = gmm_em_packed_kernel<D, KP>;
+    constexpr size_t smem = gmm_packed_smem<D, KP>();
+    const int64_t tiles = (a.n + NT - 1) / NT;
+    int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), NT, smem, 2);
+    if (grid < 0) return (int)grid;
+    if (grid > kMaxGmmGrid) grid = kMaxGmmGrid;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, NT, smem, st>>>(a);
+    SCC_CUDA(cudaGetLastError());
+    const int NS = SCC_GMM_STAT_DOUBLES(a.K, D);
+    reduce_partials_kernel<<<(NS + 255) / 256, 256, 0, st>>>(a.partials, NS, (int)grid, a.stats, a.ctrl);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
 
 // ---------------------------------------------------------------------------
 // BLOCK variant (d % 4 == 0, d >= 16): the 1 + d + d(d+1)/2 moments of a component no longer fit
@@ -480,7 +749,7 @@ static int launch_gmm_block(const GmmArgs& a, cudaStream_t st) {
 
 template <int D, int KP>
 static int launch_gmm(const GmmArgs& a, cudaStream_t st) {
-    if constexpr (D <= 12) return launch_gmm_full<D, KP>(a, st);
+    if constexpr (D <= 12) return launch_gmm_small<D, KP>(a, st);
     else return launch_gmm_block<D, KP>(a, st);
 }
 
