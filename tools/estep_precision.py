@@ -1,5 +1,5 @@
 import numpy as np, sys
-sys.path.insert(0,'tests'); sys.path.insert(0,'.')
+sys.path.insert(0,'tests'); sys.path.insert(0,'.')  # run from the repo root
 from conftest import load_golden
 from oracle import gmm as og
 g = load_golden('gmm','c1')
