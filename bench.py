@@ -531,6 +531,45 @@ def extra_benchmarks(torch, ops, synth, dev, hbm_peak):
         out["dec_fused_d9"] = {"workload": "fused latent-buffer DEC step (assign + KL grads, centroid-only), N=12.5M d=9 K=8",
                                "points_per_s": n / (ms * 1e-3), "ms": ms, "algorithmic_bytes_per_point": 8 * d,
                                "hbm_gbs": 8 * d * n / (ms * 1e-3) / 1e9, "hbm_frac": 8 * d * n / (ms * 1e-3) / 1e9 / hbm_peak}
+        del z
+        # BASELINE configs[2]: full-covariance EM fit, 100 iterations (tol=0), N=10M d=9 K=16, through the
+        # scikit-learn-style front end (device-resident loop, host polls every 25 iterations)
+        from spectrogram_cube_clustering_b200.models import GaussianMixture, DEC_training
+        from spectrogram_cube_clustering_b200.networks import DEC
+        import warnings
+        n, d, k = 10_000_000, 9, 16
+        z, _ = synth.latent_points(n, d, k, rank=77, device=dev)
+        w0, mu0, cov0 = synth.gmm_initial_state(d, k, "cpu")
+        gm = GaussianMixture(k, max_iter=100, tol=0.0, weights_init=w0.numpy(), means_init=mu0.numpy(),
+                             covariances_init=cov0.numpy(), poll_interval=25)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gm.fit(z)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["gmm_fit_100_iters"] = {"workload": "GaussianMixture.fit, 100 EM iterations, N=10M d=9 K=16 (configs[2] on 1 GPU)",
+                                    "seconds": dt, "points_per_s": n * gm.n_iter_ / dt, "ms": dt * 1e3 / max(gm.n_iter_, 1),
+                                    "n_iter": gm.n_iter_, "lower_bound": gm.lower_bound_,
+                                    "hbm_frac": 4 * d * n * gm.n_iter_ / dt / 1e9 / hbm_peak}
+        del z, gm
+        # BASELINE configs[4]: one DEC_training epoch on synthetic (N,1,4,101) spectrograms, B=4096
+        nspec, bsz = 131072, 4096
+        x = synth.spectrograms(nspec, device=dev)
+        loader = synth.TensorBatches(x, bsz)
+        model = DEC(n_clusters=5).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        DEC_training(model, loader, opt, n_epochs=1, gamma=1e-3, tol=0.0)          # warm-up epoch (cuDNN autotune)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hist = DEC_training(model, loader, opt, n_epochs=1, gamma=1e-3, tol=0.0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["dec_train_epoch"] = {"workload": f"DEC_training epoch, {nspec} synthetic (1,4,101) spectrograms, B={bsz}, K=5, "
+                                              "encoder/decoder stock torch fp32, clustering path fused (configs[4] on 1 GPU)",
+                                  "seconds": dt, "points_per_s": nspec / dt, "ms": dt * 1e3, "hbm_frac": 0.0,
+                                  "loss": hist["loss"][-1] if hist["loss"] else None}
     except Exception as exc:  # pragma: no cover
         out["error"] = repr(exc)
     del flush

@@ -66,3 +66,19 @@ def spectrograms(n: int, rank: int = 0, device="cpu", dtype=torch.float32):
     x = torch.randn(n, 1, 4, 101, generator=g, device=device, dtype=dtype)
     amax = x.abs().amax(dim=(1, 2, 3), keepdim=True)      # of the un-centred sample, as the reference
     return (x - x.mean(dim=(1, 2, 3), keepdim=True)) / (amax + 1e-8)
+
+
+class TensorBatches:
+    """Minimal sequential loader over a tensor already in memory (host or device): yields contiguous
+    ``batch_size`` slices in order, like ``DataLoader(dataset, batch_size, shuffle=False)``
+    (``production.py:131-136``) without the per-item indexing + collate cost."""
+
+    def __init__(self, data: torch.Tensor, batch_size: int):
+        self.dataset, self.batch_size = data, int(batch_size)
+
+    def __len__(self):
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        for i in range(0, len(self.dataset), self.batch_size):
+            yield self.dataset[i:i + self.batch_size]
