@@ -57,6 +57,10 @@ int scc_abi_version(void);
 const char* scc_status_string(int status);
 const char* scc_last_cuda_error(void);          /* thread-local text of the last CUDA failure */
 int scc_supported(int d, int K);                /* DEC kernels instantiated for (d, K)? 1 / 0 */
+/* Profiling hook (no reference counterpart).  In the `make timeline` build of the library the DEC
+ * kernels stamp %globaltimer at their phase boundaries into device_buffer[grid][8] (uint64);
+ * pass NULL to stop.  The production library compiles the stamps out and returns SCC_ERR_UNSUPPORTED. */
+int scc_debug_set_timeline(void* device_buffer);
 int scc_gmm_supported(int d, int K);            /* GMM kernels instantiated for (d, K)? 1 / 0 */
 
 size_t scc_workspace_bytes(int d, int K);

@@ -13,7 +13,8 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libscc_b200.so")
+# SCC_LIB selects another build of the same ABI (the `make timeline` profiling variant); never a fallback.
+LIB_PATH = os.environ.get("SCC_LIB") or os.path.join(_HERE, "libscc_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "scc_b200.h")
 
 SCC_OK = 0
@@ -51,6 +52,7 @@ _SIGNATURES = {
     "scc_status_string": (c_char_p, [c_int]),
     "scc_last_cuda_error": (c_char_p, []),
     "scc_supported": (c_int, [c_int, c_int]),
+    "scc_debug_set_timeline": (c_int, [c_void_p]),
     "scc_gmm_supported": (c_int, [c_int, c_int]),
     "scc_workspace_bytes": (c_size_t, [c_int, c_int]),
     "scc_workspace_init": (c_int, [c_void_p, c_size_t, c_void_p]),

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(256)
 dec_target_kernel(const float* __restrict__ q, int64_t n, int K, double* __restrict__ f,
                   int round5, float* __restrict__ p, PeerCtx pull) {
     __shared__ float inv_f[SCC_MAX_K];
+    pdl_wait();                         // q and f are predecessor outputs
     if (pull.windows) {                 // f comes from the exchange pushed by the preceding assign kernel
         target_pull_f(pull, K, f, inv_f);
     } else if (threadIdx.x < K) {
@@ -76,7 +77,7 @@ dec_target_kernel(const float* __restrict__ q, int64_t n, int K, double* __restr
 __global__ void __launch_bounds__(kDecThreads)
 colsum_kernel(const float* __restrict__ q, int64_t n, int K, double* stats, double* partials, unsigned int* counter) {
     constexpr int KP = SCC_MAX_K;
-    __shared__ double scratch[kDecThreads];
+    __shared__ double scratch[reduce_scratch(KP)];
     __shared__ double cta_stats[KP];
     float acc[KP];
 #pragma unroll
@@ -128,10 +129,19 @@ int dec_target(const float* q, int64_t n, int K, double* f, int round_decimals, 
     const int r5 = round_decimals == 5;
     PeerCtx px{nullptr, 0, 1, 0};
     if (pull && pull->windows) px = PeerCtx{reinterpret_cast<unsigned char* const*>(pull->windows), pull->rank, pull->world, pull->max_len};
-    if (vec && K == 4) dec_target_kernel<1><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p, px);
-    else if (vec && K == 8) dec_target_kernel<2><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p, px);
-    else if (vec && K == 16) dec_target_kernel<4><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p, px);
-    else dec_target_kernel<0><<<(unsigned)grid, 256, 0, st>>>(q, n, K, f, r5, p, px);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL, see scc_common.cuh
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (vec && K == 4) SCC_CUDA(cudaLaunchKernelEx(&cfg, dec_target_kernel<1>, q, n, K, f, r5, p, px));
+    else if (vec && K == 8) SCC_CUDA(cudaLaunchKernelEx(&cfg, dec_target_kernel<2>, q, n, K, f, r5, p, px));
+    else if (vec && K == 16) SCC_CUDA(cudaLaunchKernelEx(&cfg, dec_target_kernel<4>, q, n, K, f, r5, p, px));
+    else SCC_CUDA(cudaLaunchKernelEx(&cfg, dec_target_kernel<0>, q, n, K, f, r5, p, px));
     SCC_CUDA(cudaGetLastError());
     return SCC_OK;
 }
@@ -168,6 +178,7 @@ static void fill_exchange(DecArgs& a, const ExchangeDesc* push, int do_push, con
 static void fill_reduction(DecArgs& a, void* ws) {
     a.counter = reinterpret_cast<unsigned int*>(ws);
     a.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + kWorkspaceHeader);
+    a.timeline = g_timeline;
 }
 
 int dec_assign(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,

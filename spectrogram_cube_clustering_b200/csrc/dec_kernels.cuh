@@ -22,6 +22,13 @@ namespace scc {
 constexpr int kDecThreads = 256;
 constexpr int kDecTile = 256;
 
+// doubles of reduction scratch for an NV-long statistics vector: cta_reduce needs
+// [num_warps][round_up(NV, 32)], grid_publish needs 2 * kDecThreads
+__host__ __device__ constexpr int reduce_scratch(int nv) {
+    return (kDecThreads / 32) * ((nv + 31) / 32 * 32) > 2 * kDecThreads ? (kDecThreads / 32) * ((nv + 31) / 32 * 32)
+                                                                      : 2 * kDecThreads;
+}
+
 template <int D>
 __host__ __device__ constexpr int dec_stages() { return RowLayout<D>::kDense ? 4 : (RowLayout<D>::kVec4 ? 3 : 2); }
 
@@ -41,38 +48,44 @@ __device__ __forceinline__ void pack_row(const float (&r)[D], float2 (&p)[Pairs<
 }
 
 // ---------------------------------------------------------------------------
-// q_i, u_i and the hard label of one point.  networks.py:279-288, models.py:92.
-// Distances use the exact difference form (z_c - mu_jc)^2: no cancellation.
+// Student's-t kernel of one point against every centroid.  networks.py:279-288, models.py:92.
+//   w_j = 1 + ||z - mu_j||^2 / alpha,  u_j = 1 / w_j,  t_j = u_j^((alpha+1)/2),  tsum = sum_j t_j
+// so q_j = t_j / tsum.  Distances use the exact difference form (z_c - mu_jc)^2: no cancellation.
 // nmu2_s holds the NEGATED centroids as float2 pairs [KP][DP2] (pad lane 0).
+// LABEL: also the hard label = argmin distance (== argmax q, first index wins) and that distance.
+// With alpha == 1 and no label wanted the "1 +" rides in the accumulator's initial value.
+// Reciprocals are single MUFU.RCP instructions (w >= 1, so no range fix-up is needed).
 // ---------------------------------------------------------------------------
-template <int D, int KP, bool EXACT, bool ALPHA1>
-__device__ __forceinline__ void soft_assign_row(const float2 (&z2)[Pairs<D>::N], const float2* __restrict__ nmu2_s,
-                                                int K, float inv_alpha, float expo, float (&u)[KP], float (&q)[KP],
-                                                int& label, float& best) {
+template <int D, int KP, bool EXACT, bool ALPHA1, bool LABEL>
+__device__ __forceinline__ void student_t_row(const float2 (&z2)[Pairs<D>::N], const float2* __restrict__ nmu2_s,
+                                              int K, float inv_alpha, float expo, float (&w)[KP], float (&u)[KP],
+                                              float (&t)[KP], float& tsum, int& label, float& best) {
     constexpr int DP2 = Pairs<D>::N;
-    float tsum[2] = {0.f, 0.f};               // two chains: short serial dependencies matter at 4 warps/scheduler
+    constexpr bool kOneInAcc = ALPHA1 && !LABEL;
+    float ts[2] = {0.f, 0.f};                 // two chains: short serial dependencies matter at 4 warps/scheduler
     best = 3.4e38f;
     label = 0;
 #pragma unroll
     for (int j = 0; j < KP; ++j) {
-        u[j] = 0.f; q[j] = 0.f;
+        w[j] = 1.f; u[j] = 0.f; t[j] = 0.f;
         if (EXACT || j < K) {
-            float2 acc2 = make_float2(0.f, 0.f);
+            float2 acc2 = make_float2(kOneInAcc ? 1.f : 0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < DP2; ++c) {
                 const float2 df = __fadd2_rn(z2[c], nmu2_s[j * DP2 + c]);
                 acc2 = __ffma2_rn(df, df, acc2);
             }
             const float acc = acc2.x + acc2.y;
-            if (acc < best) { best = acc; label = j; }          // argmax q == argmin distance, first wins
-            const float uu = __fdividef(1.f, ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f));
-            const float t = ALPHA1 ? uu : __powf(uu, expo);
-            u[j] = uu; q[j] = t; tsum[j & 1] += t;
+            if (LABEL) {
+                if (acc < best) { best = acc; label = j; }
+            }
+            const float ww = kOneInAcc ? acc : (ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f));
+            const float uu = rcp_approx(ww);
+            const float tt = ALPHA1 ? uu : ex2_approx(-expo * lg2_approx(ww));
+            w[j] = ww; u[j] = uu; t[j] = tt; ts[j & 1] += tt;
         }
     }
-    const float inv = __fdividef(1.f, tsum[0] + tsum[1]);
-#pragma unroll
-    for (int j = 0; j < KP; ++j) q[j] *= inv;
+    tsum = ts[0] + ts[1];
 }
 
 // negated centroids as pairs: nmu2_s[j][c] = -(mu[j][2c], mu[j][2c+1]); rows j >= K and pad lanes are 0
@@ -115,20 +128,26 @@ __device__ __forceinline__ void load_krow(const float* __restrict__ src, int K, 
 }
 
 // Reduce NV per-thread floats across the CTA into cta_stats[0..NV) (float64).
-// scratch: [num_warps][NV] doubles.  Deterministic (fixed warp order).
+// scratch: [num_warps][round_up(NV, 32)] doubles.  Deterministic (fixed tree / warp order).
+template <int NV>
+__host__ __device__ constexpr int reduce_pad() { return (NV + 31) / 32 * 32; }
+
 template <int NV, int NT>
 __device__ __forceinline__ void cta_reduce(const float (&v)[NV], double* scratch, double* cta_stats) {
+    constexpr int NVP = reduce_pad<NV>();
+    constexpr int M = NVP / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float x[NVP];
 #pragma unroll
-    for (int s = 0; s < NV; ++s) {
-        const float w = warp_sum(v[s]);
-        if (lane == 0) scratch[warp * NV + s] = (double)w;
-    }
+    for (int s = 0; s < NVP; ++s) x[s] = (s < NV) ? v[s] : 0.f;
+    warp_reduce_scatter<NVP>(x);            // lane l now holds the warp totals of entries M*l .. M*l+M-1
+#pragma unroll
+    for (int r = 0; r < M; ++r) scratch[warp * NVP + M * lane + r] = (double)x[r];
     __syncthreads();
     for (int s = threadIdx.x; s < NV; s += NT) {
         double acc = 0.0;
 #pragma unroll
-        for (int w = 0; w < NT / 32; ++w) acc += scratch[w * NV + s];
+        for (int w = 0; w < NT / 32; ++w) acc += scratch[w * NVP + s];
         cta_stats[s] = acc;
     }
     __syncthreads();
@@ -141,16 +160,16 @@ __device__ __forceinline__ void cta_reduce(const float (&v)[NV], double* scratch
 // ---------------------------------------------------------------------------
 template <int D, int KP, bool EXACT, bool ALPHA1, int P>
 __device__ __forceinline__ void soft_assign_rows(const float2 (&z2)[P][Pairs<D>::N], const float2* __restrict__ nmu2_s,
-                                                 int K, float inv_alpha, float expo, float (&u)[P][KP],
-                                                 float (&q)[P][KP], int (&label)[P], float (&best)[P]) {
+                                                 int K, float inv_alpha, float expo,
+                                                 float (&q)[P][KP], int (&label)[P]) {
     constexpr int DP2 = Pairs<D>::N;
-    float tsum[P];
+    float tsum[P], best[P];
 #pragma unroll
     for (int r = 0; r < P; ++r) { tsum[r] = 0.f; best[r] = 3.4e38f; label[r] = 0; }
 #pragma unroll
     for (int j = 0; j < KP; ++j) {
 #pragma unroll
-        for (int r = 0; r < P; ++r) { u[r][j] = 0.f; q[r][j] = 0.f; }
+        for (int r = 0; r < P; ++r) q[r][j] = 0.f;
         if (EXACT || j < K) {
             float2 acc2[P];
 #pragma unroll
@@ -168,15 +187,15 @@ __device__ __forceinline__ void soft_assign_rows(const float2 (&z2)[P][Pairs<D>:
             for (int r = 0; r < P; ++r) {
                 const float acc = acc2[r].x + acc2[r].y;
                 if (acc < best[r]) { best[r] = acc; label[r] = j; }
-                const float uu = __fdividef(1.f, ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f));
-                const float t = ALPHA1 ? uu : __powf(uu, expo);
-                u[r][j] = uu; q[r][j] = t; tsum[r] += t;
+                const float ww = ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f);
+                const float t = ALPHA1 ? rcp_approx(ww) : ex2_approx(-expo * lg2_approx(ww));
+                q[r][j] = t; tsum[r] += t;
             }
         }
     }
 #pragma unroll
     for (int r = 0; r < P; ++r) {
-        const float inv = __fdividef(1.f, tsum[r]);
+        const float inv = rcp_approx(tsum[r]);
 #pragma unroll
         for (int j = 0; j < KP; ++j) q[r][j] *= inv;
     }
@@ -205,20 +224,22 @@ dec_assign_kernel(const DecArgs a) {
     float* ring_buf = reinterpret_cast<float*>(smem_raw);
     constexpr int DP2 = Pairs<D>::N;
     float2* nmu2_s = reinterpret_cast<float2*>(ring_buf + S * Ring::kTileFloats);      // [KP][DP2] (-mu pairs)
-    double* scratch = reinterpret_cast<double*>(nmu2_s + ((KP * DP2 + 1) & ~1));       // [max(NW*(KP+1), NT)]
-    double* cta_stats = scratch + (NW * (KP + 1) > kDecThreads ? NW * (KP + 1) : kDecThreads);   // [KP+1]
+    double* scratch = reinterpret_cast<double*>(nmu2_s + ((KP * DP2 + 1) & ~1));       // [reduce_scratch(KP+1)]
+    double* cta_stats = scratch + reduce_scratch(KP + 1);                              // [KP+1]
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + (KP + 1));
 
     const int K = EXACT ? KP : a.K;
-    load_neg_centroid_pairs<D, KP>(a.mu, K, nmu2_s);
-
     Ring ring;
     ring.init(ring_buf, bars, a.z, a.n);
     __syncthreads();
+    pdl_wait();                         // no global access before this point (see scc_common.cuh)
+    SCC_TL(a.timeline, 0);
     const int G = gridDim.x;
 #pragma unroll
     for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
+    load_neg_centroid_pairs<D, KP>(a.mu, K, nmu2_s);
     __syncthreads();
+    SCC_TL(a.timeline, 1);
 
     const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
     const bool round5 = a.round5 != 0;
@@ -230,6 +251,7 @@ dec_assign_kernel(const DecArgs a) {
     uint32_t use = 0;
     for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
         ring.wait(stage, tile, use);
+        if (tile == (int)blockIdx.x) SCC_TL(a.timeline, 2);
         const int np = ring.points(tile);
         float2 z2[P][DP2];
         bool active[P];
@@ -246,10 +268,9 @@ dec_assign_kernel(const DecArgs a) {
         __syncthreads();
         ring.issue(stage, tile + S * G);
         if (active[0]) {
-            float u[P][KP], q[P][KP];
+            float q[P][KP];
             int label[P];
-            float best[P];
-            soft_assign_rows<D, KP, EXACT, ALPHA1, P>(z2, nmu2_s, K, inv_alpha, expo, u, q, label, best);
+            soft_assign_rows<D, KP, EXACT, ALPHA1, P>(z2, nmu2_s, K, inv_alpha, expo, q, label);
 #pragma unroll
             for (int r = 0; r < P; ++r) {
                 if (active[r]) {
@@ -268,26 +289,37 @@ dec_assign_kernel(const DecArgs a) {
         }
         if (++stage == S) { stage = 0; ++use; }
     }
+    pdl_trigger();                      // successor may start its prologue under our reduction tail
+    SCC_TL(a.timeline, 3);
     cta_reduce<KP + 1, kDecThreads>(facc, scratch, cta_stats);
+    SCC_TL(a.timeline, 4);
     if (!EXACT) {                       // stats layout is [K+1]: compact the KP-padded vector
         if (threadIdx.x == 0 && K < KP) cta_stats[K] = cta_stats[KP];
         __syncthreads();
     }
     const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
     grid_publish<kDecThreads>(cta_stats, K + 1, a.partials, a.counter, a.stats, scratch, &push);
+    SCC_TL(a.timeline, 5);
 }
 
 // ---------------------------------------------------------------------------
-// Per-point gradient coefficients c_ij with dz_i = sum_j c_ij (z_i - mu_j),
-// dmu_j = -sum_i c_ij (z_i - mu_j).
-//   MODE_KL      : c_ij = scale (alpha+1)/alpha (p_ij - q_ij s_i) u_ij   (+ loss)
-//   MODE_GENERIC : c_ij = -(alpha+1)/alpha q_ij (G_ij - sum_j G_ij q_ij) u_ij
-//   MODE_KMEANS  : c_ij = [j == argmin_j ||z_i - mu_j||^2]  (Lloyd step: counts, centre shifts, inertia)
+// Per-point gradient coefficients c_ij with dz_i = cs sum_j c_ij (z_i - mu_j),
+// dmu_j = -cs sum_i c_ij (z_i - mu_j).  The common factor cs is NOT applied here: it is folded into
+// the -(mu - c0) table used for dz and into the final reduction of dmu (grad_fold_scale()).
+//   MODE_KL      : c_ij = (p_ij - q_ij s_i) u_ij,  cs = scale (alpha+1)/alpha   (+ loss, in log2 units)
+//   MODE_GENERIC : c_ij = q_ij (sum_j G_ij q_ij - G_ij) u_ij,  cs = (alpha+1)/alpha
+//   MODE_KMEANS  : c_ij = [j == argmin_j ||z_i - mu_j||^2],  cs = 1  (Lloyd step: counts, centre shifts, inertia)
+// Inputs are the Student's-t quantities of student_t_row(): q_j = t_j / tsum, 1/q_j = tsum w_j^expo.
 // ---------------------------------------------------------------------------
-template <int KP, bool EXACT, int MODE>
+template <int MODE>
+__host__ __device__ __forceinline__ float grad_fold_scale(float scale, float alpha) {
+    return MODE == MODE_KMEANS ? 1.f : (MODE == MODE_KL ? scale : 1.f) * (alpha + 1.f) / alpha;
+}
+
+template <int KP, bool EXACT, bool ALPHA1, int MODE>
 __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, int K, const float* __restrict__ inv_f,
-                                                  const float (&u)[KP], const float (&q)[KP], float cscale,
-                                                  int label, float best,
+                                                  const float (&w)[KP], const float (&u)[KP], const float (&t)[KP],
+                                                  float tsum, float expo, int label, float best,
                                                   float (&coef)[KP], float& loss, float& ssum) {
     if constexpr (MODE == MODE_KMEANS) {
         // Lloyd statistics: one-hot coefficient on the nearest centre, "loss" = inertia
@@ -297,6 +329,7 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
         if (a.labels) a.labels[i] = label;
         if (a.mindist) a.mindist[i] = best;
     } else if constexpr (MODE == MODE_KL) {
+        const float inv = rcp_approx(tsum);
         float p[KP];
         if (a.p) {
             load_krow<KP, EXACT>(a.p + i * K, K, p);
@@ -304,44 +337,52 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
             float wsum = 0.f;
 #pragma unroll
             for (int j = 0; j < KP; ++j) {
-                const float qq = a.round5 ? round_dec5(q[j]) : q[j];
+                const float q = t[j] * inv;
+                const float qq = a.round5 ? round_dec5(q) : q;
                 p[j] = (EXACT || j < K) ? qq * qq * inv_f[j] : 0.f;
                 wsum += p[j];
             }
-            const float inv = 1.f / wsum;
+            const float winv = 1.f / wsum;
 #pragma unroll
             for (int j = 0; j < KP; ++j) {
-                p[j] *= inv;
+                p[j] *= winv;
                 if (a.round5) p[j] = round_dec5(p[j]);
             }
         }
+        // sum_j p_j log2(p_j / q_j) = sum_j p_j log2(p_j w_j^expo) + s log2(tsum).  The 1e-37 keeps a zero
+        // target at 0 * finite = 0 (torch KLDivLoss: xlogy); negative / NaN targets still give NaN.
         float s2[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
             if (EXACT || j < K) {
                 s2[j & 1] += p[j];
-                // xlogy(p,p) - p log q ; 0 when p == 0 (torch KLDivLoss); NaN targets still propagate
-                const float term = p[j] * __log2f(__fdividef(p[j], q[j]));
-                l2[j & 1] += (p[j] == 0.f) ? 0.f : term;
+                const float lg = ALPHA1 ? lg2_approx(fmaf(p[j], w[j], 1e-37f))
+                                        : fmaf(expo, lg2_approx(w[j]), lg2_approx(p[j] + 1e-37f));
+                l2[j & 1] = fmaf(p[j], lg, l2[j & 1]);
             }
         }
-        const float s = s2[0] + s2[1], l = l2[0] + l2[1];
+        const float s = s2[0] + s2[1];
+        const float nis = -(inv * s);
 #pragma unroll
-        for (int j = 0; j < KP; ++j) coef[j] = (EXACT || j < K) ? (p[j] - q[j] * s) * u[j] * cscale : 0.f;
-        loss = fmaf(l, 0.693147180559945f, loss); ssum += s;
+        for (int j = 0; j < KP; ++j) coef[j] = (EXACT || j < K) ? fmaf(t[j], nis, p[j]) * u[j] : 0.f;
+        loss += fmaf(s, lg2_approx(tsum), l2[0] + l2[1]);
+        ssum += s;
     } else {
+        const float inv = rcp_approx(tsum);
         float g[KP];
         load_krow<KP, EXACT>(a.grad_q + i * K, K, g);
         float dot = 0.f;
 #pragma unroll
-        for (int j = 0; j < KP; ++j) dot = fmaf(g[j], q[j], dot);
+        for (int j = 0; j < KP; ++j) dot = fmaf(g[j], t[j], dot);
+        dot *= inv;
 #pragma unroll
-        for (int j = 0; j < KP; ++j) coef[j] = (EXACT || j < K) ? -cscale * q[j] * (g[j] - dot) * u[j] : 0.f;
+        for (int j = 0; j < KP; ++j) coef[j] = (EXACT || j < K) ? (t[j] * inv) * (dot - g[j]) * u[j] : 0.f;
     }
 }
 
-// dz_c = (sum_j c_j) zc_c - sum_j c_j mc_jc  with zc = z - c0, mc = mu - c0 (algebraic form of
-// sum_j c_j (z_c - mu_jc): K*D/2 FFMA2 instead of K*D (FADD + FMA)).  nmc2_s = -(mu - c0) pairs.
+// dz_c = cs ((sum_j c_j) zc_c - sum_j c_j mc_jc)  with zc = z - c0, mc = mu - c0 (algebraic form of
+// sum_j c_j (z_c - mu_jc): K*D/2 FFMA2 instead of K*D (FADD + FMA)).  nmc2_s = -cs (mu - c0) pairs,
+// csum = cs sum_j c_j.  The pad lane of an odd D holds garbage and is never stored.
 template <int D, int KP, bool EXACT>
 __device__ __forceinline__ void dz_from_coefficients(const float2 (&zc2)[Pairs<D>::N], const float (&coef)[KP],
                                                      float csum, const float2* __restrict__ nmc2_s, int K,
@@ -388,10 +429,10 @@ __device__ __forceinline__ void copy_tile_out(const float* __restrict__ tile, fl
     }
 }
 
-// Shared prologue of the gradient kernels: -mu pairs, -(mu - c0) pairs, c0, (mu - c0), 1/f.
+// Shared prologue of the gradient kernels: -mu pairs, -cs (mu - c0) pairs, c0, (mu - c0), 1/f.
 template <int D, int KP>
-__device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, float2* nmu2_s, float2* nmc2_s,
-                                                    float* mc_s, float* c0_s, float* inv_f) {
+__device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, float cs, float2* nmu2_s,
+                                                    float2* nmc2_s, float* mc_s, float* c0_s, float* inv_f) {
     constexpr int DP2 = Pairs<D>::N;
     if (threadIdx.x < D) {
         float m = 0.f;
@@ -414,25 +455,26 @@ __device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, flo
         const bool ok = (j < K && c < D);
         const float m = ok ? a.mu[j * D + c] : 0.f;
         nmu[i] = -m;
-        nmc[i] = ok ? -(m - c0_s[c]) : 0.f;
+        nmc[i] = ok ? -cs * (m - c0_s[c]) : 0.f;
     }
     for (int i = threadIdx.x; i < KP * D; i += kDecThreads) mc_s[i] = (i < K * D) ? a.mu[i] - c0_s[i % D] : 0.f;
 }
 
 // ---------------------------------------------------------------------------
 // dec_grad, REG variant.  Per-thread accumulators: loss, sum s, W_j = sum_i c_ij,
-// B_jc = sum_i c_ij (z_ic - c0_c);  dmu_jc = -(B_jc - W_j (mu_jc - c0_c)).
+// B_jc = sum_i c_ij (z_ic - c0_c);  dmu_jc = -cs (B_jc - W_j (mu_jc - c0_c)).
+// For odd D the pad lane of the last float2 pair of the centred point is the constant 1, so W_j
+// accumulates in the pad lane of B_j for free (no separate registers / adds).
 // stats out: [loss, sum_i s_i, dmu[K*D]]
 // ---------------------------------------------------------------------------
 template <int D, int KP, bool EXACT, bool ALPHA1, int MODE>
 __global__ void __launch_bounds__(kDecThreads, (2 + KP + 2 * KP * Pairs<D>::N) <= 100 ? 2 : 1)
 dec_grad_reg_kernel(const DecArgs a) {
     constexpr int S = dec_stages<D>();
-    constexpr int NW = kDecThreads / 32;
     constexpr int DP2 = Pairs<D>::N;
+    constexpr bool kPadW = (D & 1) != 0;
     using Ring = ZRing<D, kDecTile, S, kDecThreads>;
-    constexpr int NV = 2 + KP + KP * D;
-    constexpr int SCR = NW * NV > kDecThreads ? NW * NV : kDecThreads;
+    constexpr int NV = 2 + KP + KP * D;                                      // [loss, sum s, W[KP], B[KP*D]]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring_buf = reinterpret_cast<float*>(smem_raw);
     float* out_tile = ring_buf + S * Ring::kTileFloats;                      // [TILE*LD]
@@ -441,39 +483,42 @@ dec_grad_reg_kernel(const DecArgs a) {
     float* mc_s = reinterpret_cast<float*>(nmc2_s + ((KP * DP2 + 1) & ~1));  // [KP*D]
     float* c0_s = mc_s + ((KP * D + 3) & ~3);                                // [D]
     float* inv_f = c0_s + ((D + 3) & ~3);                                    // [KP]
-    double* scratch = reinterpret_cast<double*>(inv_f + ((KP + 3) & ~3));    // [max(NW*NV, NT)]
-    double* cta_stats = scratch + SCR;                                       // [NV]  (>= K*D + 2 + K)
+    double* scratch = reinterpret_cast<double*>(inv_f + ((KP + 3) & ~3));    // [reduce_scratch(NV)]
+    double* cta_stats = scratch + reduce_scratch(NV);                        // [NV]  (>= K*D + 2 + K)
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NV);
 
     const int K = EXACT ? KP : a.K;
-    load_grad_constants<D, KP>(a, K, nmu2_s, nmc2_s, mc_s, c0_s, inv_f);
-
+    const float cs = grad_fold_scale<MODE>(a.scale, a.alpha);
     Ring ring;
     ring.init(ring_buf, bars, a.z, a.n);
     __syncthreads();
+    pdl_wait();                         // no global access before this point (see scc_common.cuh)
+    SCC_TL(a.timeline, 0);
     const int G = gridDim.x;
 #pragma unroll
     for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
+    load_grad_constants<D, KP>(a, K, cs, nmu2_s, nmc2_s, mc_s, c0_s, inv_f);
     __syncthreads();
+    SCC_TL(a.timeline, 1);
 
     const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
-    const float cscale = (MODE == MODE_KL ? a.scale : 1.f) * (a.alpha + 1.f) / a.alpha;
     const bool want_dz = a.dz != nullptr;
-    float sm[2 + KP];                     // loss, sum s, W_j
+    float sm[2 + (kPadW ? 0 : KP)];       // loss, sum s, (W_j when there is no pad lane)
 #pragma unroll
-    for (int s = 0; s < 2 + KP; ++s) sm[s] = 0.f;
+    for (int s = 0; s < 2 + (kPadW ? 0 : KP); ++s) sm[s] = 0.f;
     float2 B2[KP * DP2];                  // B_jc = sum_i c_ij (z_ic - c0_c), as pairs
 #pragma unroll
     for (int s = 0; s < KP * DP2; ++s) B2[s] = make_float2(0.f, 0.f);
     float2 nc0[DP2];
 #pragma unroll
     for (int c = 0; c < DP2; ++c)
-        nc0[c] = make_float2(-c0_s[2 * c], (2 * c + 1 < D) ? -c0_s[2 * c + 1] : 0.f);
+        nc0[c] = make_float2(-c0_s[2 * c], (2 * c + 1 < D) ? -c0_s[2 * c + 1] : 1.f);
 
     int stage = 0;
     uint32_t use = 0;
     for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
         ring.wait(stage, tile, use);
+        if (tile == (int)blockIdx.x) SCC_TL(a.timeline, 2);
         const int np = ring.points(tile);
         const bool active = (int)threadIdx.x < np;
         float zr[D];
@@ -482,19 +527,21 @@ dec_grad_reg_kernel(const DecArgs a) {
         ring.issue(stage, tile + S * G);
         if (active) {
             const size_t i = (size_t)tile * kDecTile + threadIdx.x;
-            float u[KP], q[KP], coef[KP];
+            float w[KP], u[KP], t[KP], coef[KP];
             float2 z2[DP2];
             pack_row<D>(zr, z2);
             int label;
-            float best;
-            soft_assign_row<D, KP, EXACT, ALPHA1>(z2, nmu2_s, K, inv_alpha, expo, u, q, label, best);
-            grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, label, best, coef, sm[0], sm[1]);
-            float cs2[2] = {0.f, 0.f};
+            float best, tsum;
+            student_t_row<D, KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(z2, nmu2_s, K, inv_alpha, expo, w, u, t, tsum,
+                                                                     label, best);
+            grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f, w, u, t, tsum, expo, label, best, coef,
+                                                       sm[0], sm[1]);
+            if constexpr (!kPadW) {
 #pragma unroll
-            for (int j = 0; j < KP; ++j) { sm[2 + j] += coef[j]; cs2[j & 1] += coef[j]; }
-            const float csum = cs2[0] + cs2[1];
+                for (int j = 0; j < KP; ++j) sm[2 + j] += coef[j];
+            }
 #pragma unroll
-            for (int c = 0; c < DP2; ++c) z2[c] = __fadd2_rn(z2[c], nc0[c]);       // centred point
+            for (int c = 0; c < DP2; ++c) z2[c] = __fadd2_rn(z2[c], nc0[c]);       // centred point (pad lane: 1)
 #pragma unroll
             for (int j = 0; j < KP; ++j) {
                 if (EXACT || j < K) {
@@ -504,8 +551,11 @@ dec_grad_reg_kernel(const DecArgs a) {
                 }
             }
             if (want_dz) {
+                float cs2[2] = {0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < KP; ++j) cs2[j & 1] += coef[j];
                 float dzr[D];
-                dz_from_coefficients<D, KP, EXACT>(z2, coef, csum, nmc2_s, K, dzr);
+                dz_from_coefficients<D, KP, EXACT>(z2, coef, cs * (cs2[0] + cs2[1]), nmc2_s, K, dzr);
                 store_row<D>(out_tile, threadIdx.x, dzr);
             }
         }
@@ -515,10 +565,16 @@ dec_grad_reg_kernel(const DecArgs a) {
         }
         if (++stage == S) { stage = 0; ++use; }
     }
-    if (MODE != MODE_KMEANS) sm[0] *= a.scale;        // loss = scale * sum p log(p/q)
+    pdl_trigger();                      // successor may start its prologue under our reduction tail
+    SCC_TL(a.timeline, 3);
+    if (MODE == MODE_KL) sm[0] *= a.scale * 0.693147180559945f;     // loss = scale * ln2 * sum p log2(p/q)
     float acc[NV];
+    acc[0] = sm[0]; acc[1] = sm[1];
 #pragma unroll
-    for (int s = 0; s < 2 + KP; ++s) acc[s] = sm[s];
+    for (int j = 0; j < KP; ++j) {
+        if constexpr (kPadW) acc[2 + j] = B2[j * DP2 + DP2 - 1].y;
+        else acc[2 + j] = sm[2 + (kPadW ? 0 : j)];
+    }
 #pragma unroll
     for (int j = 0; j < KP; ++j)
 #pragma unroll
@@ -526,11 +582,12 @@ dec_grad_reg_kernel(const DecArgs a) {
             acc[2 + KP + j * D + c] = (c & 1) ? B2[j * DP2 + (c >> 1)].y : B2[j * DP2 + (c >> 1)].x;
     __syncthreads();
     cta_reduce<NV, kDecThreads>(acc, scratch, cta_stats);
-    // dmu_jc = -(B_jc - W_j (mu_jc - c0_c)), compacted to [loss, sum s, dmu[K*D]]
+    SCC_TL(a.timeline, 4);
+    // dmu_jc = -cs (B_jc - W_j (mu_jc - c0_c)), compacted to [loss, sum s, dmu[K*D]]
     // (MODE_KMEANS: [inertia, 0, sum_{i in j} (z_i - mu_j) [K*D], counts[K]])
     double dmu = 0.0, wj = 0.0;
     const int o = threadIdx.x;
-    if (o < K * D) dmu = -(cta_stats[2 + KP + o] - cta_stats[2 + o / D] * (double)mc_s[o]);
+    if (o < K * D) dmu = -(double)cs * (cta_stats[2 + KP + o] - cta_stats[2 + o / D] * (double)mc_s[o]);
     if (o < K) wj = cta_stats[2 + o];
     __syncthreads();
     if (o < K * D) cta_stats[2 + o] = (MODE == MODE_KMEANS) ? -dmu : dmu;
@@ -539,6 +596,7 @@ dec_grad_reg_kernel(const DecArgs a) {
     const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
     grid_publish<kDecThreads>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials, a.counter, a.stats,
                               scratch, &push);
+    SCC_TL(a.timeline, 5);
 }
 
 // ---------------------------------------------------------------------------
@@ -571,24 +629,26 @@ dec_grad_tiled_kernel(const DecArgs a) {
     float* mc_s = reinterpret_cast<float*>(nmc2_s + KP * DP2);               // [KP*D]
     float* c0_s = mc_s + KP * D;                             // [D]
     float* inv_f = c0_s + D;                                 // [KP]
-    double* scratch = reinterpret_cast<double*>(inv_f + KP); // [max(NW*NSM, NT)]
-    double* small_s = scratch + (NW * NSM > kDecThreads ? NW * NSM : kDecThreads);   // [NSM]
+    double* scratch = reinterpret_cast<double*>(inv_f + KP); // [reduce_scratch(NSM)]
+    double* small_s = scratch + reduce_scratch(NSM);         // [NSM]
     double* cta_stats = small_s + NSM;                       // [NS + KP]
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NS + KP);
 
     const int K = EXACT ? KP : a.K;
-    load_grad_constants<D, KP>(a, K, nmu2_s, nmc2_s, mc_s, c0_s, inv_f);
-
+    const float cs = grad_fold_scale<MODE>(a.scale, a.alpha);
     Ring ring;
     ring.init(ring_buf, bars, a.z, a.n);
     __syncthreads();
+    pdl_wait();                         // no global access before this point (see scc_common.cuh)
+    SCC_TL(a.timeline, 0);
     const int G = gridDim.x;
 #pragma unroll
     for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
+    load_grad_constants<D, KP>(a, K, cs, nmu2_s, nmc2_s, mc_s, c0_s, inv_f);
     __syncthreads();
+    SCC_TL(a.timeline, 1);
 
     const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
-    const float cscale = (MODE == MODE_KL ? a.scale : 1.f) * (a.alpha + 1.f) / a.alpha;
     const bool want_dz = a.dz != nullptr;
     float2 nc0[DP2];
 #pragma unroll
@@ -619,13 +679,15 @@ dec_grad_tiled_kernel(const DecArgs a) {
             float zr[D];
             load_row<D>(ztile, threadIdx.x, zr);
             const size_t i = (size_t)tile * kDecTile + threadIdx.x;
-            float u[KP], q[KP];
+            float w[KP], u[KP], t[KP];
             float2 z2[DP2];
             pack_row<D>(zr, z2);
             int label;
-            float best;
-            soft_assign_row<D, KP, EXACT, ALPHA1>(z2, nmu2_s, K, inv_alpha, expo, u, q, label, best);
-            grad_coefficients<KP, EXACT, MODE>(a, i, K, inv_f, u, q, cscale, label, best, coef, small[0], small[1]);
+            float best, tsum;
+            student_t_row<D, KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(z2, nmu2_s, K, inv_alpha, expo, w, u, t, tsum,
+                                                                     label, best);
+            grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f, w, u, t, tsum, expo, label, best, coef,
+                                                       small[0], small[1]);
             float csum = 0.f;
 #pragma unroll
             for (int j = 0; j < KP; ++j) { small[2 + j] += coef[j]; csum += coef[j]; }
@@ -636,7 +698,7 @@ dec_grad_tiled_kernel(const DecArgs a) {
             store_row<D>(ztile, threadIdx.x, zr);     // own row, centred, for phase 2
             if (want_dz) {
                 float dzr[D];
-                dz_from_coefficients<D, KP, EXACT>(z2, coef, csum, nmc2_s, K, dzr);
+                dz_from_coefficients<D, KP, EXACT>(z2, coef, cs * csum, nmc2_s, K, dzr);
                 store_row<D>(out_tile, threadIdx.x, dzr);
             }
         }
@@ -665,7 +727,8 @@ dec_grad_tiled_kernel(const DecArgs a) {
         if (++stage == S) { stage = 0; ++use; }
     }
     // ---- CTA reduction ----
-    if (MODE != MODE_KMEANS) small[0] *= a.scale;
+    pdl_trigger();
+    if (MODE == MODE_KL) small[0] *= a.scale * 0.693147180559945f;      // loss = scale * ln2 * sum p log2(p/q)
     cta_reduce<NSM, kDecThreads>(small, scratch, small_s);
     // per-(warp, group) 4x4 partials -> shared (the ring buffer is free now), fixed-order sum
     double* part = reinterpret_cast<double*>(ring_buf);                      // [NW*G2][KP*D]
@@ -682,7 +745,7 @@ dec_grad_tiled_kernel(const DecArgs a) {
 #pragma unroll
         for (int g = 0; g < NW * G2; ++g) accd += part[(size_t)g * (KP * D) + o];
         const double v = accd - small_s[2 + o / D] * (double)mc_s[o];
-        cta_stats[2 + o] = (MODE == MODE_KMEANS) ? v : -v;
+        cta_stats[2 + o] = (MODE == MODE_KMEANS) ? v : -(double)cs * v;
     }
     if (MODE == MODE_KMEANS && (int)threadIdx.x < K) cta_stats[2 + K * D + threadIdx.x] = small_s[2 + threadIdx.x];
     if (threadIdx.x == 0) { cta_stats[0] = small_s[0]; cta_stats[1] = small_s[1]; }
@@ -699,7 +762,7 @@ template <int D, int KP>
 constexpr size_t assign_smem() {
     constexpr int S = assign_stages<D, KP>();
     constexpr int NW = kDecThreads / 32;
-    constexpr int scr = NW * (KP + 1) > kDecThreads ? NW * (KP + 1) : kDecThreads;
+    constexpr int scr = reduce_scratch(KP + 1);
     return sizeof(float) * (S * kDecTile * assign_ppt<D, KP>() * RowLayout<D>::LD + 2 * ((KP * Pairs<D>::N + 1) & ~1)) +
            sizeof(double) * (scr + (KP + 1)) + sizeof(uint64_t) * S;
 }
@@ -707,8 +770,7 @@ template <int D, int KP>
 constexpr size_t grad_reg_smem() {
     constexpr int S = dec_stages<D>();
     constexpr int NV = 2 + KP + KP * D;
-    constexpr int NW = kDecThreads / 32;
-    constexpr int SCR = NW * NV > kDecThreads ? NW * NV : kDecThreads;
+    constexpr int SCR = reduce_scratch(NV);
     return sizeof(float) * ((S + 1) * kDecTile * RowLayout<D>::LD + 4 * ((KP * Pairs<D>::N + 1) & ~1) +
                             ((KP * D + 3) & ~3) + ((D + 3) & ~3) + ((KP + 3) & ~3)) +
            sizeof(double) * (SCR + NV) + sizeof(uint64_t) * S;
@@ -720,7 +782,7 @@ constexpr size_t grad_tiled_smem() {
     constexpr int G2 = (32 / NB) > 0 ? (32 / NB) : 1;
     constexpr int NW = kDecThreads / 32;
     constexpr int NSM = KP + 2;
-    constexpr int scr = NW * NSM > kDecThreads ? NW * NSM : kDecThreads;
+    constexpr int scr = reduce_scratch(NSM);
     size_t bytes = sizeof(float) * ((S + 1) * kDecTile * RowLayout<D>::LD + kDecTile * KP + 4 * KP * Pairs<D>::N +
                                     KP * D + D + KP) +
                    sizeof(double) * (scr + NSM + KP * D + 2 + KP) + sizeof(uint64_t) * S;
@@ -739,8 +801,17 @@ static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t 
     if (grid > kMaxDecGrid) grid = kMaxDecGrid;
     if (grid > num_tiles) grid = num_tiles;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, kDecThreads, smem, stream>>>(args);
-    SCC_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kDecThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL, see scc_common.cuh
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SCC_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
     return SCC_OK;
 }
 

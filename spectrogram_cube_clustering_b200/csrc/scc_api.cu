@@ -11,6 +11,7 @@
 namespace scc {
 
 static thread_local char g_cuda_error[512] = "";
+unsigned long long* g_timeline = nullptr;
 
 void set_cuda_error(cudaError_t e, const char* what, int line) {
     snprintf(g_cuda_error, sizeof(g_cuda_error), "%s (%s) at %s [line %d]", cudaGetErrorName(e),
@@ -53,7 +54,7 @@ int persistent_grid(const void* kernel, int threads, size_t smem, int max_ctas_p
 
 size_t workspace_bytes(int d, int K) {
     if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return 0;
-    const size_t dec = (size_t)kMaxDecGrid * (size_t)(K * d + 2 + K);
+    const size_t dec = (size_t)kMaxDecGrid * (size_t)((K * d + 2 + K + 1) & ~1);   // even slot stride (grid_publish)
     const size_t gmm = (size_t)kMaxGmmGrid * (size_t)SCC_GMM_STAT_DOUBLES(K, d);
     return kWorkspaceHeader + sizeof(double) * (dec > gmm ? dec : gmm) + (size_t)(64 << 10);   // + staged GMM params
 }
@@ -77,6 +78,16 @@ const char* scc_status_string(int status) {
 }
 
 const char* scc_last_cuda_error(void) { return scc::g_cuda_error; }
+
+int scc_debug_set_timeline(void* device_buffer) {
+#ifdef SCC_TIMELINE
+    scc::g_timeline = reinterpret_cast<unsigned long long*>(device_buffer);
+    return SCC_OK;
+#else
+    (void)device_buffer;
+    return SCC_ERR_UNSUPPORTED;        // production build: the stamps are compiled out
+#endif
+}
 
 int scc_supported(int d, int K) { return scc::dec_supported(d, K) ? 1 : 0; }
 int scc_gmm_supported(int d, int K) { return scc::gmm_supported(d, K) ? 1 : 0; }

@@ -127,6 +127,40 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
 }
 
 // ----------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The DEC kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: a kernel may START while its predecessor in
+// the stream is still in its epilogue.  Rules followed by every kernel here:
+//   * before pdl_wait(): NO global-memory access at all — only the shared-memory carve-up and the
+//     mbarrier initialisation.  (The predecessor may be a foreign kernel that wrote z or mu and never
+//     triggers; its writes are only guaranteed visible after the wait.)
+//   * pdl_wait() (griddepcontrol.wait) before the first global read or write;
+//   * pdl_trigger() (griddepcontrol.launch_dependents) after the main loop, so the successor's
+//     launch latency + prologue overlap this kernel's CTA/grid reduction tail.
+// Without the launch attribute both instructions are no-ops.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------
+// In-kernel timeline (profiling builds only: `make timeline` -> libscc_b200_timeline.so, used by
+// tools/timeline.py).  Thread 0 of every CTA stamps %globaltimer at phase boundaries into
+// timeline[blockIdx.x * 8 + k].  Compiled out of the production library.
+// ----------------------------------------------------------------------------
+#ifdef SCC_TIMELINE
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define SCC_TL(ptr, k)                                                                              \
+    do {                                                                                            \
+        if (threadIdx.x == 0 && (ptr)) (ptr)[(size_t)blockIdx.x * 8 + (k)] = ::scc::globaltimer_ns(); \
+    } while (0)
+#else
+#define SCC_TL(ptr, k) do { } while (0)
+#endif
+
+// ----------------------------------------------------------------------------
 // Streaming ring of z tiles.
 //   TILE points per tile, STAGES buffers, NT threads per CTA.
 //   Protocol per CTA (tile_i = blockIdx.x + i * gridDim.x):
@@ -282,12 +316,58 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Warp "reduce-scatter" of NVP (multiple of 32) per-lane floats: log2(32) halving steps, each lane
+// keeps one half of the vector and ships the other half to its partner, so the whole reduction
+// costs NVP - NVP/32 shuffles instead of 5 * NVP.  On return lane l holds in v[0..NVP/32) the
+// warp totals of the original entries (NVP/32) * l + r.  Fixed tree order: deterministic.
+template <int NVP>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[NVP]) {
+    static_assert(NVP % 32 == 0, "pad the vector to a multiple of 32");
+    const int lane = threadIdx.x & 31;
+    int n = NVP;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int half = n / 2;
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < NVP / 2; ++i) {
+            if (i < half) {
+                const float keep = up ? v[i + half] : v[i];
+                const float send = up ? v[i] : v[i + half];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+        n = half;
+    }
+}
+
+// Single-instruction MUFU forms (no range fix-ups): callers guarantee normal, positive operands.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void ldcg_f64x2(const double* p, double& a, double& b) {
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+
 // CTA-level statistics (float64, in shared memory) -> per-CTA slot of `partials`
 // -> the last CTA to arrive sums all slots into `out` with ALL its threads:
 // thread t owns statistic s = t % S and the CTA rows r, r+R, r+2R, ... (R = NT / S row groups),
 // then the R partial sums are combined in row-group order.  The summation order depends only
 // on (grid, S, NT), so the result is deterministic for a given device.
 // `counter` must be 0 on entry and is reset.  scratch: NT doubles of shared memory.
+// `partials` needs gridDim.x * ((S + 1) & ~1) doubles.
 // Returns true in the CTA that arrived last (after `out` is complete).
 template <int NT>
 __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, double* partials,
@@ -295,9 +375,10 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
                                              const PeerCtx* push = nullptr) {
     __shared__ int s_last;
     const int tid = threadIdx.x;
-    double* mine = partials + (size_t)blockIdx.x * S;
-    if (tid < S || S > NT) {
-        for (int s = tid; s < S; s += NT) mine[s] = cta_stats[s];
+    const int SP = (S + 1) & ~1;                  // slot stride: even, so slots stay 16-byte aligned
+    double* mine = partials + (size_t)blockIdx.x * SP;
+    if (tid < SP || SP > NT) {
+        for (int s = tid; s < SP; s += NT) mine[s] = (s < S) ? cta_stats[s] : 0.0;
         __threadfence();
     }
     __syncthreads();
@@ -309,29 +390,33 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
     if (!s_last) return false;
     __threadfence();
     const int G = gridDim.x;
-    if (S <= NT) {
-        // 16 independent loads in flight per thread (the chain is L2-latency bound), summed in a
-        // fixed order
-        const int R = NT / S;
-        const int s = tid % S, r = tid / S;
-        double acc = 0.0;
+    const int C = SP / 2;                         // 128-bit columns (pairs of statistics)
+    if (2 * C <= NT) {
+        // thread t owns column pair c = t % C and the CTA rows r, r+R, r+2R, ... (R = NT / C row groups);
+        // 16 independent 128-bit loads in flight per thread (the chain is L2-latency bound), summed in
+        // a fixed order; the R partial sums are then combined in row-group order.
+        const int R = NT / C;
+        const int c = tid % C, r = tid / C;
+        double a0 = 0.0, a1 = 0.0;
         if (r < R) {
             for (int b = r; b < G; b += 16 * R) {
-                double v[16];
+                double v0[16], v1[16];
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
                     const int bb = b + u * R;
-                    v[u] = (bb < G) ? __ldcg(partials + (size_t)bb * S + s) : 0.0;
+                    v0[u] = 0.0; v1[u] = 0.0;
+                    if (bb < G) ldcg_f64x2(partials + (size_t)bb * SP + 2 * c, v0[u], v1[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < 16; ++u) acc += v[u];
+                for (int u = 0; u < 16; ++u) { a0 += v0[u]; a1 += v1[u]; }
             }
+            scratch[(r * C + c) * 2] = a0;
+            scratch[(r * C + c) * 2 + 1] = a1;
         }
-        scratch[tid] = acc;
         __syncthreads();
         double t = 0.0;
         if (tid < S) {
-            for (int rr = 0; rr < R; ++rr) t += scratch[rr * S + tid];
+            for (int rr = 0; rr < R; ++rr) t += scratch[rr * 2 * C + tid];
             out[tid] = t;
         }
         if (push && push->windows) peer_push(*push, t, S);      // fused tail: ship the vector to every rank
@@ -341,7 +426,7 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
             for (int b = 0; b < G; b += 8) {
                 double v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (b + u < G) ? __ldcg(partials + (size_t)(b + u) * S + s) : 0.0;
+                for (int u = 0; u < 8; ++u) v[u] = (b + u < G) ? __ldcg(partials + (size_t)(b + u) * SP + s) : 0.0;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) acc += v[u];
             }

@@ -48,7 +48,11 @@ struct DecArgs {
     int ex_rank, ex_world, ex_max_len;
     int ex_push;               // last CTA pushes the reduced stats to every rank's window
     int ex_pull_f;             // f_cols are pulled from the exchange pushed by the preceding assign kernel
+    unsigned long long* timeline;   // profiling builds (-DSCC_TIMELINE): [grid][8] %globaltimer stamps, or NULL
 };
+
+// Device buffer the next DEC launches stamp their phase times into (profiling builds only).
+extern unsigned long long* g_timeline;
 
 struct ExchangeDesc {          // host-side mirror of scc_exchange
     void* const* windows;

@@ -1,5 +1,6 @@
 import json,sys
-for line in sys.stdin:
+# usage: show_bench.py FILE   (or JSON lines on stdin)
+for line in (open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin):
     line=line.strip()
     if not line.startswith('{'): 
         print(line); continue
