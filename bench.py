@@ -3,11 +3,13 @@
 
 Workload at every N (weak scaling, per-GPU work fixed) = BASELINE.json configs[1]:
   "DEC ClusteringLayer forward/backward + target distribution, N=1M latent points
-   d=9 K=8 alpha=1"  — one STEP is the reference chain over one latent set:
-     dec_assign  (q, labels, f; np.round(q,5))        networks.py:279-288, models.py:92-94
-     dec_target  (p = target_distribution(q))          models.py:1320-1322
-     dec_kl_grad (loss, dL/dz, dL/dmu; q recomputed)   models.py:1124-1127
-  with (N>1) the two packed-statistics all-reduces between/after them.
+   d=9 K=8 alpha=1"  — one STEP is the reference chain over one latent set, every N-sized
+  result the reference keeps (q, labels, p, dL/dz) written to HBM:
+     dec_assign          (q, labels, f; np.round(q,5))                 networks.py:279-288, models.py:92-94
+     dec_target_kl_grad  (p = target_distribution(q) written out, loss,
+                          dL/dz, dL/dmu; q recomputed in registers)    models.py:1320-1322, 1124-1127
+  with (N>1) the two packed-statistics all-reduces between/after them.  `--unfused` runs the
+  three-kernel chain dec_assign -> dec_target -> dec_kl_grad(p) instead (also timed under "extra").
 
 Contract (one JSON line on rank 0): metric/value/unit, n_gpus, steps, warmup,
 ms_per_step, higher_is_better, scaling, vs_baseline, dtype, data, config, clocks,
@@ -220,26 +222,35 @@ def run_gpu(args):
     def k_grad(s):
         ops.dec_kl_grad(s["z"], mu, ALPHA, p=s["p"], scale=scale, out_dz=s["dz"], out_stats=s["st2"])
 
+    def k_tgrad(s):         # target distribution + KL loss + gradients in one pass; p still materialised
+        ops.dec_target_kl_grad(s["z"], mu, s["st1"], ALPHA, 5, scale, out_p=s["p"], out_dz=s["dz"], out_stats=s["st2"])
+
     fused_ex = exchange is not None and args.fused_exchange      # measured ~2 % slower than the stand-alone kernel
+    unfused = args.unfused
+
+    def step_unfused(s):
+        k_assign(s); allreduce(s["st1"]); k_target(s); k_grad(s); allreduce(s["st2"])
 
     def step(s):
-        if fused_ex:        # collectives ride on the kernels: push in the producers' tails, pull in the consumers
+        if unfused:
+            step_unfused(s)
+        elif fused_ex:      # collectives ride on the kernels: push in the producers' tails, pull in the consumers
             ex = exchange.desc
             ops.dec_assign(s["z"], mu, ALPHA, 5, out_q=s["q"], out_labels=s["labels"], out_stats=s["st1"], push=ex)
-            ops.dec_target(s["q"], s["st1"], 5, out=s["p"], pull=ex)
-            ops.dec_kl_grad(s["z"], mu, ALPHA, p=s["p"], scale=scale, out_dz=s["dz"], out_stats=s["st2"], push=ex)
+            ops.dec_target_kl_grad(s["z"], mu, None, ALPHA, 5, scale, out_p=s["p"], out_dz=s["dz"],
+                                   out_stats=s["st2"], pull_f=ex, push=ex)
             ops.peer_finish(s["st2"], ex)
         else:
-            k_assign(s); allreduce(s["st1"]); k_target(s); k_grad(s); allreduce(s["st2"])
+            k_assign(s); allreduce(s["st1"]); k_tgrad(s); allreduce(s["st2"])
 
     dbg('inputs ready')
     if fused_ex:            # one fused step must reproduce the NCCL-reduced statistics
         s0 = sets[0]
         k_assign(s0); f_ref = s0["st1"].clone(); dist.all_reduce(f_ref, group=group)
-        ops.dec_target(s0["q"], f_ref, 5, out=s0["p"]); k_grad(s0); g_ref = s0["st2"].clone(); dist.all_reduce(g_ref, group=group)
+        ops.dec_target_kl_grad(s0["z"], mu, f_ref, ALPHA, 5, scale, out_p=s0["p"], out_dz=s0["dz"], out_stats=s0["st2"])
+        g_ref = s0["st2"].clone(); dist.all_reduce(g_ref, group=group)
         step(s0)
         torch.cuda.synchronize()
-        assert torch.equal(s0["st1"], f_ref), "fused exchange: column sums differ from NCCL"
         assert torch.allclose(s0["st2"], g_ref, rtol=1e-12, atol=0), "fused exchange: gradient statistics differ from NCCL"
         dbg("fused exchange verified against NCCL")
     # warm-up (eager): also creates workspaces and primes NCCL
@@ -249,7 +260,7 @@ def run_gpu(args):
 
     dbg('eager warm-up done')
     # CUDA graphs: one per input set (pointers are baked in)
-    graphs, use_graphs = [], not args.no_graphs
+    graphs, graph_all, use_graphs = [], None, not args.no_graphs
     if use_graphs:
         try:
             cap_stream = torch.cuda.Stream()
@@ -262,9 +273,16 @@ def run_gpu(args):
                     with torch.cuda.graph(g, stream=cap_stream):
                         step(s)
                     graphs.append(g)
+                # N_SETS consecutive steps in ONE graph: the programmatic (PDL) edges between kernels then
+                # also span step boundaries and there is one graph launch per N_SETS steps
+                graph_all = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_all, stream=cap_stream):
+                    for s in sets:
+                        step(s)
             torch.cuda.synchronize()
             for g in graphs:
                 g.replay()
+            graph_all.replay()
             torch.cuda.synchronize()
         except Exception as exc:                  # pragma: no cover
             if rank == 0:
@@ -276,6 +294,17 @@ def run_gpu(args):
             graphs[i % N_SETS].replay()
         else:
             step(sets[i % N_SETS])
+
+    def run_steps(n_steps):
+        """Exactly n_steps steps: whole N_SETS-step graphs, then single-step graphs for the remainder."""
+        i = 0
+        if use_graphs and not args.single_step_graphs:
+            while i + N_SETS <= n_steps:
+                graph_all.replay()
+                i += N_SETS
+        while i < n_steps:
+            run_step(i)
+            i += 1
 
     dbg(f'graphs={use_graphs}')
     for i in range(3):
@@ -293,8 +322,7 @@ def run_gpu(args):
     barrier()
     sampler.start()
     ev0.record()
-    for i in range(args.steps):
-        run_step(i)
+    run_steps(args.steps)
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -305,56 +333,85 @@ def run_gpu(args):
     # keep the same load running a little longer so NVML gets samples even for very short regions
     # (a FIXED step count derived from the max-reduced time: every rank must issue the same collectives)
     n_extra = max(8, min(20000, int(150.0 / max(ms_total / args.steps, 1e-3))))
-    for i in range(n_extra):
-        run_step(i)
-        if i % 64 == 63:
-            torch.cuda.synchronize()
+    for i in range(0, n_extra, 64):
+        run_steps(64)
+        torch.cuda.synchronize()
     torch.cuda.synchronize()
     sampler.stop()
     ms_per_step = ms_total / args.steps
     value = n_total / (ms_per_step * 1e-3)
 
     dbg('per-kernel pass')
-    # ---------------- per-kernel durations (CUDA events, launch queue pre-loaded) ----------------
-    # The stream is first blocked by a spin kernel so that all launches + event records are queued
-    # before the GPU starts: consecutive events then bracket exactly one kernel.
-    kern = {"dec_assign": [], "dec_target": [], "dec_kl_grad": []}
-    reps = min(args.steps, 40)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(reps)]
-    torch.cuda.synchronize()
-    torch.cuda._sleep(int(4e8))
-    for r in range(reps):
-        s = sets[r % N_SETS]
-        evs[r][0].record(); k_assign(s); evs[r][1].record(); k_target(s); evs[r][2].record(); k_grad(s)
-        evs[r][3].record()
-    torch.cuda.synchronize()
-    for r in range(reps):
-        kern["dec_assign"].append(evs[r][0].elapsed_time(evs[r][1]))
-        kern["dec_target"].append(evs[r][1].elapsed_time(evs[r][2]))
-        kern["dec_kl_grad"].append(evs[r][2].elapsed_time(evs[r][3]))
-    kavg = {k: sum(v) / len(v) for k, v in kern.items()}
-    alg_bytes = {"dec_assign": 4 * D + 4 * K + 4, "dec_target": 8 * K, "dec_kl_grad": 8 * D + 4 * K}   # per point
+    # ---------------- per-kernel durations ----------------
+    # One CUDA graph per kernel holding that launch on each of the N_SETS rotating input sets; the
+    # replays are timed with CUDA events on the launching stream, so a kernel's figure is its average
+    # launch duration in steady state (in-graph launch gaps included), inputs cold in L2 like the step.
+    def graph_of(fn):
+        cs = torch.cuda.Stream()
+        with torch.cuda.stream(cs):
+            for s_ in sets:
+                fn(s_)
+            cs.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cs):
+                for s_ in sets:
+                    fn(s_)
+        torch.cuda.synchronize()
+        return g
+
+    def time_graph(g, launches, reps):
+        for _ in range(3):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (reps * launches)
+
+    reps = max(5, min(args.steps, 50))
+    kfns = {"dec_assign": k_assign, "dec_target": k_target, "dec_kl_grad": k_grad} if unfused else \
+           {"dec_assign": k_assign, "dec_target_kl_grad": k_tgrad}
+    for s_ in sets:                      # q / f / p of every set valid for the stand-alone kernels
+        k_assign(s_); k_target(s_)
+    kavg = {k: time_graph(graph_of(fn), N_SETS, reps) for k, fn in kfns.items()}
+    alg_bytes = {"dec_assign": 4 * D + 4 * K + 4, "dec_target": 8 * K, "dec_kl_grad": 8 * D + 4 * K,
+                 "dec_target_kl_grad": 8 * D + 4 * K}                                  # per point
     dominant = max(kavg, key=kavg.get)
     achieved = alg_bytes[dominant] * N_PER_GPU / (kavg[dominant] * 1e-3) / 1e9
-    step_bytes = sum(alg_bytes.values())
+    step_bytes = sum(alg_bytes[k] for k in kavg)
     traffic = None
     try:          # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f)
         traffic = tr.get({"dec_assign": "dec_assign_kernel", "dec_target": "dec_target_kernel",
-                          "dec_kl_grad": "dec_grad_reg_kernel"}[dominant])
+                          "dec_kl_grad": "dec_grad_reg_kernel", "dec_target_kl_grad": "dec_grad_reg_kernel_fused"}[dominant])
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic,
-                "traffic_note": "ncu cold-cache capture (profiles/r01_ncu_dec.txt); dz/p written by the kernel are still "
-                                "in the 126 MB L2 when it ends, so DRAM writes are below the algorithmic store bytes",
+                "traffic_note": "ncu cold-cache capture (profiles/); rows written by the kernel are still in the "
+                                "126 MB L2 when it ends, so DRAM writes are below the algorithmic store bytes",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_point": alg_bytes[dominant],
+                "algorithmic_bytes": "z read 4d + p written 4K + dz written 4d (q is recomputed in registers)"
+                                     if dominant == "dec_target_kl_grad" else None,
                 "kernels_ms": kavg,
                 "kernels_gbs": {k: alg_bytes[k] * N_PER_GPU / (kavg[k] * 1e-3) / 1e9 for k in kavg},
+                "step_bytes_per_point": step_bytes,
                 "step_gbs": step_bytes * N_PER_GPU / (ms_per_step * 1e-3) / 1e9,
-                "step_frac": step_bytes * N_PER_GPU / (ms_per_step * 1e-3) / 1e9 / hbm_peak}
+                "step_frac": step_bytes * N_PER_GPU / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                "fp32_note": "the kernel is FP32-issue/latency-bound, not HBM-bound (SURVEY.md 8d; profiles/)"}
+
+    unfused_extra = None
+    if world == 1 and not unfused:       # the three-kernel chain of the earlier rounds, for comparison
+        g3 = graph_of(lambda s_: (k_assign(s_), k_target(s_), k_grad(s_)))
+        ms3 = time_graph(g3, N_SETS, reps)
+        unfused_extra = {"workload": "dec_assign -> dec_target -> dec_kl_grad(p): the 3-kernel chain (240 B/point)",
+                         "ms": ms3, "points_per_s": N_PER_GPU / (ms3 * 1e-3),
+                         "hbm_frac": 240 * N_PER_GPU / (ms3 * 1e-3) / 1e9 / hbm_peak}
 
     dbg('e2e pass')
     # ---------------- end to end: host buffers in, host results out, every step ----------------
@@ -385,17 +442,23 @@ def run_gpu(args):
         main.wait_event(up_done[b])
         zd = zd2[b]
         mud.copy_(mu_h, non_blocking=True)
-        if fused_ex:
-            ex = exchange.desc
-            ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"], push=ex)
-            ops.dec_target(sd["q"], sd["st1"], 5, out=sd["p"], pull=ex)
-            ops.dec_kl_grad(zd, mud, ALPHA, p=sd["p"], scale=scale, out_dz=sd["dz"], out_stats=sd["st2"], push=ex)
-            ops.peer_finish(sd["st2"], ex)
-        else:
+        if unfused:
             ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"])
             allreduce(sd["st1"])
             ops.dec_target(sd["q"], sd["st1"], 5, out=sd["p"])
             ops.dec_kl_grad(zd, mud, ALPHA, p=sd["p"], scale=scale, out_dz=sd["dz"], out_stats=sd["st2"])
+            allreduce(sd["st2"])
+        elif fused_ex:
+            ex = exchange.desc
+            ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"], push=ex)
+            ops.dec_target_kl_grad(zd, mud, None, ALPHA, 5, scale, out_p=sd["p"], out_dz=sd["dz"], out_stats=sd["st2"],
+                                   pull_f=ex, push=ex)
+            ops.peer_finish(sd["st2"], ex)
+        else:
+            ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"])
+            allreduce(sd["st1"])
+            ops.dec_target_kl_grad(zd, mud, sd["st1"], ALPHA, 5, scale, out_p=sd["p"], out_dz=sd["dz"],
+                                   out_stats=sd["st2"])
             allreduce(sd["st2"])
         buf_free[b].record(main)
         res_h[:K * D + 2].copy_(sd["st2"], non_blocking=True)
@@ -421,7 +484,7 @@ def run_gpu(args):
     e2e_ms = float(t.item())
     e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int(zd2[0].numel() * 4 + mud.numel() * 4), "d2h_bytes_per_step": int(res_h.numel() * 8),
-           "ms_per_step": e2e_ms, "api": "ops.dec_assign/dec_target/dec_kl_grad on a pinned host latent set "
+           "ms_per_step": e2e_ms, "api": "ops.dec_assign + ops.dec_target_kl_grad on a pinned host latent set "
                                          "(upload of step i+1 double-buffered behind step i's kernels); "
                                          "loss, dmu, f, label-change count read back every step", "loss": loss_h}
 
@@ -429,6 +492,8 @@ def run_gpu(args):
     extra = {}
     if world == 1 and not args.no_extra:
         extra = extra_benchmarks(torch, ops, synth, dev, hbm_peak)
+    if unfused_extra is not None:
+        extra["dec_step_3_kernels"] = unfused_extra
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -447,12 +512,17 @@ def run_gpu(args):
                                            "last CTA, pull in the consumer's prologue)" if fused_ex else
                                            "one-shot NVLink peer-memory exchange kernel") if exchange is not None else "NCCL"))
                                       if world > 1 else "single GPU",
-                       "launch": "CUDA graph replay per step" if use_graphs else "eager launches",
+                       "launch": (("one CUDA graph replay per step" if args.single_step_graphs else
+                                   f"CUDA graph replays of {N_SETS} consecutive steps (one per rotating input set)")
+                                  if use_graphs else "eager launches"),
+                       "kernels_per_step": ["dec_assign", "dec_target", "dec_kl_grad"] if unfused else
+                                           ["dec_assign", "dec_target_kl_grad"],
                        "l2": f"inputs/outputs rotate over {N_SETS} sets ({N_SETS * 140} MB) > 126 MB L2",
                        "timing": "CUDA events around the K steps, max over ranks; per-kernel durations from "
-                                 "CUDA events in a second pass with the launch queue pre-loaded"},
+                                 "CUDA events around replays of single-kernel graphs over the same rotating sets"},
             "clocks": sampler.summary(), "e2e": e2e,
-            "gpu_launches": (3 + ((1 if fused_ex else 2) if exchange is not None else 0)) * args.steps, "roofline": roofline,
+            "gpu_launches": ((3 if unfused else 2) + ((1 if fused_ex else 2) if exchange is not None else 0)) * args.steps,
+            "roofline": roofline,
             "cpu_baseline": cpu, "extra": extra,
         }
         print(json.dumps(line), flush=True)
@@ -462,6 +532,7 @@ def run_gpu(args):
         # guarantees the process exits even if communicator teardown stalls.
         threading.Timer(20.0, lambda: os._exit(0)).start()
         graphs.clear()
+        graph_all = None
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
@@ -583,8 +654,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--single-step-graphs", action="store_true", help="one graph replay per step")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--unfused", action="store_true",
+                    help="three-kernel chain dec_assign -> dec_target -> dec_kl_grad(p) instead of the fused "
+                         "target + KL-gradient kernel")
     ap.add_argument("--nccl", action="store_true", help="use NCCL all_reduce instead of the peer-memory exchange")
     ap.add_argument("--fused-exchange", action="store_true",
                     help="ride the exchange on the kernels (push in the producer's last CTA, pull in the consumer) "

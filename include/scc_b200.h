@@ -277,6 +277,21 @@ int scc_dec_kl_grad_ex(const float* z, int64_t n, int d, const float* mu, int K,
                        const float* p, const double* f_cols, int round_decimals, float scale, float* dz,
                        double* stats, void* workspace, size_t workspace_bytes,
                        const scc_exchange* pull_f, const scc_exchange* push, scc_stream_t stream);
+/*
+ * scc_dec_target_kl_grad — target distribution + KL loss + gradients in ONE pass over z.
+ *   The step `p = target_distribution(np.round(q, 5))` (Cluster/models.py:1302-1322) followed by
+ *   `gamma * KLDivLoss('sum')(log q, p) / B` + backward (models.py:1124-1127) for the same batch:
+ *   q is recomputed from z in registers, p is rebuilt per point from the column sums f_cols[K]
+ *   (output of scc_dec_assign; or pulled from the exchange `pull_f`) with the same rounding as
+ *   scc_dec_target, consumed by the loss / gradient and — when p_out != NULL — written out as the
+ *   [n, K] float32 target the reference keeps (`tar_dist`).  Replaces scc_dec_target +
+ *   scc_dec_kl_grad(p) and saves one read of q, one read of p and a launch.
+ *   p_out, dz nullable; pull_f / push nullable (single GPU).  stats as scc_dec_kl_grad.
+ */
+int scc_dec_target_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float alpha,
+                           const double* f_cols, int round_decimals, float scale, float* p_out, float* dz,
+                           double* stats, void* workspace, size_t workspace_bytes,
+                           const scc_exchange* pull_f, const scc_exchange* push, scc_stream_t stream);
 int scc_peer_finish(double* out, int len, const scc_exchange* ex, scc_stream_t stream);
 int scc_peer_allreduce(const double* local, int len, double* out,
                        void* const* peer_windows, int rank, int world, int max_len,

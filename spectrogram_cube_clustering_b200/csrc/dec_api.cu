@@ -213,10 +213,13 @@ static int dec_grad_dispatch(const DecArgs& a, int d, int mode, cudaStream_t st)
 
 int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* p,
                 const double* f_cols, int round_decimals, float scale, float* dz, double* stats,
-                void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* pull_f, const ExchangeDesc* push) {
+                void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* pull_f, const ExchangeDesc* push,
+                float* p_out) {
     int rc = check_common(z, n, d, mu, K, alpha, stats, ws, ws_bytes);
     if (rc != SCC_OK) return rc;
     if (!p && !f_cols && !(pull_f && pull_f->windows)) return SCC_ERR_INVALID;
+    if (p && p_out) return SCC_ERR_INVALID;            // the target is either given or produced, not both
+    if (p_out && (K % 4 == 0) && (reinterpret_cast<uintptr_t>(p_out) & 15u)) return SCC_ERR_MISALIGNED;
     if (round_decimals != 0 && round_decimals != 5) return SCC_ERR_INVALID;
     if (p && (K % 4 == 0) && (reinterpret_cast<uintptr_t>(p) & 15u)) return SCC_ERR_MISALIGNED;
     if (dz && (reinterpret_cast<uintptr_t>(dz) & 15u)) return SCC_ERR_MISALIGNED;
@@ -227,7 +230,7 @@ int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float 
     }
     DecArgs a{};
     a.z = z; a.n = n; a.mu = mu; a.K = K; a.alpha = alpha; a.round5 = round_decimals == 5;
-    a.p = p; a.f_cols = f_cols; a.scale = scale; a.dz = dz; a.stats = stats;
+    a.p = p; a.p_out = p_out; a.f_cols = f_cols; a.scale = scale; a.dz = dz; a.stats = stats;
     fill_reduction(a, ws);
     fill_exchange(a, push, 1, p ? nullptr : pull_f);
     return dec_grad_dispatch(a, d, MODE_KL, st);

@@ -53,15 +53,14 @@ __device__ __forceinline__ void pack_row(const float (&r)[D], float2 (&p)[Pairs<
 // so q_j = t_j / tsum.  Distances use the exact difference form (z_c - mu_jc)^2: no cancellation.
 // nmu2_s holds the NEGATED centroids as float2 pairs [KP][DP2] (pad lane 0).
 // LABEL: also the hard label = argmin distance (== argmax q, first index wins) and that distance.
-// With alpha == 1 and no label wanted the "1 +" rides in the accumulator's initial value.
-// Reciprocals are single MUFU.RCP instructions (w >= 1, so no range fix-up is needed).
+// The arithmetic (operation order included) is the same as soft_assign_rows() of the assign kernel,
+// so the gradient kernels recompute bit-identical q.  Reciprocals are single MUFU.RCP instructions (w >= 1, so no range fix-up is needed).
 // ---------------------------------------------------------------------------
 template <int D, int KP, bool EXACT, bool ALPHA1, bool LABEL>
 __device__ __forceinline__ void student_t_row(const float2 (&z2)[Pairs<D>::N], const float2* __restrict__ nmu2_s,
                                               int K, float inv_alpha, float expo, float (&w)[KP], float (&u)[KP],
                                               float (&t)[KP], float& tsum, int& label, float& best) {
     constexpr int DP2 = Pairs<D>::N;
-    constexpr bool kOneInAcc = ALPHA1 && !LABEL;
     float ts[2] = {0.f, 0.f};                 // two chains: short serial dependencies matter at 4 warps/scheduler
     best = 3.4e38f;
     label = 0;
@@ -69,7 +68,7 @@ __device__ __forceinline__ void student_t_row(const float2 (&z2)[Pairs<D>::N], c
     for (int j = 0; j < KP; ++j) {
         w[j] = 1.f; u[j] = 0.f; t[j] = 0.f;
         if (EXACT || j < K) {
-            float2 acc2 = make_float2(kOneInAcc ? 1.f : 0.f, 0.f);
+            float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < DP2; ++c) {
                 const float2 df = __fadd2_rn(z2[c], nmu2_s[j * DP2 + c]);
@@ -79,7 +78,7 @@ __device__ __forceinline__ void student_t_row(const float2 (&z2)[Pairs<D>::N], c
             if (LABEL) {
                 if (acc < best) { best = acc; label = j; }
             }
-            const float ww = kOneInAcc ? acc : (ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f));
+            const float ww = ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f);
             const float uu = rcp_approx(ww);
             const float tt = ALPHA1 ? uu : ex2_approx(-expo * lg2_approx(ww));
             w[j] = ww; u[j] = uu; t[j] = tt; ts[j & 1] += tt;
@@ -163,9 +162,9 @@ __device__ __forceinline__ void soft_assign_rows(const float2 (&z2)[P][Pairs<D>:
                                                  int K, float inv_alpha, float expo,
                                                  float (&q)[P][KP], int (&label)[P]) {
     constexpr int DP2 = Pairs<D>::N;
-    float tsum[P], best[P];
+    float tsum[P][2], best[P];
 #pragma unroll
-    for (int r = 0; r < P; ++r) { tsum[r] = 0.f; best[r] = 3.4e38f; label[r] = 0; }
+    for (int r = 0; r < P; ++r) { tsum[r][0] = 0.f; tsum[r][1] = 0.f; best[r] = 3.4e38f; label[r] = 0; }
 #pragma unroll
     for (int j = 0; j < KP; ++j) {
 #pragma unroll
@@ -189,13 +188,13 @@ __device__ __forceinline__ void soft_assign_rows(const float2 (&z2)[P][Pairs<D>:
                 if (acc < best[r]) { best[r] = acc; label[r] = j; }
                 const float ww = ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f);
                 const float t = ALPHA1 ? rcp_approx(ww) : ex2_approx(-expo * lg2_approx(ww));
-                q[r][j] = t; tsum[r] += t;
+                q[r][j] = t; tsum[r][j & 1] += t;
             }
         }
     }
 #pragma unroll
     for (int r = 0; r < P; ++r) {
-        const float inv = rcp_approx(tsum[r]);
+        const float inv = rcp_approx(tsum[r][0] + tsum[r][1]);
 #pragma unroll
         for (int j = 0; j < KP; ++j) q[r][j] *= inv;
     }
@@ -219,14 +218,19 @@ dec_assign_kernel(const DecArgs a) {
     constexpr int TILE = kDecTile * P;
     constexpr int S = assign_stages<D, KP>();
     constexpr int NW = kDecThreads / 32;
+    // CTA-level ring: a per-warp ring (WarpRing) was measured for this kernel too — its 6x more, 6x smaller
+    // TMA copies lengthen the prologue by ~1.3 us and the short main loop gains nothing
     using Ring = ZRing<D, TILE, S, kDecThreads>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring_buf = reinterpret_cast<float*>(smem_raw);
     constexpr int DP2 = Pairs<D>::N;
     float2* nmu2_s = reinterpret_cast<float2*>(ring_buf + S * Ring::kTileFloats);      // [KP][DP2] (-mu pairs)
-    double* scratch = reinterpret_cast<double*>(nmu2_s + ((KP * DP2 + 1) & ~1));       // [reduce_scratch(KP+1)]
-    double* cta_stats = scratch + reduce_scratch(KP + 1);                              // [KP+1]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + (KP + 1));
+    double* cta_stats = reinterpret_cast<double*>(nmu2_s + ((KP * DP2 + 1) & ~1));     // [KP+1]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + (KP + 1));                // [S]
+    // the reduction scratch [reduce_scratch(KP+1)] reuses the ring once the main loop is over: keeping it
+    // separate pushes the d = 32 kernel (3 x 36 KB of stages) over half an SM's shared memory -> 1 CTA/SM
+    double* scratch = reinterpret_cast<double*>(ring_buf);
+    static_assert(sizeof(float) * S * Ring::kTileFloats >= sizeof(double) * reduce_scratch(KP + 1), "ring too small");
 
     const int K = EXACT ? KP : a.K;
     Ring ring;
@@ -265,7 +269,7 @@ dec_assign_kernel(const DecArgs a) {
             if (active[r]) load_row<D>(ring.stage_ptr(stage), t, zr);
             pack_row<D>(zr, z2[r]);
         }
-        __syncthreads();
+        __syncthreads();                 // every row of the stage is in registers: refill it
         ring.issue(stage, tile + S * G);
         if (active[0]) {
             float q[P][KP];
@@ -291,6 +295,7 @@ dec_assign_kernel(const DecArgs a) {
     }
     pdl_trigger();                      // successor may start its prologue under our reduction tail
     SCC_TL(a.timeline, 3);
+    __syncthreads();                    // every warp is done with the ring: it becomes the reduction scratch
     cta_reduce<KP + 1, kDecThreads>(facc, scratch, cta_stats);
     SCC_TL(a.timeline, 4);
     if (!EXACT) {                       // stats layout is [K+1]: compact the KP-padded vector
@@ -311,6 +316,20 @@ dec_assign_kernel(const DecArgs a) {
 //   MODE_KMEANS  : c_ij = [j == argmin_j ||z_i - mu_j||^2],  cs = 1  (Lloyd step: counts, centre shifts, inertia)
 // Inputs are the Student's-t quantities of student_t_row(): q_j = t_j / tsum, 1/q_j = tsum w_j^expo.
 // ---------------------------------------------------------------------------
+// The [n, K] operand a gradient kernel streams besides z: the target p (MODE_KL, API mode) or the
+// upstream gradient dL/dq (MODE_GENERIC).  The row is requested at the top of the iteration, before
+// the wait on the z tile.  (Requesting it a whole iteration ahead was measured: the 8 extra live
+// registers spill at the 128-register cap and the kernel got 12 % slower.)
+template <int MODE>
+__device__ __forceinline__ const float* krow_operand(const DecArgs& a) {
+    return MODE == MODE_KL ? a.p : (MODE == MODE_GENERIC ? a.grad_q : nullptr);
+}
+template <int KP, bool EXACT>
+__device__ __forceinline__ void prefetch_krow(const float* __restrict__ src, int64_t base, int np, int K,
+                                              float (&row)[KP]) {
+    if (src && (int)threadIdx.x < np) load_krow<KP, EXACT>(src + ((size_t)base + threadIdx.x) * K, K, row);
+}
+
 template <int MODE>
 __host__ __device__ __forceinline__ float grad_fold_scale(float scale, float alpha) {
     return MODE == MODE_KMEANS ? 1.f : (MODE == MODE_KL ? scale : 1.f) * (alpha + 1.f) / alpha;
@@ -320,6 +339,7 @@ template <int KP, bool EXACT, bool ALPHA1, int MODE>
 __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, int K, const float* __restrict__ inv_f,
                                                   const float (&w)[KP], const float (&u)[KP], const float (&t)[KP],
                                                   float tsum, float expo, int label, float best,
+                                                  const float (&pre)[KP],
                                                   float (&coef)[KP], float& loss, float& ssum) {
     if constexpr (MODE == MODE_KMEANS) {
         // Lloyd statistics: one-hot coefficient on the nearest centre, "loss" = inertia
@@ -331,16 +351,30 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
     } else if constexpr (MODE == MODE_KL) {
         const float inv = rcp_approx(tsum);
         float p[KP];
-        if (a.p) {
-            load_krow<KP, EXACT>(a.p + i * K, K, p);
+        if (a.p) {                                 // target row prefetched one tile ahead (prefetch_krow)
+#pragma unroll
+            for (int j = 0; j < KP; ++j) p[j] = pre[j];
         } else {                                   // rebuild p from the column sums (fused mode)
-            float wsum = 0.f;
 #pragma unroll
             for (int j = 0; j < KP; ++j) {
                 const float q = t[j] * inv;
                 const float qq = a.round5 ? round_dec5(q) : q;
                 p[j] = (EXACT || j < K) ? qq * qq * inv_f[j] : 0.f;
-                wsum += p[j];
+            }
+            // row sum in the order dec_target_kernel uses (groups of 4, then a pairwise tree over the
+            // groups; sequential when K is not 4, 8 or 16), so the rebuilt p is bit-identical to its output
+            float wsum;
+            if ((K & 3) == 0 && K != 12) {
+                float g4[KP / 4];
+#pragma unroll
+                for (int b = 0; b < KP / 4; ++b) g4[b] = (p[4 * b] + p[4 * b + 1]) + (p[4 * b + 2] + p[4 * b + 3]);
+                if constexpr (KP == 4) wsum = g4[0];
+                else if constexpr (KP == 8) wsum = (K == 4) ? g4[0] : g4[0] + g4[1];
+                else wsum = (K == 4) ? g4[0] : ((K == 8) ? g4[0] + g4[1] : (g4[0] + g4[1]) + (g4[2] + g4[3]));
+            } else {
+                wsum = 0.f;
+#pragma unroll
+                for (int j = 0; j < KP; ++j) wsum += (EXACT || j < K) ? p[j] : 0.f;
             }
             const float winv = 1.f / wsum;
 #pragma unroll
@@ -348,6 +382,7 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
                 p[j] *= winv;
                 if (a.round5) p[j] = round_dec5(p[j]);
             }
+            if (a.p_out) store_krow<KP, EXACT>(a.p_out + i * K, K, p);      // materialise target_distribution(q)
         }
         // sum_j p_j log2(p_j / q_j) = sum_j p_j log2(p_j w_j^expo) + s log2(tsum).  The 1e-37 keeps a zero
         // target at 0 * finite = 0 (torch KLDivLoss: xlogy); negative / NaN targets still give NaN.
@@ -370,7 +405,8 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
     } else {
         const float inv = rcp_approx(tsum);
         float g[KP];
-        load_krow<KP, EXACT>(a.grad_q + i * K, K, g);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) g[j] = pre[j];
         float dot = 0.f;
 #pragma unroll
         for (int j = 0; j < KP; ++j) dot = fmaf(g[j], t[j], dot);
@@ -473,25 +509,30 @@ dec_grad_reg_kernel(const DecArgs a) {
     constexpr int S = dec_stages<D>();
     constexpr int DP2 = Pairs<D>::N;
     constexpr bool kPadW = (D & 1) != 0;
-    using Ring = ZRing<D, kDecTile, S, kDecThreads>;
+    using Ring = WarpRing<D, kDecTile, S, kDecThreads>;
+    using L = RowLayout<D>;
     constexpr int NV = 2 + KP + KP * D;                                      // [loss, sum s, W[KP], B[KP*D]]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring_buf = reinterpret_cast<float*>(smem_raw);
-    float* out_tile = ring_buf + S * Ring::kTileFloats;                      // [TILE*LD]
-    float2* nmu2_s = reinterpret_cast<float2*>(out_tile + Ring::kTileFloats);  // [KP][DP2]
+    // dz staging, per warp: dense row layouts ship the warp's 32 rows with a TMA bulk store from two
+    // alternating buffers; padded layouts keep one buffer and a coalesced copy by the warp's lanes
+    constexpr bool kBulkOut = L::kDense;
+    constexpr int NOUT = kBulkOut ? 2 : 1;
+    float* out_tile = ring_buf + S * Ring::kTileFloats;                      // [NOUT][TILE*LD]
+    float2* nmu2_s = reinterpret_cast<float2*>(out_tile + NOUT * Ring::kTileFloats);  // [KP][DP2]
     float2* nmc2_s = nmu2_s + ((KP * DP2 + 1) & ~1);                         // [KP][DP2]
     float* mc_s = reinterpret_cast<float*>(nmc2_s + ((KP * DP2 + 1) & ~1));  // [KP*D]
     float* c0_s = mc_s + ((KP * D + 3) & ~3);                                // [D]
     float* inv_f = c0_s + ((D + 3) & ~3);                                    // [KP]
-    double* scratch = reinterpret_cast<double*>(inv_f + ((KP + 3) & ~3));    // [reduce_scratch(NV)]
+    float2* nc0_s = reinterpret_cast<float2*>(inv_f + ((KP + 3) & ~3));      // [DP2] -c0 pairs (pad lane: +1)
+    double* scratch = reinterpret_cast<double*>(nc0_s + ((DP2 + 1) & ~1));   // [reduce_scratch(NV)]
     double* cta_stats = scratch + reduce_scratch(NV);                        // [NV]  (>= K*D + 2 + K)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NV);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NV);            // [NW][S]
 
     const int K = EXACT ? KP : a.K;
     const float cs = grad_fold_scale<MODE>(a.scale, a.alpha);
     Ring ring;
     ring.init(ring_buf, bars, a.z, a.n);
-    __syncthreads();
     pdl_wait();                         // no global access before this point (see scc_common.cuh)
     SCC_TL(a.timeline, 0);
     const int G = gridDim.x;
@@ -509,22 +550,32 @@ dec_grad_reg_kernel(const DecArgs a) {
     float2 B2[KP * DP2];                  // B_jc = sum_i c_ij (z_ic - c0_c), as pairs
 #pragma unroll
     for (int s = 0; s < KP * DP2; ++s) B2[s] = make_float2(0.f, 0.f);
-    float2 nc0[DP2];
-#pragma unroll
-    for (int c = 0; c < DP2; ++c)
-        nc0[c] = make_float2(-c0_s[2 * c], (2 * c + 1 < D) ? -c0_s[2 * c + 1] : 1.f);
+    // -c0 as pairs, read back from shared memory once per tile (keeping them in registers costs
+    // 2*DP2 live registers the accumulators need)
+    if (threadIdx.x < DP2)
+        nc0_s[threadIdx.x] = make_float2(-c0_s[2 * threadIdx.x],
+                                         (2 * threadIdx.x + 1 < D) ? -c0_s[2 * threadIdx.x + 1] : 1.f);
+    __syncthreads();
 
-    int stage = 0;
+    const float* krows = krow_operand<MODE>(a);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int stage = 0, ob = 0;
     uint32_t use = 0;
-    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
-        ring.wait(stage, tile, use);
-        if (tile == (int)blockIdx.x) SCC_TL(a.timeline, 2);
+    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {       // no CTA-wide barrier in this loop
         const int np = ring.points(tile);
         const bool active = (int)threadIdx.x < np;
+        // the [n, K] operand row (target p / upstream dL/dq) is requested before the wait on the z tile
+        float kcur[KP];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) kcur[j] = 0.f;
+        prefetch_krow<KP, EXACT>(krows, (int64_t)tile * kDecTile, np, K, kcur);
+        ring.wait(stage, tile, use);
+        if (tile == (int)blockIdx.x) SCC_TL(a.timeline, 2);
         float zr[D];
         if (active) load_row<D>(ring.stage_ptr(stage), threadIdx.x, zr);
-        __syncthreads();                 // stage free; previous out_tile fully copied out
+        __syncwarp();                    // the warp's rows are in registers (and its previous dz rows copied out)
         ring.issue(stage, tile + S * G);
+        float* out_cur = out_tile + ob * Ring::kTileFloats;
         if (active) {
             const size_t i = (size_t)tile * kDecTile + threadIdx.x;
             float w[KP], u[KP], t[KP], coef[KP];
@@ -534,14 +585,14 @@ dec_grad_reg_kernel(const DecArgs a) {
             float best, tsum;
             student_t_row<D, KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(z2, nmu2_s, K, inv_alpha, expo, w, u, t, tsum,
                                                                      label, best);
-            grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f, w, u, t, tsum, expo, label, best, coef,
+            grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f, w, u, t, tsum, expo, label, best, kcur, coef,
                                                        sm[0], sm[1]);
             if constexpr (!kPadW) {
 #pragma unroll
                 for (int j = 0; j < KP; ++j) sm[2 + j] += coef[j];
             }
 #pragma unroll
-            for (int c = 0; c < DP2; ++c) z2[c] = __fadd2_rn(z2[c], nc0[c]);       // centred point (pad lane: 1)
+            for (int c = 0; c < DP2; ++c) z2[c] = __fadd2_rn(z2[c], nc0_s[c]);     // centred point (pad lane: 1)
 #pragma unroll
             for (int j = 0; j < KP; ++j) {
                 if (EXACT || j < K) {
@@ -556,15 +607,33 @@ dec_grad_reg_kernel(const DecArgs a) {
                 for (int j = 0; j < KP; ++j) cs2[j & 1] += coef[j];
                 float dzr[D];
                 dz_from_coefficients<D, KP, EXACT>(z2, coef, cs * (cs2[0] + cs2[1]), nmc2_s, K, dzr);
-                store_row<D>(out_tile, threadIdx.x, dzr);
+                store_row<D>(out_cur, threadIdx.x, dzr);
             }
         }
         if (want_dz) {
-            __syncthreads();
-            copy_tile_out<D, kDecThreads>(out_tile, a.dz + (size_t)tile * (kDecTile * D), np);
+            const int nv = ring.slice_rows(np, 0);
+            const float* src_w = out_cur + 32 * warp * L::LD;
+            float* dst_w = a.dz + ((size_t)tile * kDecTile + 32 * warp) * D;
+            if (kBulkOut && Ring::tma_ok(nv)) {
+                // the warp's rows -> async proxy -> one bulk store by lane 0.  wait_group.read 1 leaves this
+                // store in flight but guarantees the previous one has finished reading the OTHER buffer,
+                // which the warp overwrites after the next iteration's __syncwarp().
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_s2g(dst_w, src_w, (uint32_t)nv * D * sizeof(float));
+                    bulk_commit();
+                    bulk_wait_read<1>();
+                }
+                ob ^= 1;
+            } else if (nv > 0) {
+                __syncwarp();
+                warp_copy_rows_out<D>(src_w, dst_w, nv);
+            }
         }
         if (++stage == S) { stage = 0; ++use; }
     }
+    if (kBulkOut && lane == 0) bulk_wait0();             // this warp's dz stores are complete
     pdl_trigger();                      // successor may start its prologue under our reduction tail
     SCC_TL(a.timeline, 3);
     if (MODE == MODE_KL) sm[0] *= a.scale * 0.693147180559945f;     // loss = scale * ln2 * sum p log2(p/q)
@@ -594,8 +663,8 @@ dec_grad_reg_kernel(const DecArgs a) {
     if (MODE == MODE_KMEANS && o < K) cta_stats[2 + K * D + o] = wj;
     __syncthreads();
     const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
-    grid_publish<kDecThreads>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials, a.counter, a.stats,
-                              scratch, &push);
+    grid_publish<kDecThreads, 25>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials, a.counter,
+                                  a.stats, scratch, &push);
     SCC_TL(a.timeline, 5);
 }
 
@@ -640,13 +709,11 @@ dec_grad_tiled_kernel(const DecArgs a) {
     ring.init(ring_buf, bars, a.z, a.n);
     __syncthreads();
     pdl_wait();                         // no global access before this point (see scc_common.cuh)
-    SCC_TL(a.timeline, 0);
     const int G = gridDim.x;
 #pragma unroll
     for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
     load_grad_constants<D, KP>(a, K, cs, nmu2_s, nmc2_s, mc_s, c0_s, inv_f);
     __syncthreads();
-    SCC_TL(a.timeline, 1);
 
     const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
     const bool want_dz = a.dz != nullptr;
@@ -665,11 +732,17 @@ dec_grad_tiled_kernel(const DecArgs a) {
     const int jb = lb / (D / 4), cb = lb - jb * (D / 4);
     const bool p2_active = grp < G2;
 
+    const float* krows = krow_operand<MODE>(a);
     int stage = 0;
     uint32_t use = 0;
     for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
-        ring.wait(stage, tile, use);
         const int np = ring.points(tile);
+        const int64_t base = (int64_t)tile * kDecTile;
+        float kcur[KP];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) kcur[j] = 0.f;
+        prefetch_krow<KP, EXACT>(krows, base, np, K, kcur);
+        ring.wait(stage, tile, use);
         const bool active = (int)threadIdx.x < np;
         float* ztile = ring.stage_ptr(stage);
         float coef[KP];
@@ -678,7 +751,7 @@ dec_grad_tiled_kernel(const DecArgs a) {
         if (active) {
             float zr[D];
             load_row<D>(ztile, threadIdx.x, zr);
-            const size_t i = (size_t)tile * kDecTile + threadIdx.x;
+            const size_t i = (size_t)base + threadIdx.x;
             float w[KP], u[KP], t[KP];
             float2 z2[DP2];
             pack_row<D>(zr, z2);
@@ -686,7 +759,7 @@ dec_grad_tiled_kernel(const DecArgs a) {
             float best, tsum;
             student_t_row<D, KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(z2, nmu2_s, K, inv_alpha, expo, w, u, t, tsum,
                                                                      label, best);
-            grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f, w, u, t, tsum, expo, label, best, coef,
+            grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f, w, u, t, tsum, expo, label, best, kcur, coef,
                                                        small[0], small[1]);
             float csum = 0.f;
 #pragma unroll
@@ -707,11 +780,13 @@ dec_grad_tiled_kernel(const DecArgs a) {
             *reinterpret_cast<float4*>(w_tile + threadIdx.x * KP + j) =
                 make_float4(coef[j], coef[j + 1], coef[j + 2], coef[j + 3]);
         __syncthreads();
-        if (want_dz) copy_tile_out<D, kDecThreads>(out_tile, a.dz + (size_t)tile * (kDecTile * D), np);
+        if (want_dz) copy_tile_out<D, kDecThreads>(out_tile, a.dz + (size_t)base * D, np);
         if (p2_active) {
             for (int r = warp * G2 + grp; r < np; r += NW * G2) {
                 const float4 w = *reinterpret_cast<const float4*>(w_tile + r * KP + 4 * jb);
                 const float4 x = *reinterpret_cast<const float4*>(ztile + r * L::LD + 4 * cb);
+                // scalar FMAs on purpose: the packed form (8 FFMA2 with a broadcast coefficient) was measured
+                // 7 % SLOWER for d = 32, K = 16 — this phase is bound by its two LDS.128 per 16 FMAs
                 blk[0] = fmaf(w.x, x.x, blk[0]);  blk[1] = fmaf(w.x, x.y, blk[1]);
                 blk[2] = fmaf(w.x, x.z, blk[2]);  blk[3] = fmaf(w.x, x.w, blk[3]);
                 blk[4] = fmaf(w.y, x.x, blk[4]);  blk[5] = fmaf(w.y, x.y, blk[5]);
@@ -762,18 +837,18 @@ template <int D, int KP>
 constexpr size_t assign_smem() {
     constexpr int S = assign_stages<D, KP>();
     constexpr int NW = kDecThreads / 32;
-    constexpr int scr = reduce_scratch(KP + 1);
     return sizeof(float) * (S * kDecTile * assign_ppt<D, KP>() * RowLayout<D>::LD + 2 * ((KP * Pairs<D>::N + 1) & ~1)) +
-           sizeof(double) * (scr + (KP + 1)) + sizeof(uint64_t) * S;
+           sizeof(double) * (KP + 1) + sizeof(uint64_t) * S;
 }
 template <int D, int KP>
 constexpr size_t grad_reg_smem() {
     constexpr int S = dec_stages<D>();
     constexpr int NV = 2 + KP + KP * D;
     constexpr int SCR = reduce_scratch(NV);
-    return sizeof(float) * ((S + 1) * kDecTile * RowLayout<D>::LD + 4 * ((KP * Pairs<D>::N + 1) & ~1) +
-                            ((KP * D + 3) & ~3) + ((D + 3) & ~3) + ((KP + 3) & ~3)) +
-           sizeof(double) * (SCR + NV) + sizeof(uint64_t) * S;
+    return sizeof(float) * ((S + (RowLayout<D>::kDense ? 2 : 1)) * kDecTile * RowLayout<D>::LD +
+                            4 * ((KP * Pairs<D>::N + 1) & ~1) +
+                            ((KP * D + 3) & ~3) + ((D + 3) & ~3) + ((KP + 3) & ~3) + 2 * ((Pairs<D>::N + 1) & ~1)) +
+           sizeof(double) * (SCR + NV) + sizeof(uint64_t) * S * (kDecThreads / 32);
 }
 template <int D, int KP>
 constexpr size_t grad_tiled_smem() {

@@ -165,6 +165,15 @@ int scc_dec_kl_grad_ex(const float* z, int64_t n, int d, const float* mu, int K,
                             workspace_bytes, (cudaStream_t)stream, as_desc(pull_f, &t1), as_desc(push, &t2));
 }
 
+int scc_dec_target_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float alpha,
+                           const double* f_cols, int round_decimals, float scale, float* p_out, float* dz,
+                           double* stats, void* workspace, size_t workspace_bytes, const scc_exchange* pull_f,
+                           const scc_exchange* push, scc_stream_t stream) {
+    scc::ExchangeDesc t1, t2;
+    return scc::dec_kl_grad(z, n, d, mu, K, alpha, nullptr, f_cols, round_decimals, scale, dz, stats, workspace,
+                            workspace_bytes, (cudaStream_t)stream, as_desc(pull_f, &t1), as_desc(push, &t2), p_out);
+}
+
 int scc_peer_finish(double* out, int len, const scc_exchange* ex, scc_stream_t stream) {
     if (!ex || !ex->windows) return SCC_ERR_INVALID;
     return scc::peer_finish(out, len, ex->windows, ex->rank, ex->world, ex->max_len, (cudaStream_t)stream);

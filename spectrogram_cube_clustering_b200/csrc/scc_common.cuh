@@ -103,6 +103,8 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // Ampere-style asynchronous 16-byte global -> shared copy (LDGSTS), used for the padded row layouts
@@ -242,6 +244,138 @@ struct ZRing {
 };
 
 // ----------------------------------------------------------------------------
+// Per-warp streaming ring (DEC assign / gradient kernels).
+//   Same tile order and shared-memory layout as ZRing (CTA tile i = blockIdx.x + i * gridDim.x, TILE =
+//   NT * P rows, thread t owns rows t, t + NT, ...), but every WARP moves and synchronises only its own
+//   32-row slices: lane 0 issues the TMA bulk copies of the warp's slices onto the warp's own mbarrier
+//   (padded layouts: the warp's lanes issue cp.async / plain loads), and the only synchronisation in the
+//   main loop is __syncwarp().  Warps of a CTA drift apart, so their latency stalls (MUFU, LDS, the
+//   dependent FMA chains) no longer line up the way they do behind a CTA-wide barrier per tile.
+//   Protocol per warp:  prologue issue(s, tile_s) for s < STAGES;  iteration: wait(stage) ; read own rows
+//   into registers ; __syncwarp() ; issue(stage, tile_{i+STAGES}) ; compute.
+// ----------------------------------------------------------------------------
+template <int D, int TILE, int STAGES, int NT, int P = 1>
+struct WarpRing {
+    using L = RowLayout<D>;
+    static constexpr int NW = NT / 32;
+    static constexpr int kTileFloats = TILE * L::LD;
+    static constexpr bool kCpAsync = L::kVec4 && !L::kDense;
+    static_assert(TILE == NT * P, "one row per thread and sub-tile");
+    static_assert(STAGES >= 2, "ring needs two stages");
+
+    float* buf;
+    uint64_t* bar;      // this warp's STAGES barriers
+    const float* z;
+    int num_tiles, last_points, warp, lane;
+
+    // bars: [NW][STAGES] uint64.  Ends with __syncwarp(); no CTA-wide barrier needed (each warp only ever
+    // touches its own barriers and its own rows).
+    __device__ __forceinline__ void init(float* b, uint64_t* bars, const float* z_, int64_t n_) {
+        buf = b; z = z_;
+        warp = threadIdx.x >> 5; lane = threadIdx.x & 31;
+        bar = bars + warp * STAGES;
+        num_tiles = (int)((n_ + TILE - 1) / TILE);
+        last_points = (int)(n_ - (int64_t)(num_tiles - 1) * TILE);
+        if (L::kDense && lane == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ int points(int tile) const { return tile == num_tiles - 1 ? last_points : TILE; }
+    __device__ __forceinline__ float* stage_ptr(int stage) const { return buf + stage * kTileFloats; }
+    // valid rows of this warp's slice r (rows r*NT + 32*warp ... + 31) in a tile of np points
+    __device__ __forceinline__ int slice_rows(int np, int r) const {
+        const int v = np - (r * NT + 32 * warp);
+        return v <= 0 ? 0 : (v > 32 ? 32 : v);
+    }
+    static __device__ __forceinline__ bool tma_ok(int rows) { return L::kDense && rows > 0 && ((rows * D) & 3) == 0; }
+
+    // Called by all lanes of the warp (converged).
+    __device__ __forceinline__ void issue(int stage, int tile) {
+        if (tile < num_tiles) {
+            const int np = points(tile);
+            if (L::kDense && lane == 0) {                       // one expect_tx for all of the warp's TMA slices
+                uint32_t bytes = 0;
+#pragma unroll
+                for (int r = 0; r < P; ++r) {
+                    const int nv = slice_rows(np, r);
+                    if (tma_ok(nv)) bytes += (uint32_t)nv * D * sizeof(float);
+                }
+                if (bytes) mbar_expect_tx(&bar[stage], bytes);
+            }
+#pragma unroll
+            for (int r = 0; r < P; ++r) {
+                const int nv = slice_rows(np, r);
+                if (nv == 0) continue;
+                const int row0 = r * NT + 32 * warp;
+                float* dst = stage_ptr(stage) + row0 * L::LD;
+                const float* src = z + ((size_t)tile * TILE + row0) * D;
+                if (tma_ok(nv)) {
+                    if (lane == 0) bulk_g2s(dst, src, (uint32_t)nv * D * sizeof(float), &bar[stage]);
+                } else if constexpr (L::kVec4) {
+                    const int nvec = nv * (D / 4);
+                    const float4* src4 = reinterpret_cast<const float4*>(src);
+                    for (int v = lane; v < nvec; v += 32) {
+                        const int row = v / (D / 4), c4 = v - row * (D / 4);
+                        if constexpr (kCpAsync) cp_async16(dst + row * L::LD + 4 * c4, src4 + v);
+                        else *reinterpret_cast<float4*>(dst + row * L::LD + 4 * c4) = ldg_stream4(src4 + v);
+                    }
+                } else {
+                    const int nf = nv * D;
+                    for (int f = lane; f < nf; f += 32) {
+                        const int row = f / D, c = f - row * D;
+                        dst[row * L::LD + c] = ldg_stream(src + f);
+                    }
+                }
+            }
+        }
+        if constexpr (kCpAsync) cp_async_commit();        // empty groups keep the per-thread count aligned
+    }
+    // use_index = how many times this stage has been consumed before.  After wait() returns every lane
+    // may read any row of the warp's slices.  (Slices filled with plain stores were written STAGES
+    // iterations ago and are ordered by the __syncwarp() of the iterations in between.)
+    __device__ __forceinline__ void wait(int stage, int tile, uint32_t use_index) {
+        if constexpr (kCpAsync) {
+            cp_async_wait<STAGES - 1>();
+            __syncwarp();
+        } else if constexpr (L::kDense) {
+            const int np = points(tile);
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < P; ++r) any = any || tma_ok(slice_rows(np, r));
+            if (any) mbar_wait(&bar[stage], use_index & 1u);
+        }
+    }
+};
+
+// Copy this warp's `rows` staged rows (row stride LD, first row at `src`) to `rows * D` contiguous
+// floats at dst (16-byte aligned), all lanes.
+template <int D>
+__device__ __forceinline__ void warp_copy_rows_out(const float* __restrict__ src, float* __restrict__ dst, int rows) {
+    using L = RowLayout<D>;
+    const int lane = threadIdx.x & 31;
+    if constexpr (L::kVec4) {
+        const int nvec = rows * (D / 4);
+        for (int v = lane; v < nvec; v += 32) {
+            const int row = v / (D / 4), c4 = v - row * (D / 4);
+            reinterpret_cast<float4*>(dst)[v] = *reinterpret_cast<const float4*>(src + row * L::LD + 4 * c4);
+        }
+    } else if constexpr (L::kDense) {
+        const int nf = rows * D, nvec = nf / 4;
+        for (int v = lane; v < nvec; v += 32) reinterpret_cast<float4*>(dst)[v] = reinterpret_cast<const float4*>(src)[v];
+        for (int f = nvec * 4 + lane; f < nf; f += 32) dst[f] = src[f];
+    } else {
+        const int nf = rows * D;
+        for (int f = lane; f < nf; f += 32) {
+            const int row = f / D, c = f - row * D;
+            dst[f] = src[row * L::LD + c];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
 // Peer-memory exchange window (see peer_exchange.cu): header {seq, flags[2][16]} then
 // slots[2][16][max_len] float64.  `push` runs in the LAST CTA of a statistics kernel (fused into
 // its tail), `pull` in the prologue of the kernel that consumes the all-reduced vector.
@@ -369,7 +503,7 @@ __device__ __forceinline__ void ldcg_f64x2(const double* p, double& a, double& b
 // `counter` must be 0 on entry and is reset.  scratch: NT doubles of shared memory.
 // `partials` needs gridDim.x * ((S + 1) & ~1) doubles.
 // Returns true in the CTA that arrived last (after `out` is complete).
-template <int NT>
+template <int NT, int U = 16>
 __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, double* partials,
                                              unsigned int* counter, double* out, double* scratch,
                                              const PeerCtx* push = nullptr) {
@@ -393,22 +527,22 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
     const int C = SP / 2;                         // 128-bit columns (pairs of statistics)
     if (2 * C <= NT) {
         // thread t owns column pair c = t % C and the CTA rows r, r+R, r+2R, ... (R = NT / C row groups);
-        // 16 independent 128-bit loads in flight per thread (the chain is L2-latency bound), summed in
+        // U independent 128-bit loads in flight per thread (the chain is L2-latency bound), summed in
         // a fixed order; the R partial sums are then combined in row-group order.
         const int R = NT / C;
         const int c = tid % C, r = tid / C;
         double a0 = 0.0, a1 = 0.0;
         if (r < R) {
-            for (int b = r; b < G; b += 16 * R) {
-                double v0[16], v1[16];
+            for (int b = r; b < G; b += U * R) {
+                double v0[U], v1[U];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int bb = b + u * R;
                     v0[u] = 0.0; v1[u] = 0.0;
                     if (bb < G) ldcg_f64x2(partials + (size_t)bb * SP + 2 * c, v0[u], v1[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < 16; ++u) { a0 += v0[u]; a1 += v1[u]; }
+                for (int u = 0; u < U; ++u) { a0 += v0[u]; a1 += v1[u]; }
             }
             scratch[(r * C + c) * 2] = a0;
             scratch[(r * C + c) * 2 + 1] = a1;

@@ -35,6 +35,7 @@ struct DecArgs {
     float* mindist;            // MODE_KMEANS: squared distance to the nearest centre, or NULL
     // grad
     const float* p;
+    float* p_out;              // fused mode (p == NULL): also write the rebuilt target rows here, or NULL
     const double* f_cols;
     const float* grad_q;
     float scale;
@@ -90,7 +91,7 @@ int colsum(const float* q, int64_t n, int K, double* f, void* ws, size_t ws_byte
 int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* p,
                 const double* f_cols, int round_decimals, float scale, float* dz, double* stats,
                 void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* pull_f = nullptr,
-                const ExchangeDesc* push = nullptr);
+                const ExchangeDesc* push = nullptr, float* p_out = nullptr);
 int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* grad_q,
                  float* dz, double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
 int kmeans_step(const float* z, int64_t n, int d, const float* centers, int K, int32_t* labels, float* mindist,

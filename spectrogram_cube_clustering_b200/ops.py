@@ -143,6 +143,31 @@ def dec_kl_grad(z, mu, alpha=1.0, p=None, f=None, round_decimals=0, scale=1.0, w
     return stats, dz
 
 
+def dec_target_kl_grad(z, mu, f, alpha=1.0, round_decimals=0, scale=1.0, want_p=True, want_dz=True,
+                       out_p=None, out_dz=None, out_stats=None, pull_f=None, push=None):
+    """target_distribution + KL loss + gradients in one pass over z (models.py:1302-1322 + 1124-1127).
+
+    -> (stats float64 [K*d+2] = (loss, sum_i s_i, dmu[K,d]), p [n,K] | None, dz [n,d] | None).
+    ``f`` are the column sums from :func:`dec_assign` for the same z and mu."""
+    lib = _lib.load()
+    _require(z, "z"); _require(mu, "mu")
+    n, d = z.shape
+    K = mu.shape[0]
+    if f is not None:
+        _require(f, "f", torch.float64)
+    elif pull_f is None:
+        raise ValueError("need the column sums f")
+    p = out_p if out_p is not None else (torch.empty(n, K, dtype=torch.float32, device=z.device) if want_p else None)
+    dz = out_dz if out_dz is not None else (torch.empty_like(z) if want_dz else None)
+    stats = out_stats if out_stats is not None else torch.empty(K * d + 2, dtype=torch.float64, device=z.device)
+    ws = workspace(z.device, d, K)
+    rc = lib.scc_dec_target_kl_grad(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), _ptr(f), int(round_decimals),
+                                    float(scale), _ptr(p), _ptr(dz), stats.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    _ex(pull_f), _ex(push), _stream())
+    _lib.check(rc, "scc_dec_target_kl_grad")
+    return stats, p, dz
+
+
 def dec_backward(z, mu, grad_q, alpha=1.0, want_dz=True):
     """Layer backward for an arbitrary dL/dq -> (dz [n,d] | None, dmu float64 [K,d])."""
     lib = _lib.load()

@@ -107,6 +107,44 @@ def test_dec_kl_grad_fused_mode_oracle(ops, case):
 
 
 @pytest.mark.parametrize("case", DEC_CASES)
+def test_dec_target_kl_grad_golden(ops, case):
+    """One-pass target + KL gradient: p written by the kernel == target_distribution(np.round(q,5)) of the
+    reference to one rounding quantum; loss / dz / dmu == the three-kernel chain fed with that same p."""
+    g = load_golden("dec", case)
+    n, d = g["z"].shape
+    K = g["mu"].shape[0]
+    alpha, gamma = float(g["alpha"]), float(g["gamma"])
+    z, mu = dev(g["z"]), dev(g["mu"])
+    q5, _, st5 = ops.dec_assign(z, mu, alpha, 5)
+    stats, p, dz = ops.dec_target_kl_grad(z, mu, st5, alpha, 5, gamma / n)
+    # here p comes from the kernel's OWN fp32 q: a q that rounds to the other side of a 5-decimal
+    # boundary (one quantum) moves p = q^2/f/sum by up to 2p/q quanta before p's own rounding
+    dp = np.abs(p.cpu().numpy() - g["p"])
+    assert dp.max() <= 3 * QUANTUM * 1.01 and (dp > 1e-7).mean() < 0.03 and (dp > 1.5 * QUANTUM).mean() < 2e-3
+    # q recomputed by the gradient kernel and the row sum of the rebuilt p follow the operation order of
+    # dec_assign / dec_target, so the one-pass p is bit-identical to the two stand-alone kernels' output
+    p3 = ops.dec_target(q5, st5, 5)
+    assert torch.equal(p, p3)
+    stats3, dz3 = ops.dec_kl_grad(z, mu, alpha, p=p, scale=gamma / n)  # same target, p read from memory
+    assert torch.equal(stats, stats3) and torch.equal(dz, dz3)
+    stats = stats.cpu().numpy()
+    assert abs(stats[0] - float(g["loss"])) <= 2e-4 * abs(float(g["loss"]))
+    assert rel_err(stats[2:].reshape(K, d), g["dmu"]) < 2e-4
+    # unrounded: against the float64 oracle chain
+    from oracle import dec as odec
+    ref = odec.dec_step(g["z"], g["mu"], alpha, gamma, round_to=None)
+    _, _, st0 = ops.dec_assign(z, mu, alpha, 0, want_q=False, want_labels=False)
+    stats0, p0, dz0 = ops.dec_target_kl_grad(z, mu, st0, alpha, 0, gamma / n)
+    assert rel_err(p0.cpu().numpy(), ref["p"]) < 2 * TOL
+    assert abs(stats0[0].item() - ref["loss"]) <= TOL * abs(ref["loss"])
+    assert rel_err(dz0.cpu().numpy(), ref["dz"]) < TOL
+    assert rel_err(stats0[2:].cpu().numpy().reshape(K, d), ref["dmu"]) < TOL
+    # no N-sized outputs requested: statistics unchanged
+    stats_n, none_p, none_dz = ops.dec_target_kl_grad(z, mu, st0, alpha, 0, gamma / n, want_p=False, want_dz=False)
+    assert none_p is None and none_dz is None and torch.equal(stats_n, stats0)
+
+
+@pytest.mark.parametrize("case", DEC_CASES)
 def test_dec_backward_generic_golden(ops, case):
     g = load_golden("dec", case)
     z, mu, G = dev(g["z"]), dev(g["mu"]), dev(g["G"])
