@@ -38,6 +38,27 @@ N_SETS = 4                      # distinct input/output sets cycled so no step r
 WORKLOAD = "DEC fwd/bwd + target distribution, N=1M latent points per GPU, d=9, K=8, alpha=1 (BASELINE configs[1])"
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """Keep stdout for the ONE JSON line: native libraries (the NCCL version banner) write to fd 1 too,
+    so fd 1 is pointed at stderr and the JSON line goes out through a saved duplicate of the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def dbg(msg):
     if os.environ.get("SCC_BENCH_DEBUG"):
         print(f"[bench r{os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
@@ -158,7 +179,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -307,8 +328,12 @@ def run_gpu(args):
             i += 1
 
     dbg(f'graphs={use_graphs}')
-    for i in range(3):
-        run_step(i)
+    # untimed: the W warm-up steps through the timed launch path, then ~0.25 s of the same load so that
+    # the timed region starts with the GPU at its steady clocks (a fixed, rank-uniform step count)
+    run_steps(max(args.warmup, 3))
+    for _ in range(0, 4096, 512):
+        run_steps(512)
+        torch.cuda.synchronize()
     sampler = ClockSampler(local)
 
     def barrier():
@@ -386,14 +411,14 @@ def run_gpu(args):
     try:          # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f)
-        traffic = tr.get({"dec_assign": "dec_assign_kernel", "dec_target": "dec_target_kernel",
-                          "dec_kl_grad": "dec_grad_reg_kernel", "dec_target_kl_grad": "dec_grad_reg_kernel_fused"}[dominant])
+        traffic = tr.get(dominant)
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic,
-                "traffic_note": "ncu cold-cache capture (profiles/); rows written by the kernel are still in the "
-                                "126 MB L2 when it ends, so DRAM writes are below the algorithmic store bytes",
+                "traffic_note": "ncu --set full cold-cache capture (profiles/traffic.json, profiles/r01_ncu_kernels.txt); rows "
+                                "written by the kernel are still in the 126 MB L2 when it ends, so DRAM writes are "
+                                "below the algorithmic store bytes",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_point": alg_bytes[dominant],
                 "algorithmic_bytes": "z read 4d + p written 4K + dz written 4d (q is recomputed in registers)"
@@ -525,7 +550,7 @@ def run_gpu(args):
             "roofline": roofline,
             "cpu_baseline": cpu, "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     sys.stdout.flush()
     if world > 1:
         # CUDA graphs that captured NCCL kernels must die before the communicator does; a watchdog
@@ -650,7 +675,7 @@ def extra_benchmarks(torch, ops, synth, dev, hbm_peak):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graphs", action="store_true")
@@ -665,6 +690,7 @@ def main():
                     help="ride the exchange on the kernels (push in the producer's last CTA, pull in the consumer) "
                          "instead of the stand-alone exchange kernel")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

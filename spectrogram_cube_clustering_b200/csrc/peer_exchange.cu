@@ -20,6 +20,11 @@ namespace scc {
 __global__ void __launch_bounds__(256)
 peer_allreduce_kernel(const double* __restrict__ local, int len, double* __restrict__ out,
                       unsigned char* const* __restrict__ windows, int rank, int world, int max_len) {
+    // Launched with the PDL attribute: this one-CTA kernel is already resident when the statistics kernel
+    // before it drains, and the kernel after it may be scheduled (up to its own dependency wait) while
+    // the exchange is in flight — the two launch latencies around the exchange leave the critical path.
+    pdl_wait();
+    pdl_trigger();
     PeerHeader* me = reinterpret_cast<PeerHeader*>(windows[rank]);
     const unsigned int seq = me->seq + 1u;
     const int parity = seq & 1u;
@@ -53,6 +58,8 @@ peer_allreduce_kernel(const double* __restrict__ local, int len, double* __restr
 // PeerCtx); wait for the world and write the rank-ordered sum.
 __global__ void __launch_bounds__(256)
 peer_finish_kernel(double* __restrict__ out, int len, PeerCtx ex) {
+    pdl_wait();
+    pdl_trigger();
     peer_pull(ex, out, len);
 }
 
@@ -61,6 +68,21 @@ peer_finish_kernel(double* __restrict__ out, int len, PeerCtx ex) {
 __global__ void __launch_bounds__(256)
 peer_push_kernel(const double* __restrict__ local, int len, PeerCtx ex) {
     peer_push(ex, ((int)threadIdx.x < len) ? local[threadIdx.x] : 0.0, len);
+}
+
+// One-CTA launch with programmatic stream serialization allowed (see scc_common.cuh, PDL).
+template <typename Kern, typename... Args>
+static cudaError_t launch_one_cta_pdl(Kern kern, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 size_t peer_window_bytes(int max_len) {
@@ -72,9 +94,8 @@ int peer_allreduce(const double* local, int len, double* out, void* const* windo
                    int max_len, cudaStream_t st) {
     if (!local || !out || !windows_dev || len < 1 || len > max_len) return SCC_ERR_INVALID;
     if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world) return SCC_ERR_INVALID;
-    peer_allreduce_kernel<<<1, 256, 0, st>>>(local, len, out, reinterpret_cast<unsigned char* const*>(windows_dev),
-                                             rank, world, max_len);
-    SCC_CUDA(cudaGetLastError());
+    SCC_CUDA(launch_one_cta_pdl(peer_allreduce_kernel, st, local, len, out,
+                                reinterpret_cast<unsigned char* const*>(windows_dev), rank, world, max_len));
     return SCC_OK;
 }
 
@@ -91,8 +112,7 @@ int peer_finish(double* out, int len, void* const* windows_dev, int rank, int wo
     if (!out || !windows_dev || len < 1 || len > max_len) return SCC_ERR_INVALID;
     if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world) return SCC_ERR_INVALID;
     PeerCtx ex{reinterpret_cast<unsigned char* const*>(windows_dev), rank, world, max_len};
-    peer_finish_kernel<<<1, 256, 0, st>>>(out, len, ex);
-    SCC_CUDA(cudaGetLastError());
+    SCC_CUDA(launch_one_cta_pdl(peer_finish_kernel, st, out, len, ex));
     return SCC_OK;
 }
 

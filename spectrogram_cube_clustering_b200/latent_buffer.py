@@ -34,6 +34,7 @@ class DecStepResult:
     f: torch.Tensor            # float64 [K]
     n_changed: torch.Tensor    # float64 scalar tensor (label changes vs previous pass)
     dz: torch.Tensor | None
+    p: torch.Tensor | None = None   # [n_local, K] target distribution of this shard (want_p=True)
 
 
 class PeerExchange:
@@ -143,16 +144,24 @@ class LatentBuffer:
         return q, stats
 
     def dec_grad(self, mu: torch.Tensor, f_stats: torch.Tensor, alpha: float = 1.0, gamma: float = 1e-3,
-                 round_decimals: int = 0, p: torch.Tensor | None = None, want_dz: bool = False):
+                 round_decimals: int = 0, p: torch.Tensor | None = None, want_dz: bool = False,
+                 out_p: torch.Tensor | None = None):
         """Pass 2: loss, dL/dmu (summed over shards) and optionally dL/dz for the encoder.
-        scale = gamma / N_total, i.e. the whole latent set is one batch (models.py:1124-1125)."""
-        stats, dz = ops.dec_kl_grad(self.z, mu, alpha, p=p, f=None if p is not None else f_stats,
-                                    round_decimals=round_decimals, scale=gamma / self.n_total, want_dz=want_dz)
+        scale = gamma / N_total, i.e. the whole latent set is one batch (models.py:1124-1125).
+        With ``out_p`` (and no ``p``) the shard's target distribution rows — what
+        ``target_distribution`` (models.py:1302-1322) returns for them — are written there by the
+        same pass (``scc_dec_target_kl_grad``)."""
+        if p is None and out_p is not None:
+            stats, _, dz = ops.dec_target_kl_grad(self.z, mu, f_stats, alpha, round_decimals, gamma / self.n_total,
+                                                  out_p=out_p, want_dz=want_dz)
+        else:
+            stats, dz = ops.dec_kl_grad(self.z, mu, alpha, p=p, f=None if p is not None else f_stats,
+                                        round_decimals=round_decimals, scale=gamma / self.n_total, want_dz=want_dz)
         self._allreduce(stats)
         return stats, dz
 
     def dec_step(self, mu: torch.Tensor, alpha: float = 1.0, gamma: float = 1e-3, round_decimals: int = 0,
-                 want_dz: bool = False) -> DecStepResult:
+                 want_dz: bool = False, want_p: bool = False) -> DecStepResult:
         """Fused latent-buffer DEC step: assign -> (allreduce f) -> KL gradients -> (allreduce dmu).
         With a peer exchange the collectives ride on the kernels: the assign kernel's last CTA pushes f
         to every rank, the gradient kernel pulls it in its prologue and pushes its own statistics, and
@@ -166,16 +175,18 @@ class LatentBuffer:
             _, labels, st = ops.dec_assign(self.z, mu, alpha, round_decimals, want_q=False, want_labels=True,
                                            labels_prev=prev, out_labels=out_labels, push=ex)
             self._labels_spare, self.labels = self.labels, labels
-            stats, dz = ops.dec_kl_grad(self.z, mu, alpha, round_decimals=round_decimals,
-                                        scale=gamma / self.n_total, want_dz=want_dz, pull_f=ex, push=ex)
+            stats, p_out, dz = ops.dec_target_kl_grad(self.z, mu, None, alpha, round_decimals, gamma / self.n_total,
+                                                      want_p=want_p, want_dz=want_dz, pull_f=ex, push=ex)
             ops.peer_finish(stats, ex)
             # st holds only this shard's f; the all-reduced f is not needed by the caller of a fused step,
             # the label-change count is: exchange it with the (tiny) standalone kernel
             self.exchange.all_reduce(st)
-            return DecStepResult(loss=stats[0], dmu=stats[2:].view(K, self.d), f=st[:K], n_changed=st[K], dz=dz)
+            return DecStepResult(loss=stats[0], dmu=stats[2:].view(K, self.d), f=st[:K], n_changed=st[K], dz=dz,
+                                 p=p_out)
         _, st = self.dec_assign(mu, alpha, round_decimals)
-        stats, dz = self.dec_grad(mu, st, alpha, gamma, round_decimals, want_dz=want_dz)
-        return DecStepResult(loss=stats[0], dmu=stats[2:].view(K, self.d), f=st[:K], n_changed=st[K], dz=dz)
+        p_out = torch.empty(self.n_local, K, dtype=torch.float32, device=self.z.device) if want_p else None
+        stats, dz = self.dec_grad(mu, st, alpha, gamma, round_decimals, want_dz=want_dz, out_p=p_out)
+        return DecStepResult(loss=stats[0], dmu=stats[2:].view(K, self.d), f=st[:K], n_changed=st[K], dz=dz, p=p_out)
 
     def delta_label(self, assign_stats: torch.Tensor) -> float:
         """models.py:1098-1099 from the fused count (one host sync)."""

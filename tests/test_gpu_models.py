@@ -159,6 +159,8 @@ def test_latent_buffer_dec_step_and_refine():
     ref = odec.dec_step(z.numpy(), mu.numpy(), 1.0, 1e-3, round_to=None)
     assert abs(res.loss.item() - ref["loss"]) < TOL * abs(ref["loss"])
     assert rel_err(res.dmu.cpu().numpy(), ref["dmu"]) < TOL and rel_err(res.f.cpu().numpy(), ref["f"]) < TOL
+    res_p = buf.dec_step(mu.cuda(), 1.0, 1e-3, round_decimals=0, want_p=True)      # same pass, target rows kept
+    assert rel_err(res_p.p.cpu().numpy(), ref["p"]) < 2 * TOL and torch.equal(res_p.dmu, res.dmu)
     cent, hist = dec_refine(buf, mu, lr=1e-2, max_steps=30, tol=0.0)
     assert cent.shape == (8, 9) and len(hist) == 30 and np.isfinite(cent).all()
     assert hist[-1]["delta"] <= hist[1]["delta"] + 1e-3

@@ -23,6 +23,7 @@ def main(rep, out_txt, out_json=None):
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     traffic = {}
+    launches = []
     with open(out_txt, 'w') as f:
         f.write(f"# ncu --set full --clock-control none summary of {rep.split('/')[-1]} (cold-cache, serialised replays)\n")
         for r in rows[2:]:
@@ -39,11 +40,15 @@ def main(rep, out_txt, out_json=None):
                     return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
                 short = name.split('<')[0].split('(')[0].replace('void ', '').replace('scc::', '')
                 traffic.setdefault(short, []).append(tobytes('dram__bytes_read.sum') + tobytes('dram__bytes_write.sum'))
+                launches.append([name, tobytes('dram__bytes_read.sum') + tobytes('dram__bytes_write.sum'),
+                                 vals.get('gpu__time_duration.sum')])
             except Exception:
                 pass
     if out_json:
         with open(out_json, 'w') as f:
-            json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, f, indent=1)
+            out = {k: sum(v) / len(v) for k, v in traffic.items()}
+            out["per_launch"] = launches          # in launch order: [kernel, dram bytes, duration us]
+            json.dump(out, f, indent=1)
 
 
 if __name__ == '__main__':
