@@ -35,6 +35,7 @@ METRIC = "latent points/sec per DEC step (ClusteringLayer fwd+bwd + target distr
 UNIT = "points/s"
 N_PER_GPU, D, K, ALPHA, GAMMA = 1_000_000, 9, 8, 1.0, 1e-3
 N_SETS = 4                      # distinct input/output sets cycled so no step re-finds its data in L2
+GRAPH_STEPS = 16                # consecutive steps captured into one CUDA graph (a multiple of N_SETS)
 WORKLOAD = "DEC fwd/bwd + target distribution, N=1M latent points per GPU, d=9, K=8, alpha=1 (BASELINE configs[1])"
 
 
@@ -294,12 +295,13 @@ def run_gpu(args):
                     with torch.cuda.graph(g, stream=cap_stream):
                         step(s)
                     graphs.append(g)
-                # N_SETS consecutive steps in ONE graph: the programmatic (PDL) edges between kernels then
-                # also span step boundaries and there is one graph launch per N_SETS steps
+                # GRAPH_STEPS consecutive steps in ONE graph: the programmatic (PDL) edges between kernels then
+                # also span step boundaries and there is one graph launch per GRAPH_STEPS steps
                 graph_all = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph_all, stream=cap_stream):
-                    for s in sets:
-                        step(s)
+                    for _ in range(GRAPH_STEPS // N_SETS):
+                        for s in sets:
+                            step(s)
             torch.cuda.synchronize()
             for g in graphs:
                 g.replay()
@@ -317,12 +319,12 @@ def run_gpu(args):
             step(sets[i % N_SETS])
 
     def run_steps(n_steps):
-        """Exactly n_steps steps: whole N_SETS-step graphs, then single-step graphs for the remainder."""
+        """Exactly n_steps steps: whole GRAPH_STEPS-step graphs, then single-step graphs for the remainder."""
         i = 0
         if use_graphs and not args.single_step_graphs:
-            while i + N_SETS <= n_steps:
+            while i + GRAPH_STEPS <= n_steps:
                 graph_all.replay()
-                i += N_SETS
+                i += GRAPH_STEPS
         while i < n_steps:
             run_step(i)
             i += 1
@@ -538,7 +540,8 @@ def run_gpu(args):
                                            "one-shot NVLink peer-memory exchange kernel") if exchange is not None else "NCCL"))
                                       if world > 1 else "single GPU",
                        "launch": (("one CUDA graph replay per step" if args.single_step_graphs else
-                                   f"CUDA graph replays of {N_SETS} consecutive steps (one per rotating input set)")
+                                   f"CUDA graph replays of {GRAPH_STEPS} consecutive steps (rotating over the {N_SETS} input sets), "
+                                   "single-step graphs for the remainder")
                                   if use_graphs else "eager launches"),
                        "kernels_per_step": ["dec_assign", "dec_target", "dec_kl_grad"] if unfused else
                                            ["dec_assign", "dec_target_kl_grad"],

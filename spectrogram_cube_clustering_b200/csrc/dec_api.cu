@@ -233,7 +233,7 @@ int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float 
     a.p = p; a.p_out = p_out; a.f_cols = f_cols; a.scale = scale; a.dz = dz; a.stats = stats;
     fill_reduction(a, ws);
     fill_exchange(a, push, 1, p ? nullptr : pull_f);
-    return dec_grad_dispatch(a, d, MODE_KL, st);
+    return dec_grad_dispatch(a, d, p ? MODE_KL : MODE_KLF, st);
 }
 
 int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* grad_q,

@@ -311,7 +311,8 @@ dec_assign_kernel(const DecArgs a) {
 // Per-point gradient coefficients c_ij with dz_i = cs sum_j c_ij (z_i - mu_j),
 // dmu_j = -cs sum_i c_ij (z_i - mu_j).  The common factor cs is NOT applied here: it is folded into
 // the -(mu - c0) table used for dz and into the final reduction of dmu (grad_fold_scale()).
-//   MODE_KL      : c_ij = (p_ij - q_ij s_i) u_ij,  cs = scale (alpha+1)/alpha   (+ loss, in log2 units)
+//   MODE_KL/KLF  : c_ij = (p_ij - q_ij s_i) u_ij,  cs = scale (alpha+1)/alpha   (+ loss, in log2 units);
+//                  KL streams p from memory, KLF rebuilds it from the column sums (and may write it out)
 //   MODE_GENERIC : c_ij = q_ij (sum_j G_ij q_ij - G_ij) u_ij,  cs = (alpha+1)/alpha
 //   MODE_KMEANS  : c_ij = [j == argmin_j ||z_i - mu_j||^2],  cs = 1  (Lloyd step: counts, centre shifts, inertia)
 // Inputs are the Student's-t quantities of student_t_row(): q_j = t_j / tsum, 1/q_j = tsum w_j^expo.
@@ -332,7 +333,7 @@ __device__ __forceinline__ void prefetch_krow(const float* __restrict__ src, int
 
 template <int MODE>
 __host__ __device__ __forceinline__ float grad_fold_scale(float scale, float alpha) {
-    return MODE == MODE_KMEANS ? 1.f : (MODE == MODE_KL ? scale : 1.f) * (alpha + 1.f) / alpha;
+    return MODE == MODE_KMEANS ? 1.f : ((MODE == MODE_KL || MODE == MODE_KLF) ? scale : 1.f) * (alpha + 1.f) / alpha;
 }
 
 template <int KP, bool EXACT, bool ALPHA1, int MODE>
@@ -348,13 +349,13 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
         loss += best;
         if (a.labels) a.labels[i] = label;
         if (a.mindist) a.mindist[i] = best;
-    } else if constexpr (MODE == MODE_KL) {
+    } else if constexpr (MODE == MODE_KL || MODE == MODE_KLF) {
         const float inv = rcp_approx(tsum);
         float p[KP];
-        if (a.p) {                                 // target row prefetched one tile ahead (prefetch_krow)
+        if constexpr (MODE == MODE_KL) {           // target row requested before the z tile wait (prefetch_krow)
 #pragma unroll
             for (int j = 0; j < KP; ++j) p[j] = pre[j];
-        } else {                                   // rebuild p from the column sums (fused mode)
+        } else {                                   // MODE_KLF: rebuild p from the column sums (fused mode)
 #pragma unroll
             for (int j = 0; j < KP; ++j) {
                 const float q = t[j] * inv;
@@ -611,10 +612,10 @@ dec_grad_reg_kernel(const DecArgs a) {
             }
         }
         if (want_dz) {
-            const int nv = ring.slice_rows(np, 0);
+            const int nv = (np == kDecTile) ? 32 : ring.slice_rows(np, 0);
             const float* src_w = out_cur + 32 * warp * L::LD;
             float* dst_w = a.dz + ((size_t)tile * kDecTile + 32 * warp) * D;
-            if (kBulkOut && Ring::tma_ok(nv)) {
+            if (kBulkOut && (np == kDecTile || Ring::tma_ok(nv))) {
                 // the warp's rows -> async proxy -> one bulk store by lane 0.  wait_group.read 1 leaves this
                 // store in flight but guarantees the previous one has finished reading the OTHER buffer,
                 // which the warp overwrites after the next iteration's __syncwarp().
@@ -636,7 +637,7 @@ dec_grad_reg_kernel(const DecArgs a) {
     if (kBulkOut && lane == 0) bulk_wait0();             // this warp's dz stores are complete
     pdl_trigger();                      // successor may start its prologue under our reduction tail
     SCC_TL(a.timeline, 3);
-    if (MODE == MODE_KL) sm[0] *= a.scale * 0.693147180559945f;     // loss = scale * ln2 * sum p log2(p/q)
+    if (MODE == MODE_KL || MODE == MODE_KLF) sm[0] *= a.scale * 0.693147180559945f;     // loss = scale * ln2 * sum p log2(p/q)
     float acc[NV];
     acc[0] = sm[0]; acc[1] = sm[1];
 #pragma unroll
@@ -803,7 +804,7 @@ dec_grad_tiled_kernel(const DecArgs a) {
     }
     // ---- CTA reduction ----
     pdl_trigger();
-    if (MODE == MODE_KL) small[0] *= a.scale * 0.693147180559945f;      // loss = scale * ln2 * sum p log2(p/q)
+    if (MODE == MODE_KL || MODE == MODE_KLF) small[0] *= a.scale * 0.693147180559945f;      // loss = scale * ln2 * sum p log2(p/q)
     cta_reduce<NSM, kDecThreads>(small, scratch, small_s);
     // per-(warp, group) 4x4 partials -> shared (the ring buffer is free now), fixed-order sum
     double* part = reinterpret_cast<double*>(ring_buf);                      // [NW*G2][KP*D]

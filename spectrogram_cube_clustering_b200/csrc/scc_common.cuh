@@ -294,7 +294,17 @@ struct WarpRing {
 
     // Called by all lanes of the warp (converged).
     __device__ __forceinline__ void issue(int stage, int tile) {
-        if (tile < num_tiles) {
+        if (L::kDense && tile < num_tiles && (tile != num_tiles - 1 || last_points == TILE)) {
+            // fast path, whole tile: fixed-size slices, no per-slice bookkeeping
+            if (lane == 0) {
+                mbar_expect_tx(&bar[stage], P * 32u * D * (uint32_t)sizeof(float));
+                float* dst = stage_ptr(stage) + 32 * warp * L::LD;
+                const float* src = z + ((size_t)tile * TILE + 32 * warp) * D;
+#pragma unroll
+                for (int r = 0; r < P; ++r)
+                    bulk_g2s(dst + r * NT * L::LD, src + (size_t)r * NT * D, 32u * D * (uint32_t)sizeof(float), &bar[stage]);
+            }
+        } else if (tile < num_tiles) {
             const int np = points(tile);
             if (L::kDense && lane == 0) {                       // one expect_tx for all of the warp's TMA slices
                 uint32_t bytes = 0;
@@ -341,10 +351,12 @@ struct WarpRing {
             cp_async_wait<STAGES - 1>();
             __syncwarp();
         } else if constexpr (L::kDense) {
-            const int np = points(tile);
-            bool any = false;
+            bool any = true;
+            if (tile == num_tiles - 1 && last_points != TILE) {
+                any = false;
 #pragma unroll
-            for (int r = 0; r < P; ++r) any = any || tma_ok(slice_rows(np, r));
+                for (int r = 0; r < P; ++r) any = any || tma_ok(slice_rows(last_points, r));
+            }
             if (any) mbar_wait(&bar[stage], use_index & 1u);
         }
     }

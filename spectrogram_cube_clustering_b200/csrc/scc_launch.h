@@ -19,7 +19,8 @@ constexpr int kMaxDecGrid = 2048;      // persistent DEC grids never exceed this
 constexpr int kMaxGmmGrid = 512;
 constexpr size_t kWorkspaceHeader = 256;   // counters live in front of the partial slots
 
-enum { MODE_KL = 0, MODE_GENERIC = 1, MODE_KMEANS = 2 };
+// MODE_KL: target p streamed from memory;  MODE_KLF: p rebuilt in registers from the column sums (fused mode)
+enum { MODE_KL = 0, MODE_GENERIC = 1, MODE_KMEANS = 2, MODE_KLF = 3 };
 
 struct DecArgs {
     const float* z;
