@@ -523,18 +523,17 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
     const int tid = threadIdx.x;
     const int SP = (S + 1) & ~1;                  // slot stride: even, so slots stay 16-byte aligned
     double* mine = partials + (size_t)blockIdx.x * SP;
-    if (tid < SP || SP > NT) {
-        for (int s = tid; s < SP; s += NT) mine[s] = (s < S) ? cta_stats[s] : 0.0;
-        __threadfence();
-    }
+    // the slot is written by many threads; the CTA barrier orders those writes before thread 0's ticket,
+    // whose acq_rel semantics at GPU scope publishes them (and acquires every earlier CTA's slot)
+    for (int s = tid; s < SP; s += NT) __stcg(mine + s, (s < S) ? cta_stats[s] : 0.0);
     __syncthreads();
     if (tid == 0) {
-        const unsigned int prev = atomicAdd(counter, 1u);
+        unsigned int prev;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(counter) : "memory");
         s_last = (prev == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
     if (!s_last) return false;
-    __threadfence();
     const int G = gridDim.x;
     const int C = SP / 2;                         // 128-bit columns (pairs of statistics)
     if (2 * C <= NT) {
@@ -607,7 +606,10 @@ __device__ __forceinline__ float2 splat2(float x) { return make_float2(x, x); }
 
 __device__ __forceinline__ float round_dec5(float x) {
     // np.round(x, 5): rint (half-to-even) of x * 1e5, scaled back.
-    return rintf(x * 100000.0f) * 1.0e-5f;
+    // 0 <= x * 1e5 < 2^22: adding 1.5 * 2^23 rounds the EXACT product to an integer in the FMA itself
+    // (one rounding, half-to-even) and keeps the conversion (XU) pipe free of an FRND per value
+    const float y = fmaf(x, 100000.0f, 12582912.0f);
+    return (y - 12582912.0f) * 1.0e-5f;
 }
 
 }  // namespace scc

@@ -42,6 +42,24 @@ def dec_kl_grad(z, mu, alpha=1.0, p=None, f=None, round_decimals=0, scale=1.0, w
     return stats, (torch.from_numpy(dz.astype(np.float32)) if want_dz else None)
 
 
+def dec_target_kl_grad(z, mu, f, alpha=1.0, round_decimals=0, scale=1.0, want_p=True, want_dz=True,
+                       out_p=None, out_dz=None, out_stats=None, pull_f=None, push=None):
+    stats, dz = dec_kl_grad(z, mu, alpha, p=None, f=f, round_decimals=round_decimals, scale=scale, want_dz=want_dz)
+    zn, mn = z.numpy().astype(np.float64), mu.numpy().astype(np.float64)
+    q = odec.soft_assign(zn, mn, alpha)
+    if round_decimals:
+        q = np.round(q, round_decimals)
+    w = q ** 2 / f.numpy()[:mn.shape[0]]
+    pn = w / w.sum(1, keepdims=True)
+    if round_decimals:
+        pn = np.round(pn, round_decimals)
+    p = torch.from_numpy(pn.astype(np.float32))
+    if out_p is not None:
+        out_p.copy_(p)
+        p = out_p
+    return stats, (p if (want_p or out_p is not None) else None), dz
+
+
 def _unpack(params, K, d):
     tri = d * (d + 1) // 2
     p = params.numpy().astype(np.float64)

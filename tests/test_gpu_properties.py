@@ -38,6 +38,16 @@ def test_full_size_invariants(ops, n, d, K):
     # determinism: a second launch reproduces every statistic bit for bit
     _, _, st2 = ops.dec_assign(z, mu, 1.0, 0, want_q=False, want_labels=False)
     assert torch.equal(st[:K], st2[:K])
+    # one-pass target + gradient: its p is bit-identical to dec_assign + dec_target (rounded chain, as the
+    # reference runs it), and streaming that p back in gives the same statistics and dz bit for bit
+    q5, _, st5 = ops.dec_assign(z, mu, 1.0, 5, want_labels=False)
+    p5 = ops.dec_target(q5, st5, 5)
+    stats_o, p_o, dz_o = ops.dec_target_kl_grad(z, mu, st5, 1.0, 5, 1e-3 / n)
+    assert torch.equal(p_o, p5)
+    stats_s, dz_s = ops.dec_kl_grad(z, mu, 1.0, p=p5, scale=1e-3 / n)
+    assert (stats_o - stats_s).abs().max() <= 1e-6 * stats_s.abs().max()      # separate instantiations of one template
+    assert (dz_o - dz_s).abs().max() <= 1e-6 * dz_s.abs().max()
+    assert (p_o.sum(1) - 1).abs().max().item() <= 1e-5 * K
 
 
 def test_cluster_permutation_equivariance(ops):

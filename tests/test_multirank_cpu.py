@@ -39,6 +39,12 @@ def _worker(rank, world, port, n, d, K, out_dir):
     np.testing.assert_allclose(res.f.numpy(), ref["f"], rtol=1e-12)
     np.testing.assert_allclose(res.dmu.numpy(), ref["dmu"], rtol=1e-9, atol=1e-18)
     np.testing.assert_allclose(float(res.loss), ref["loss"], rtol=1e-10)
+    # same step with the shard's target rows kept (one-pass target + gradient launch)
+    res_p = buf.dec_step(mu, 1.0, 1e-3, round_decimals=5, want_p=True)
+    np.testing.assert_allclose(res_p.p.numpy(), ref["p"][lo:hi], atol=1e-7)
+    assert torch.equal(res_p.dmu, res.dmu)
+    buf.labels = None                                   # the extra pass above must not count as a label change
+    buf.dec_assign(mu, 1.0)
     # label-change counter: second pass with moved centroids, summed over ranks
     mu2 = mu.clone(); mu2[0] += 0.5
     _, st = buf.dec_assign(mu2, 1.0)
