@@ -8,8 +8,9 @@ Workload at every N (weak scaling, per-GPU work fixed) = BASELINE.json configs[1
      dec_assign          (q, labels, f; np.round(q,5))                 networks.py:279-288, models.py:92-94
      dec_target_kl_grad  (p = target_distribution(q) written out, loss,
                           dL/dz, dL/dmu; q recomputed in registers)    models.py:1320-1322, 1124-1127
-  with (N>1) the two packed-statistics all-reduces between/after them.  `--unfused` runs the
-  three-kernel chain dec_assign -> dec_target -> dec_kl_grad(p) instead (also timed under "extra").
+  On one GPU both passes run as ONE cooperative kernel (`ops.dec_step`: a grid-wide barrier all-reduces f
+  between them); with N>1 they are two kernels with the two packed-statistics exchanges between/after
+  them.  `--two-kernel` / `--unfused` run the two- / three-kernel chains instead (also timed under "extra").
 
 Contract (one JSON line on rank 0): metric/value/unit, n_gpus, steps, warmup,
 ms_per_step, higher_is_better, scaling, vs_baseline, dtype, data, config, clocks,
@@ -249,12 +250,19 @@ def run_gpu(args):
 
     fused_ex = exchange is not None and args.fused_exchange      # measured ~2 % slower than the stand-alone kernel
     unfused = args.unfused
+    one_kernel = world == 1 and not unfused and not args.two_kernel
+
+    def k_step(s):          # assign pass + grid-wide all-reduce of f + target/gradient pass in one cooperative kernel
+        ops.dec_step(s["z"], mu, ALPHA, 5, scale, out_q=s["q"], out_labels=s["labels"], out_p=s["p"], out_dz=s["dz"],
+                     out_f=s["st1"], out_stats=s["st2"])
 
     def step_unfused(s):
         k_assign(s); allreduce(s["st1"]); k_target(s); k_grad(s); allreduce(s["st2"])
 
     def step(s):
-        if unfused:
+        if one_kernel:
+            k_step(s)
+        elif unfused:
             step_unfused(s)
         elif fused_ex:      # collectives ride on the kernels: push in the producers' tails, pull in the consumers
             ex = exchange.desc
@@ -399,13 +407,15 @@ def run_gpu(args):
         return e0.elapsed_time(e1) / (reps * launches)
 
     reps = max(5, min(args.steps, 50))
-    kfns = {"dec_assign": k_assign, "dec_target": k_target, "dec_kl_grad": k_grad} if unfused else \
-           {"dec_assign": k_assign, "dec_target_kl_grad": k_tgrad}
+    kfns = {"dec_step": k_step} if one_kernel else (
+        {"dec_assign": k_assign, "dec_target": k_target, "dec_kl_grad": k_grad} if unfused else
+        {"dec_assign": k_assign, "dec_target_kl_grad": k_tgrad})
     for s_ in sets:                      # q / f / p of every set valid for the stand-alone kernels
         k_assign(s_); k_target(s_)
     kavg = {k: time_graph(graph_of(fn), N_SETS, reps) for k, fn in kfns.items()}
     alg_bytes = {"dec_assign": 4 * D + 4 * K + 4, "dec_target": 8 * K, "dec_kl_grad": 8 * D + 4 * K,
-                 "dec_target_kl_grad": 8 * D + 4 * K}                                  # per point
+                 "dec_target_kl_grad": 8 * D + 4 * K,
+                 "dec_step": (4 * D + 4 * K + 4) + (8 * D + 4 * K)}                    # per point
     dominant = max(kavg, key=kavg.get)
     achieved = alg_bytes[dominant] * N_PER_GPU / (kavg[dominant] * 1e-3) / 1e9
     step_bytes = sum(alg_bytes[k] for k in kavg)
@@ -423,8 +433,9 @@ def run_gpu(args):
                                 "below the algorithmic store bytes",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_point": alg_bytes[dominant],
-                "algorithmic_bytes": "z read 4d + p written 4K + dz written 4d (q is recomputed in registers)"
-                                     if dominant == "dec_target_kl_grad" else None,
+                "algorithmic_bytes": {"dec_target_kl_grad": "z read 4d + p written 4K + dz written 4d (q is recomputed in registers)",
+                                      "dec_step": "pass 1: z read 4d + q written 4K + labels 4; pass 2: z read 4d (mostly from "
+                                                  "L2) + p written 4K + dz written 4d"}.get(dominant),
                 "kernels_ms": kavg,
                 "kernels_gbs": {k: alg_bytes[k] * N_PER_GPU / (kavg[k] * 1e-3) / 1e9 for k in kavg},
                 "step_bytes_per_point": step_bytes,
@@ -432,13 +443,19 @@ def run_gpu(args):
                 "step_frac": step_bytes * N_PER_GPU / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                 "fp32_note": "the kernel is FP32-issue/latency-bound, not HBM-bound (SURVEY.md 8d; profiles/)"}
 
-    unfused_extra = None
-    if world == 1 and not unfused:       # the three-kernel chain of the earlier rounds, for comparison
+    unfused_extra, two_extra = None, None
+    if world == 1 and not unfused:       # the three-kernel chain of the earlier sessions, for comparison
         g3 = graph_of(lambda s_: (k_assign(s_), k_target(s_), k_grad(s_)))
         ms3 = time_graph(g3, N_SETS, reps)
         unfused_extra = {"workload": "dec_assign -> dec_target -> dec_kl_grad(p): the 3-kernel chain (240 B/point)",
                          "ms": ms3, "points_per_s": N_PER_GPU / (ms3 * 1e-3),
                          "hbm_frac": 240 * N_PER_GPU / (ms3 * 1e-3) / 1e9 / hbm_peak}
+    if one_kernel:                       # the two-kernel chain every rank runs when N > 1
+        g2 = graph_of(lambda s_: (k_assign(s_), k_tgrad(s_)))
+        ms2 = time_graph(g2, N_SETS, reps)
+        two_extra = {"workload": "dec_assign -> dec_target_kl_grad: the 2-kernel chain (176 B/point)",
+                     "ms": ms2, "points_per_s": N_PER_GPU / (ms2 * 1e-3),
+                     "hbm_frac": 176 * N_PER_GPU / (ms2 * 1e-3) / 1e9 / hbm_peak}
 
     dbg('e2e pass')
     # ---------------- end to end: host buffers in, host results out, every step ----------------
@@ -469,7 +486,10 @@ def run_gpu(args):
         main.wait_event(up_done[b])
         zd = zd2[b]
         mud.copy_(mu_h, non_blocking=True)
-        if unfused:
+        if one_kernel:
+            ops.dec_step(zd, mud, ALPHA, 5, scale, out_q=sd["q"], out_labels=sd["labels"], out_p=sd["p"], out_dz=sd["dz"],
+                         out_f=sd["st1"], out_stats=sd["st2"])
+        elif unfused:
             ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"])
             allreduce(sd["st1"])
             ops.dec_target(sd["q"], sd["st1"], 5, out=sd["p"])
@@ -511,7 +531,7 @@ def run_gpu(args):
     e2e_ms = float(t.item())
     e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int(zd2[0].numel() * 4 + mud.numel() * 4), "d2h_bytes_per_step": int(res_h.numel() * 8),
-           "ms_per_step": e2e_ms, "api": "ops.dec_assign + ops.dec_target_kl_grad on a pinned host latent set "
+           "ms_per_step": e2e_ms, "api": ("ops.dec_step" if one_kernel else "ops.dec_assign + ops.dec_target_kl_grad") + " on a pinned host latent set "
                                          "(upload of step i+1 double-buffered behind step i's kernels); "
                                          "loss, dmu, f, label-change count read back every step", "loss": loss_h}
 
@@ -521,6 +541,8 @@ def run_gpu(args):
         extra = extra_benchmarks(torch, ops, synth, dev, hbm_peak)
     if unfused_extra is not None:
         extra["dec_step_3_kernels"] = unfused_extra
+    if two_extra is not None:
+        extra["dec_step_2_kernels"] = two_extra
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -543,13 +565,16 @@ def run_gpu(args):
                                    f"CUDA graph replays of {GRAPH_STEPS} consecutive steps (rotating over the {N_SETS} input sets), "
                                    "single-step graphs for the remainder")
                                   if use_graphs else "eager launches"),
-                       "kernels_per_step": ["dec_assign", "dec_target", "dec_kl_grad"] if unfused else
-                                           ["dec_assign", "dec_target_kl_grad"],
+                       "kernels_per_step": ["dec_step (one cooperative kernel: assign pass, grid-wide all-reduce of f, "
+                                            "target + KL-gradient pass)"] if one_kernel else (
+                                           ["dec_assign", "dec_target", "dec_kl_grad"] if unfused else
+                                           ["dec_assign", "dec_target_kl_grad"]),
                        "l2": f"inputs/outputs rotate over {N_SETS} sets ({N_SETS * 140} MB) > 126 MB L2",
                        "timing": "CUDA events around the K steps, max over ranks; per-kernel durations from "
                                  "CUDA events around replays of single-kernel graphs over the same rotating sets"},
             "clocks": sampler.summary(), "e2e": e2e,
-            "gpu_launches": ((3 if unfused else 2) + ((1 if fused_ex else 2) if exchange is not None else 0)) * args.steps,
+            "gpu_launches": ((1 if one_kernel else (3 if unfused else 2)) +
+                             ((1 if fused_ex else 2) if exchange is not None else 0)) * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu, "extra": extra,
         }
@@ -685,6 +710,8 @@ def main():
     ap.add_argument("--single-step-graphs", action="store_true", help="one graph replay per step")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--two-kernel", action="store_true",
+                    help="one GPU: dec_assign + dec_target_kl_grad as two kernels instead of the one-kernel dec_step")
     ap.add_argument("--unfused", action="store_true",
                     help="three-kernel chain dec_assign -> dec_target -> dec_kl_grad(p) instead of the fused "
                          "target + KL-gradient kernel")

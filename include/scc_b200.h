@@ -292,6 +292,21 @@ int scc_dec_target_kl_grad(const float* z, int64_t n, int d, const float* mu, in
                            const double* f_cols, int round_decimals, float scale, float* p_out, float* dz,
                            double* stats, void* workspace, size_t workspace_bytes,
                            const scc_exchange* pull_f, const scc_exchange* push, scc_stream_t stream);
+/*
+ * scc_dec_step — the whole DEC step of one batch in ONE kernel (single GPU):
+ *   pass 1 = scc_dec_assign (q, labels, f, label-change count), a grid-wide barrier that all-reduces f
+ *   across the CTAs, pass 2 = scc_dec_target_kl_grad (p, loss, dL/dz, dL/dmu) with z re-read from L2.
+ *   Same arithmetic as the two stand-alone kernels (q and p bit-identical to them).  Cooperative launch:
+ *   all CTAs are co-resident.  Replaces networks.py:279-288 + models.py:92-94,1098-1099,1302-1322,1124-1127
+ *   for a batch that is processed whole (batch_eval + the update step on the same latent set).
+ *   q, labels, labels_prev, p_out, dz nullable.  f_stats [K+1], stats [K*d+2] float64 out.
+ *   Returns SCC_ERR_UNSUPPORTED for (d, K) served by the tiled gradient kernel (K*d > 160): call the two
+ *   kernels instead.
+ */
+int scc_dec_step(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
+                 float scale, float* q, int32_t* labels, const int32_t* labels_prev, double* f_stats,
+                 float* p_out, float* dz, double* stats, void* workspace, size_t workspace_bytes,
+                 scc_stream_t stream);
 int scc_peer_finish(double* out, int len, const scc_exchange* ex, scc_stream_t stream);
 int scc_peer_allreduce(const double* local, int len, double* out,
                        void* const* peer_windows, int rank, int world, int max_len,

@@ -332,8 +332,11 @@ __device__ __forceinline__ void prefetch_krow(const float* __restrict__ src, int
 }
 
 template <int MODE>
+__host__ __device__ constexpr bool mode_is_kl() { return MODE == MODE_KL || MODE == MODE_KLF || MODE == MODE_STEP; }
+
+template <int MODE>
 __host__ __device__ __forceinline__ float grad_fold_scale(float scale, float alpha) {
-    return MODE == MODE_KMEANS ? 1.f : ((MODE == MODE_KL || MODE == MODE_KLF) ? scale : 1.f) * (alpha + 1.f) / alpha;
+    return MODE == MODE_KMEANS ? 1.f : (mode_is_kl<MODE>() ? scale : 1.f) * (alpha + 1.f) / alpha;
 }
 
 template <int KP, bool EXACT, bool ALPHA1, int MODE>
@@ -349,13 +352,13 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
         loss += best;
         if (a.labels) a.labels[i] = label;
         if (a.mindist) a.mindist[i] = best;
-    } else if constexpr (MODE == MODE_KL || MODE == MODE_KLF) {
+    } else if constexpr (mode_is_kl<MODE>()) {
         const float inv = rcp_approx(tsum);
         float p[KP];
         if constexpr (MODE == MODE_KL) {           // target row requested before the z tile wait (prefetch_krow)
 #pragma unroll
             for (int j = 0; j < KP; ++j) p[j] = pre[j];
-        } else {                                   // MODE_KLF: rebuild p from the column sums (fused mode)
+        } else {                                   // MODE_KLF / MODE_STEP: rebuild p from the column sums
 #pragma unroll
             for (int j = 0; j < KP; ++j) {
                 const float q = t[j] * inv;
@@ -385,23 +388,25 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
             }
             if (a.p_out) store_krow<KP, EXACT>(a.p_out + i * K, K, p);      // materialise target_distribution(q)
         }
-        // sum_j p_j log2(p_j / q_j) = sum_j p_j log2(p_j w_j^expo) + s log2(tsum).  The 1e-37 keeps a zero
-        // target at 0 * finite = 0 (torch KLDivLoss: xlogy); negative / NaN targets still give NaN.
+        // p_j / q_j = p_j w_j tsum for alpha == 1 (w_j = 1 + d_j is already in registers: no division); the log is
+        // taken of the RATIO (near 1), not of its large factors separately — lg2.approx has a relative error, so
+        // log2(p w) + log2(tsum) would lose the digits that cancel.  The 1e-37 keeps a zero target at
+        // 0 * finite = 0 (torch KLDivLoss: xlogy); negative / NaN targets still give NaN.
         float s2[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
             if (EXACT || j < K) {
                 s2[j & 1] += p[j];
-                const float lg = ALPHA1 ? lg2_approx(fmaf(p[j], w[j], 1e-37f))
-                                        : fmaf(expo, lg2_approx(w[j]), lg2_approx(p[j] + 1e-37f));
-                l2[j & 1] = fmaf(p[j], lg, l2[j & 1]);
+                const float ratio = ALPHA1 ? fmaf(p[j] * w[j], tsum, 1e-37f)
+                                           : fmaf(p[j], rcp_approx(fmaxf(t[j] * inv, 1e-37f)), 1e-37f);
+                l2[j & 1] = fmaf(p[j], lg2_approx(ratio), l2[j & 1]);
             }
         }
         const float s = s2[0] + s2[1];
         const float nis = -(inv * s);
 #pragma unroll
         for (int j = 0; j < KP; ++j) coef[j] = (EXACT || j < K) ? fmaf(t[j], nis, p[j]) * u[j] : 0.f;
-        loss += fmaf(s, lg2_approx(tsum), l2[0] + l2[1]);
+        loss += l2[0] + l2[1];
         ssum += s;
     } else {
         const float inv = rcp_approx(tsum);
@@ -561,7 +566,64 @@ dec_grad_reg_kernel(const DecArgs a) {
     const float* krows = krow_operand<MODE>(a);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int stage = 0, ob = 0;
-    uint32_t use = 0;
+
+    if constexpr (MODE == MODE_STEP) {
+        // ---- pass 1 of the one-kernel DEC step: the assign pass (same arithmetic as dec_assign_kernel) over
+        // this CTA's tiles, then a grid-wide barrier + all-reduce of f, all CTAs co-resident (cooperative launch)
+        float facc[KP + 1];
+#pragma unroll
+        for (int j = 0; j <= KP; ++j) facc[j] = 0.f;
+        for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
+            const int np = ring.points(tile);
+            const bool active = (int)threadIdx.x < np;
+            ring.wait(stage, tile);
+            float zr[D];
+            if (active) load_row<D>(ring.stage_ptr(stage), threadIdx.x, zr);
+            __syncwarp();
+            ring.issue(stage, tile + S * G);
+            if (active) {
+                const size_t i = (size_t)tile * kDecTile + threadIdx.x;
+                float w[KP], u[KP], t[KP];
+                float2 z2[DP2];
+                pack_row<D>(zr, z2);
+                int label;
+                float best, tsum;
+                student_t_row<D, KP, EXACT, ALPHA1, true>(z2, nmu2_s, K, inv_alpha, expo, w, u, t, tsum, label, best);
+                const float inv = rcp_approx(tsum);
+#pragma unroll
+                for (int j = 0; j < KP; ++j) {
+                    float q = t[j] * inv;
+                    if (a.round5) q = round_dec5(q);
+                    t[j] = q;
+                    facc[j] += q;
+                }
+                if (a.q) store_krow<KP, EXACT>(a.q + i * K, K, t);
+                if (a.labels) a.labels[i] = label;
+                if (a.labels_prev) facc[KP] += (a.labels_prev[i] != label) ? 1.f : 0.f;
+            }
+            if (++stage == S) stage = 0;
+        }
+        SCC_TL(a.timeline, 6);                                     // pass 1 main loop done
+        // pass 2's first tiles are requested before the grid barrier: they land while the CTAs wait
+#pragma unroll
+        for (int s = 0; s < S; ++s) ring.issue((stage + s) % S, blockIdx.x + s * G);
+        __syncthreads();
+        double* f_s = cta_stats;                                   // [K+1] (cta_stats is free until the tail)
+        double* mine_s = cta_stats + ((KP + 2) & ~1);              // [KP+1] this CTA's sums
+        cta_reduce<KP + 1, kDecThreads>(facc, scratch, mine_s);
+        if (!EXACT) {
+            if (threadIdx.x == 0 && K < KP) mine_s[K] = mine_s[KP];
+            __syncthreads();
+        }
+        const int sp_tail = (K * D + 2 + 1) & ~1;                  // pass-1 slots live behind the tail's slots
+        grid_barrier_sum<kDecThreads>(mine_s, K + 1, a.partials + (size_t)gridDim.x * sp_tail, a.counter + 1, f_s,
+                                      scratch);
+        if (threadIdx.x < KP) inv_f[threadIdx.x] = ((int)threadIdx.x < K) ? (float)(1.0 / f_s[threadIdx.x]) : 0.f;
+        if (blockIdx.x == 0 && (int)threadIdx.x <= K && a.f_out) a.f_out[threadIdx.x] = f_s[threadIdx.x];
+        __syncthreads();
+        SCC_TL(a.timeline, 7);                                     // grid barrier + f all-reduce done
+    }
+
     for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {       // no CTA-wide barrier in this loop
         const int np = ring.points(tile);
         const bool active = (int)threadIdx.x < np;
@@ -570,7 +632,7 @@ dec_grad_reg_kernel(const DecArgs a) {
 #pragma unroll
         for (int j = 0; j < KP; ++j) kcur[j] = 0.f;
         prefetch_krow<KP, EXACT>(krows, (int64_t)tile * kDecTile, np, K, kcur);
-        ring.wait(stage, tile, use);
+        ring.wait(stage, tile);
         if (tile == (int)blockIdx.x) SCC_TL(a.timeline, 2);
         float zr[D];
         if (active) load_row<D>(ring.stage_ptr(stage), threadIdx.x, zr);
@@ -632,12 +694,12 @@ dec_grad_reg_kernel(const DecArgs a) {
                 warp_copy_rows_out<D>(src_w, dst_w, nv);
             }
         }
-        if (++stage == S) { stage = 0; ++use; }
+        if (++stage == S) stage = 0;
     }
     if (kBulkOut && lane == 0) bulk_wait0();             // this warp's dz stores are complete
     pdl_trigger();                      // successor may start its prologue under our reduction tail
     SCC_TL(a.timeline, 3);
-    if (MODE == MODE_KL || MODE == MODE_KLF) sm[0] *= a.scale * 0.693147180559945f;     // loss = scale * ln2 * sum p log2(p/q)
+    if (mode_is_kl<MODE>()) sm[0] *= a.scale * 0.693147180559945f;     // loss = scale * ln2 * sum p log2(p/q)
     float acc[NV];
     acc[0] = sm[0]; acc[1] = sm[1];
 #pragma unroll
@@ -664,8 +726,9 @@ dec_grad_reg_kernel(const DecArgs a) {
     if (MODE == MODE_KMEANS && o < K) cta_stats[2 + K * D + o] = wj;
     __syncthreads();
     const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
-    grid_publish<kDecThreads, 25>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials, a.counter,
-                                  a.stats, scratch, &push);
+    const bool last = grid_publish<kDecThreads, 25>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials,
+                                                    a.counter, a.stats, scratch, &push);
+    if (MODE == MODE_STEP && last && threadIdx.x == 0) a.counter[1] = 0u;    // every CTA is past the pass-1 barrier
     SCC_TL(a.timeline, 5);
 }
 
@@ -804,7 +867,7 @@ dec_grad_tiled_kernel(const DecArgs a) {
     }
     // ---- CTA reduction ----
     pdl_trigger();
-    if (MODE == MODE_KL || MODE == MODE_KLF) small[0] *= a.scale * 0.693147180559945f;      // loss = scale * ln2 * sum p log2(p/q)
+    if (mode_is_kl<MODE>()) small[0] *= a.scale * 0.693147180559945f;      // loss = scale * ln2 * sum p log2(p/q)
     cta_reduce<NSM, kDecThreads>(small, scratch, small_s);
     // per-(warp, group) 4x4 partials -> shared (the ring buffer is free now), fixed-order sum
     double* part = reinterpret_cast<double*>(ring_buf);                      // [NW*G2][KP*D]
@@ -870,7 +933,8 @@ constexpr size_t grad_tiled_smem() {
 }
 
 template <typename Kern>
-static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t stream, int tile_points = kDecTile) {
+static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t stream, int tile_points = kDecTile,
+                      bool cooperative = false) {
     const int64_t num_tiles = (args.n + tile_points - 1) / tile_points;
     int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), kDecThreads, smem, kMaxCtasPerSm);
     if (grid < 0) return (int)grid;
@@ -883,8 +947,13 @@ static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t 
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL, see scc_common.cuh
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    if (cooperative) {              // grid-wide barrier inside: every CTA must be resident (grid <= SMs x occupancy)
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+    } else {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL, see scc_common.cuh
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+    }
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     SCC_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
@@ -906,12 +975,15 @@ struct DecOps {
     static int grad_inst(const DecArgs& a, cudaStream_t st) {
         constexpr bool kTiled = (KP * D > 160);
         if constexpr (kTiled) {
-            if constexpr (D % 4 == 0 && KP % 4 == 0)
+            if constexpr (MODE == MODE_STEP)
+                return SCC_ERR_UNSUPPORTED;          // the one-kernel step exists for the register-blocked shapes only
+            else if constexpr (D % 4 == 0 && KP % 4 == 0)
                 return launch_dec(dec_grad_tiled_kernel<D, KP, EXACT, A1, MODE>, a, grad_tiled_smem<D, KP>(), st);
             else
                 return SCC_ERR_UNSUPPORTED;
         } else {
-            return launch_dec(dec_grad_reg_kernel<D, KP, EXACT, A1, MODE>, a, grad_reg_smem<D, KP>(), st);
+            return launch_dec(dec_grad_reg_kernel<D, KP, EXACT, A1, MODE>, a, grad_reg_smem<D, KP>(), st, kDecTile,
+                              MODE == MODE_STEP);
         }
     }
     template <int MODE>

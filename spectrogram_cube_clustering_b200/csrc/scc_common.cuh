@@ -267,11 +267,12 @@ struct WarpRing {
     uint64_t* bar;      // this warp's STAGES barriers
     const float* z;
     int num_tiles, last_points, warp, lane;
+    uint32_t phase;     // bit s = parity the next wait on stage s expects (flips per completed TMA fill)
 
     // bars: [NW][STAGES] uint64.  Ends with __syncwarp(); no CTA-wide barrier needed (each warp only ever
     // touches its own barriers and its own rows).
     __device__ __forceinline__ void init(float* b, uint64_t* bars, const float* z_, int64_t n_) {
-        buf = b; z = z_;
+        buf = b; z = z_; phase = 0u;
         warp = threadIdx.x >> 5; lane = threadIdx.x & 31;
         bar = bars + warp * STAGES;
         num_tiles = (int)((n_ + TILE - 1) / TILE);
@@ -343,10 +344,10 @@ struct WarpRing {
         }
         if constexpr (kCpAsync) cp_async_commit();        // empty groups keep the per-thread count aligned
     }
-    // use_index = how many times this stage has been consumed before.  After wait() returns every lane
-    // may read any row of the warp's slices.  (Slices filled with plain stores were written STAGES
-    // iterations ago and are ordered by the __syncwarp() of the iterations in between.)
-    __device__ __forceinline__ void wait(int stage, int tile, uint32_t use_index) {
+    // After wait() returns every lane may read any row of the warp's slices.  (Slices filled with plain
+    // stores were written STAGES iterations ago and are ordered by the __syncwarp() of the iterations in
+    // between.)  The mbarrier parity is tracked per stage, so a kernel may run several passes over z.
+    __device__ __forceinline__ void wait(int stage, int tile) {
         if constexpr (kCpAsync) {
             cp_async_wait<STAGES - 1>();
             __syncwarp();
@@ -357,7 +358,10 @@ struct WarpRing {
 #pragma unroll
                 for (int r = 0; r < P; ++r) any = any || tma_ok(slice_rows(last_points, r));
             }
-            if (any) mbar_wait(&bar[stage], use_index & 1u);
+            if (any) {
+                mbar_wait(&bar[stage], (phase >> stage) & 1u);
+                phase ^= 1u << stage;
+            }
         }
     }
 };
@@ -580,6 +584,54 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
     }
     if (tid == 0) *counter = 0u;
     return true;
+}
+
+// Grid-wide barrier + all-reduce of a short per-CTA statistics vector INSIDE a kernel whose CTAs are all
+// co-resident (cooperative launch): every CTA publishes its S doubles, takes a ticket, waits until the
+// whole grid has, and then sums all slots itself in the same fixed order (thread t: column t % SP, rows
+// t / SP, t / SP + R, ...; row groups combined in order) — every CTA ends with the bit-identical vector in
+// out_s (shared memory, S doubles).  `counter` must be 0 on entry; the caller resets it once no CTA can
+// still be waiting (e.g. in the kernel's final grid_publish).  scratch: NT doubles.
+template <int NT>
+__device__ __forceinline__ void grid_barrier_sum(const double* cta_stats, int S, double* slots, unsigned int* counter,
+                                                 double* out_s, double* scratch) {
+    const int tid = threadIdx.x;
+    const int SP = (S + 1) & ~1;
+    const int G = gridDim.x;
+    double* mine = slots + (size_t)blockIdx.x * SP;
+    for (int s = tid; s < SP; s += NT) __stcg(mine + s, (s < S) ? cta_stats[s] : 0.0);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int seen;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
+        ++seen;
+        while (seen < (unsigned int)G)
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    }
+    __syncthreads();
+    const int R = NT / SP;                        // SP <= NT
+    const int c = tid % SP, r = tid / SP;
+    double acc = 0.0;
+    if (r < R) {
+        for (int b = r; b < G; b += 16 * R) {
+            double v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int bb = b + u * R;
+                v[u] = (bb < G) ? __ldcg(slots + (size_t)bb * SP + c) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc += v[u];
+        }
+        scratch[r * SP + c] = acc;
+    }
+    __syncthreads();
+    if (tid < S) {
+        double t = 0.0;
+        for (int rr = 0; rr < R; ++rr) t += scratch[rr * SP + tid];
+        out_s[tid] = t;
+    }
+    __syncthreads();
 }
 
 // Stand-alone fixed-order reduction of per-CTA partial slots, for statistics vectors too long

@@ -20,7 +20,8 @@ constexpr int kMaxGmmGrid = 512;
 constexpr size_t kWorkspaceHeader = 256;   // counters live in front of the partial slots
 
 // MODE_KL: target p streamed from memory;  MODE_KLF: p rebuilt in registers from the column sums (fused mode)
-enum { MODE_KL = 0, MODE_GENERIC = 1, MODE_KMEANS = 2, MODE_KLF = 3 };
+// MODE_STEP: MODE_KLF preceded, in the same (cooperative) kernel, by the assign pass and a grid-wide all-reduce of f
+enum { MODE_KL = 0, MODE_GENERIC = 1, MODE_KMEANS = 2, MODE_KLF = 3, MODE_STEP = 4 };
 
 struct DecArgs {
     const float* z;
@@ -38,6 +39,7 @@ struct DecArgs {
     const float* p;
     float* p_out;              // fused mode (p == NULL): also write the rebuilt target rows here, or NULL
     const double* f_cols;
+    double* f_out;             // MODE_STEP: [K+1] column sums + label-change count of the assign pass
     const float* grad_q;
     float scale;
     float* dz;
@@ -93,6 +95,9 @@ int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float 
                 const double* f_cols, int round_decimals, float scale, float* dz, double* stats,
                 void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* pull_f = nullptr,
                 const ExchangeDesc* push = nullptr, float* p_out = nullptr);
+int dec_step(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals, float scale,
+             float* q, int32_t* labels, const int32_t* labels_prev, double* f_stats, float* p_out, float* dz,
+             double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
 int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* grad_q,
                  float* dz, double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
 int kmeans_step(const float* z, int64_t n, int d, const float* centers, int K, int32_t* labels, float* mindist,

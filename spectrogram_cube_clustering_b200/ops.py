@@ -168,6 +168,38 @@ def dec_target_kl_grad(z, mu, f, alpha=1.0, round_decimals=0, scale=1.0, want_p=
     return stats, p, dz
 
 
+def dec_step_supported(d: int, K: int) -> bool:
+    """Shapes the one-kernel step exists for (the register-blocked gradient kernel: K_padded * d <= 160)."""
+    kp = 4 if K <= 4 else (8 if K <= 8 else 16)
+    return d in SUPPORTED_DIMS and K <= MAX_K and kp * d <= 160
+
+
+def dec_step(z, mu, alpha=1.0, round_decimals=0, scale=1.0, want_q=True, want_labels=True, want_p=True, want_dz=True,
+             labels_prev=None, out_q=None, out_labels=None, out_p=None, out_dz=None, out_f=None, out_stats=None):
+    """The whole DEC step of one batch in ONE (cooperative) kernel launch — assign pass, grid-wide all-reduce of
+    f, target + KL-gradient pass.  -> dict(q, labels, f [K+1 float64: f_j, label changes], p, dz,
+    stats [K*d+2 float64: loss, sum_i s_i, dmu]).  networks.py:279-288 + models.py:1302-1322 + 1124-1127."""
+    lib = _lib.load()
+    _require(z, "z"); _require(mu, "mu")
+    n, d = z.shape
+    K = mu.shape[0]
+    dev = z.device
+    q = out_q if out_q is not None else (torch.empty(n, K, dtype=torch.float32, device=dev) if want_q else None)
+    labels = out_labels if out_labels is not None else (torch.empty(n, dtype=torch.int32, device=dev) if want_labels else None)
+    p = out_p if out_p is not None else (torch.empty(n, K, dtype=torch.float32, device=dev) if want_p else None)
+    dz = out_dz if out_dz is not None else (torch.empty_like(z) if want_dz else None)
+    if labels_prev is not None:
+        _require(labels_prev, "labels_prev", torch.int32)
+    f = out_f if out_f is not None else torch.empty(K + 1, dtype=torch.float64, device=dev)
+    stats = out_stats if out_stats is not None else torch.empty(K * d + 2, dtype=torch.float64, device=dev)
+    ws = workspace(dev, d, K)
+    rc = lib.scc_dec_step(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), int(round_decimals), float(scale),
+                          _ptr(q), _ptr(labels), _ptr(labels_prev), f.data_ptr(), _ptr(p), _ptr(dz), stats.data_ptr(),
+                          ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "scc_dec_step")
+    return dict(q=q, labels=labels, f=f, p=p, dz=dz, stats=stats)
+
+
 def dec_backward(z, mu, grad_q, alpha=1.0, want_dz=True):
     """Layer backward for an arbitrary dL/dq -> (dz [n,d] | None, dmu float64 [K,d])."""
     lib = _lib.load()

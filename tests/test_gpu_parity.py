@@ -144,6 +144,75 @@ def test_dec_target_kl_grad_golden(ops, case):
     assert none_p is None and none_dz is None and torch.equal(stats_n, stats0)
 
 
+@pytest.mark.parametrize("n,d,K,alpha,rd", [(1, 9, 8, 1.0, 5), (255, 9, 5, 1.0, 0), (4097, 16, 7, 1.0, 5),
+                                            (1000, 10, 16, 2.0, 5), (777, 8, 3, 0.5, 0), (300, 4, 2, 1.0, 5),
+                                            (70001, 9, 8, 1.0, 5), (5000, 32, 4, 1.0, 0), (2049, 12, 8, 1.0, 5),
+                                            (333, 20, 8, 1.0, 5), (640, 24, 4, 1.0, 0)])
+def test_dec_step_one_kernel_matches_two_kernel_chain(ops, n, d, K, alpha, rd):
+    """scc_dec_step (assign pass + grid barrier + target/gradient pass in one cooperative kernel) against
+    scc_dec_assign + scc_dec_target_kl_grad, and through them against the oracle."""
+    assert ops.dec_step_supported(d, K)
+    rng = np.random.default_rng(7 * n + d + K)
+    z = dev(rng.normal(size=(n, d)).astype(np.float32) * 1.5 + 1.0)
+    mu = dev(rng.normal(size=(K, d)).astype(np.float32) + 1.0)
+    prev = torch.randint(0, K, (n,), device="cuda", dtype=torch.int32)
+    scale = 1e-3 / n
+    q2, lab2, f2 = ops.dec_assign(z, mu, alpha, rd, labels_prev=prev)
+    st2, p2, dz2 = ops.dec_target_kl_grad(z, mu, f2, alpha, rd, scale)
+    out = ops.dec_step(z, mu, alpha, rd, scale, labels_prev=prev)
+    torch.cuda.synchronize()
+    assert torch.equal(out["q"], q2) and torch.equal(out["labels"], lab2)      # same per-point arithmetic
+    assert out["f"][K].item() == f2[K].item()                                  # label-change count
+    torch.testing.assert_close(out["f"][:K], f2[:K], rtol=1e-6, atol=0)        # different summation order
+    dp = (out["p"] - p2).abs()
+    if rd:      # f enters p through (float)(1/f): a last-bit difference may move a value across a rounding boundary
+        assert dp.max().item() <= QUANTUM * 1.01 and (dp > 1e-7).float().mean().item() < 5e-3
+    else:
+        assert dp.max().item() <= 2e-6
+    if n > 1:
+        assert abs(out["stats"][0].item() - st2[0].item()) <= 2e-4 * abs(st2[0].item()) + 1e-12
+        assert (out["stats"][2:] - st2[2:]).abs().max() <= 2e-4 * st2[2:].abs().max()
+        assert (out["dz"] - dz2).abs().max() <= 2e-4 * dz2.abs().max()
+    if not rd and n > 1:        # unrounded chain: straight against the float64 oracle
+        from oracle import dec as odec
+        ref = odec.dec_step(z.cpu().numpy(), mu.cpu().numpy(), alpha, 1e-3, round_to=None)
+        assert rel_err(out["p"].cpu().numpy(), ref["p"]) < 2 * TOL
+        assert abs(out["stats"][0].item() - ref["loss"]) <= TOL * abs(ref["loss"])
+        assert rel_err(out["dz"].cpu().numpy(), ref["dz"]) < TOL
+        assert rel_err(out["stats"][2:].cpu().numpy().reshape(K, d), ref["dmu"]) < TOL
+    # repeat: bit-identical (fixed reduction order), and the barrier counter was reset
+    out2 = ops.dec_step(z, mu, alpha, rd, scale, labels_prev=prev)
+    assert all(torch.equal(out[k], out2[k]) for k in ("q", "labels", "f", "p", "dz", "stats"))
+    # nothing N-sized requested
+    out3 = ops.dec_step(z, mu, alpha, rd, scale, want_q=False, want_labels=False, want_p=False, want_dz=False)
+    assert out3["q"] is None and out3["dz"] is None and torch.equal(out3["stats"], out["stats"])
+
+
+def test_dec_step_in_cuda_graph_and_unsupported_shape(ops):
+    from spectrogram_cube_clustering_b200 import _lib, synth
+    z, mu = synth.latent_points(100_000, 9, 8, device="cuda", rank=3)
+    eager = ops.dec_step(z, mu, 1.0, 5, 1e-8)
+    bufs = ops.dec_step(z, mu, 1.0, 5, 1e-8)          # allocates the outputs the graph will write
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ops.dec_step(z, mu, 1.0, 5, 1e-8, out_q=bufs["q"], out_labels=bufs["labels"], out_p=bufs["p"],
+                     out_dz=bufs["dz"], out_f=bufs["f"], out_stats=bufs["stats"])        # workspace of this stream
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            ops.dec_step(z, mu, 1.0, 5, 1e-8, out_q=bufs["q"], out_labels=bufs["labels"], out_p=bufs["p"],
+                         out_dz=bufs["dz"], out_f=bufs["f"], out_stats=bufs["stats"])
+    for k in ("p", "dz", "stats"):
+        bufs[k].zero_()
+    g.replay(); g.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(eager[k], bufs[k]) for k in ("q", "labels", "f", "p", "dz", "stats"))
+    assert not ops.dec_step_supported(32, 16)
+    z32, mu32 = synth.latent_points(1000, 32, 16, device="cuda")
+    with pytest.raises(_lib.SccError):
+        ops.dec_step(z32, mu32)
+
+
 @pytest.mark.parametrize("case", DEC_CASES)
 def test_dec_backward_generic_golden(ops, case):
     g = load_golden("dec", case)
@@ -154,7 +223,8 @@ def test_dec_backward_generic_golden(ops, case):
 
 
 @pytest.mark.parametrize("n,d,K", [(1, 9, 8), (255, 9, 5), (257, 32, 16), (4097, 16, 7), (1000, 10, 16),
-                                   (777, 8, 3), (300, 4, 2), (513, 12, 16), (1025, 20, 8), (640, 24, 12)])
+                                   (777, 8, 3), (300, 4, 2), (513, 12, 16), (1025, 20, 8), (640, 24, 12),
+                                   (5000, 32, 4)])          # last: large distances in the register-blocked kernel
 def test_dec_shapes_vs_oracle(ops, n, d, K):
     from oracle import dec as odec
     rng = np.random.default_rng(n + d + K)

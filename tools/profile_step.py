@@ -3,7 +3,7 @@
   ncu --set full --clock-control none --import-source on -k regex:"dec_|gmm_em" -o OUT python tools/profile_step.py
 
 Order of the profiled launches (after two unprofiled-size warm-ups each, so run with --launch-skip if needed):
-  headline shapes N=1M d=9 K=8: dec_assign (q, labels, f) | dec_target | dec_kl_grad(p) | dec_target_kl_grad
+  headline shapes N=1M d=9 K=8: dec_assign (q, labels, f) | dec_target | dec_kl_grad(p) | dec_target_kl_grad | dec_step
   configs[3] shard    N=4M d=32 K=16: dec_assign (stats only) | dec_target_kl_grad (centroid-only)
   configs[2] shape    N=4M d=9 K=16: gmm_em_step
 """
@@ -30,6 +30,8 @@ def headline(n=1_000_000, d=9, K=8):
         ops.dec_kl_grad(z, mu, 1.0, p=p, scale=1e-9, out_dz=dz, out_stats=st2)
         flush.zero_()
         ops.dec_target_kl_grad(z, mu, st1, 1.0, 5, 1e-9, out_p=p, out_dz=dz, out_stats=st2)
+        flush.zero_()
+        ops.dec_step(z, mu, 1.0, 5, 1e-9, out_q=q, out_labels=lab, out_p=p, out_dz=dz, out_f=st1, out_stats=st2)
     torch.cuda.synchronize()
 
 

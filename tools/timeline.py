@@ -31,7 +31,13 @@ def main(n=1_000_000, d=9, K=8):
         "dec_kl_grad (p given, dz)": lambda: ops.dec_kl_grad(z, mu, 1.0, p=p, scale=1e-9, out_dz=dz, out_stats=st2),
         "dec_kl_grad (fused p from f, no dz)": lambda: ops.dec_kl_grad(z, mu, 1.0, f=st1, scale=1e-9, want_dz=False,
                                                                        out_stats=st2),
+        "dec_target_kl_grad (p out, dz)": lambda: ops.dec_target_kl_grad(z, mu, st1, 1.0, 5, 1e-9, out_p=p, out_dz=dz,
+                                                                        out_stats=st2),
     }
+    if ops.dec_step_supported(d, K):
+        stf = torch.empty(K + 1, dtype=torch.float64, device=dev)
+        cases["dec_step (one kernel: q, labels, f | barrier | p, dz, stats)"] = lambda: ops.dec_step(
+            z, mu, 1.0, 5, 1e-9, out_q=q, out_labels=lab, out_p=p, out_dz=dz, out_f=stf, out_stats=st2)
     ops.dec_assign(z, mu, 1.0, 5, out_q=q, out_labels=lab, out_stats=st1)
     ops.dec_target(q, st1, 5, out=p)
     print(f"N={n} d={d} K={K}; times in us relative to the earliest CTA start (min / median / max over CTAs)")
@@ -46,14 +52,17 @@ def main(n=1_000_000, d=9, K=8):
         torch.cuda.synchronize()
         lib.scc_debug_set_timeline(None)
         t = tl.view(-1, 8).cpu()
-        t = t[t[:, 0] > 0][:, :6].double()
+        t = t[t[:, 0] > 0].double()
         t0 = t[:, 0].min()
+        two_pass = bool((t[:, 6] > 0).any())
         t = (t - t0) / 1e3
         print(f"\n{name}: {t.shape[0]} CTAs, event time {e0.elapsed_time(e1) * 1e3:.1f} us")
-        for k, nm in enumerate(NAMES):
+        order = [(0, "start"), (1, "prologue")] + ([(6, "pass 1 loop"), (7, "grid barrier")] if two_pass else []) + \
+                [(2, "first tile"), (3, "main loop"), (4, "cta reduce"), (5, "end")]
+        for k, nm in order:
             col = t[:, k]
             col = col[col >= 0]
-            print(f"  {nm:<11} {col.min():8.2f} {col.median():8.2f} {col.max():8.2f}")
+            print(f"  {nm:<12} {col.min():8.2f} {col.median():8.2f} {col.max():8.2f}")
         busy = (t[:, 3] - t[:, 2])
         print(f"  main-loop span per CTA: min {busy.min():.2f} median {busy.median():.2f} max {busy.max():.2f}")
 
