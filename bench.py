@@ -250,11 +250,13 @@ def run_gpu(args):
 
     fused_ex = exchange is not None and args.fused_exchange      # measured ~2 % slower than the stand-alone kernel
     unfused = args.unfused
-    one_kernel = world == 1 and not unfused and not args.two_kernel
+    # one cooperative kernel per step; with N > 1 the all-reduce of f runs inside it over NVLink peer memory
+    one_kernel = (world == 1 or exchange is not None) and not (unfused or args.two_kernel or fused_ex)
+    ex_desc = exchange.desc if (exchange is not None and world > 1) else None
 
     def k_step(s):          # assign pass + grid-wide all-reduce of f + target/gradient pass in one cooperative kernel
         ops.dec_step(s["z"], mu, ALPHA, 5, scale, out_q=s["q"], out_labels=s["labels"], out_p=s["p"], out_dz=s["dz"],
-                     out_f=s["st1"], out_stats=s["st2"])
+                     out_f=s["st1"], out_stats=s["st2"], exchange=ex_desc)
 
     def step_unfused(s):
         k_assign(s); allreduce(s["st1"]); k_target(s); k_grad(s); allreduce(s["st2"])
@@ -283,6 +285,20 @@ def run_gpu(args):
         torch.cuda.synchronize()
         assert torch.allclose(s0["st2"], g_ref, rtol=1e-12, atol=0), "fused exchange: gradient statistics differ from NCCL"
         dbg("fused exchange verified against NCCL")
+    if one_kernel and world > 1:    # the in-kernel exchange must reproduce the NCCL-reduced two-kernel chain
+        s0 = sets[0]
+        k_assign(s0); f_ref = s0["st1"].clone(); dist.all_reduce(f_ref, group=group)
+        ops.dec_target_kl_grad(s0["z"], mu, f_ref, ALPHA, 5, scale, out_p=s0["p"], out_dz=s0["dz"], out_stats=s0["st2"])
+        g_ref = s0["st2"].clone(); dist.all_reduce(g_ref, group=group)
+        p_ref = s0["p"].clone()
+        k_step(s0)
+        torch.cuda.synchronize()
+        # (f: per-thread fp32 partial sums are grouped differently in the two kernels -> ~1e-7 relative)
+        f_err = ((s0["st1"] - f_ref).abs() / f_ref.abs().clamp_min(1e-300)).max().item()
+        assert f_err <= 1e-6, f"one-kernel step: column sums differ from NCCL (max rel {f_err:.3e})"
+        assert torch.allclose(s0["st2"], g_ref, rtol=1e-4, atol=1e-18), "one-kernel step: gradient statistics differ from NCCL"
+        assert (s0["p"] - p_ref).abs().max().item() <= 1.01e-5, "one-kernel step: target distribution differs"
+        dbg("one-kernel step verified against NCCL")
     # warm-up (eager): also creates workspaces and primes NCCL
     for w in range(max(args.warmup, 3)):
         step(sets[w % N_SETS])
@@ -488,7 +504,7 @@ def run_gpu(args):
         mud.copy_(mu_h, non_blocking=True)
         if one_kernel:
             ops.dec_step(zd, mud, ALPHA, 5, scale, out_q=sd["q"], out_labels=sd["labels"], out_p=sd["p"], out_dz=sd["dz"],
-                         out_f=sd["st1"], out_stats=sd["st2"])
+                         out_f=sd["st1"], out_stats=sd["st2"], exchange=ex_desc)
         elif unfused:
             ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"])
             allreduce(sd["st1"])
@@ -549,6 +565,21 @@ def run_gpu(args):
         r = time_reference(3, 1, budget_s=25.0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
+    if world == 1:
+        parallelism = "single GPU"
+    else:
+        if one_kernel:
+            how = ("NVLink peer-memory exchange INSIDE the one-kernel step (f: pushed/pulled by the last CTA at the grid "
+                   "barrier between the two passes; gradient statistics: pushed by the kernel's last CTA, collected by a "
+                   "one-CTA finish kernel)")
+        elif fused_ex:
+            how = ("NVLink peer-memory exchange fused into the kernels (push in the producer's last CTA, pull in the "
+                   "consumer's prologue)")
+        elif exchange is not None:
+            how = "one-shot NVLink peer-memory exchange kernel"
+        else:
+            how = "NCCL"
+        parallelism = f"latent points sharded over {world} GPU(s); packed f64 stat all-reduce x2/step via " + how
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -556,11 +587,7 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_points_per_gpu": N_PER_GPU, "n_points_total": n_total, "d": D,
                        "K": K, "alpha": ALPHA, "gamma": GAMMA, "round_decimals": 5,
-                       "parallelism": (f"latent points sharded over {world} GPU(s); packed f64 stat all-reduce x2/step via "
-                                       + (("NVLink peer-memory exchange fused into the kernels (push in the producer's "
-                                           "last CTA, pull in the consumer's prologue)" if fused_ex else
-                                           "one-shot NVLink peer-memory exchange kernel") if exchange is not None else "NCCL"))
-                                      if world > 1 else "single GPU",
+                       "parallelism": parallelism,
                        "launch": (("one CUDA graph replay per step" if args.single_step_graphs else
                                    f"CUDA graph replays of {GRAPH_STEPS} consecutive steps (rotating over the {N_SETS} input sets), "
                                    "single-step graphs for the remainder")
@@ -574,7 +601,8 @@ def run_gpu(args):
                                  "CUDA events around replays of single-kernel graphs over the same rotating sets"},
             "clocks": sampler.summary(), "e2e": e2e,
             "gpu_launches": ((1 if one_kernel else (3 if unfused else 2)) +
-                             ((1 if fused_ex else 2) if exchange is not None else 0)) * args.steps,
+                             (((1 if (fused_ex or one_kernel) else 2) if exchange is not None else 0)
+                              if world > 1 else 0)) * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu, "extra": extra,
         }

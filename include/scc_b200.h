@@ -307,6 +307,15 @@ int scc_dec_step(const float* z, int64_t n, int d, const float* mu, int K, float
                  float scale, float* q, int32_t* labels, const int32_t* labels_prev, double* f_stats,
                  float* p_out, float* dz, double* stats, void* workspace, size_t workspace_bytes,
                  scc_stream_t stream);
+/* Multi-GPU form: the all-reduce of f over the GPUs runs INSIDE the kernel, between its two passes — the last
+ * CTA to reach the grid barrier pushes this GPU's f to every rank's exchange window (NVLink peer stores), waits
+ * for the world's vectors and releases the other CTAs with the rank-ordered sum; the kernel's last CTA pushes
+ * the final statistics, which scc_peer_finish(stats, K*d+2, ex) then collects.  scale = gamma / N_total;
+ * f_stats receives the all-reduced f.  Every rank must launch it (an empty shard, n == 0, included). */
+int scc_dec_step_ex(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
+                    float scale, float* q, int32_t* labels, const int32_t* labels_prev, double* f_stats,
+                    float* p_out, float* dz, double* stats, void* workspace, size_t workspace_bytes,
+                    const scc_exchange* ex, scc_stream_t stream);
 int scc_peer_finish(double* out, int len, const scc_exchange* ex, scc_stream_t stream);
 int scc_peer_allreduce(const double* local, int len, double* out,
                        void* const* peer_windows, int rank, int world, int max_len,

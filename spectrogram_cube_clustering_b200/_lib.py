@@ -75,6 +75,8 @@ _SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "scc_dec_step": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_int, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scc_dec_step_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_int, c_float, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "scc_peer_finish": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "scc_peer_window_bytes": (c_size_t, [c_int]),
     "scc_peer_allreduce": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -238,7 +238,7 @@ int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float 
 
 int dec_step(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals, float scale,
              float* q, int32_t* labels, const int32_t* labels_prev, double* f_stats, float* p_out, float* dz,
-             double* stats, void* ws, size_t ws_bytes, cudaStream_t st) {
+             double* stats, void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* ex) {
     int rc = check_common(z, n, d, mu, K, alpha, stats, ws, ws_bytes);
     if (rc != SCC_OK) return rc;
     if (!f_stats) return SCC_ERR_INVALID;
@@ -246,7 +246,8 @@ int dec_step(const float* z, int64_t n, int d, const float* mu, int K, float alp
     if ((K % 4 == 0) && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(p_out)) & 15u))
         return SCC_ERR_MISALIGNED;
     if (dz && (reinterpret_cast<uintptr_t>(dz) & 15u)) return SCC_ERR_MISALIGNED;
-    if (n == 0) {
+    const bool multi = ex && ex->windows;
+    if (n == 0 && !multi) {         // (an empty shard of a multi-GPU step still runs: it takes part in the exchanges)
         SCC_CUDA(cudaMemsetAsync(f_stats, 0, sizeof(double) * (K + 1), st));
         SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (K * d + 2), st));
         return SCC_OK;
@@ -256,6 +257,7 @@ int dec_step(const float* z, int64_t n, int d, const float* mu, int K, float alp
     a.q = q; a.labels = labels; a.labels_prev = labels_prev; a.f_out = f_stats;
     a.p_out = p_out; a.scale = scale; a.dz = dz; a.stats = stats;
     fill_reduction(a, ws);
+    fill_exchange(a, ex, /*push the final statistics=*/1, nullptr);
     return dec_grad_dispatch(a, d, MODE_STEP, st);
 }
 

@@ -616,8 +616,9 @@ dec_grad_reg_kernel(const DecArgs a) {
             __syncthreads();
         }
         const int sp_tail = (K * D + 2 + 1) & ~1;                  // pass-1 slots live behind the tail's slots
+        const PeerCtx ex1{a.ex_windows, a.ex_rank, a.ex_world, a.ex_max_len};
         grid_barrier_sum<kDecThreads>(mine_s, K + 1, a.partials + (size_t)gridDim.x * sp_tail, a.counter + 1, f_s,
-                                      scratch);
+                                      scratch, &ex1);
         if (threadIdx.x < KP) inv_f[threadIdx.x] = ((int)threadIdx.x < K) ? (float)(1.0 / f_s[threadIdx.x]) : 0.f;
         if (blockIdx.x == 0 && (int)threadIdx.x <= K && a.f_out) a.f_out[threadIdx.x] = f_s[threadIdx.x];
         __syncthreads();

@@ -181,6 +181,15 @@ int scc_dec_step(const float* z, int64_t n, int d, const float* mu, int K, float
                          stats, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int scc_dec_step_ex(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
+                    float scale, float* q, int32_t* labels, const int32_t* labels_prev, double* f_stats, float* p_out,
+                    float* dz, double* stats, void* workspace, size_t workspace_bytes, const scc_exchange* ex,
+                    scc_stream_t stream) {
+    scc::ExchangeDesc t;
+    return scc::dec_step(z, n, d, mu, K, alpha, round_decimals, scale, q, labels, labels_prev, f_stats, p_out, dz,
+                         stats, workspace, workspace_bytes, (cudaStream_t)stream, as_desc(ex, &t));
+}
+
 int scc_peer_finish(double* out, int len, const scc_exchange* ex, scc_stream_t stream) {
     if (!ex || !ex->windows) return SCC_ERR_INVALID;
     return scc::peer_finish(out, len, ex->windows, ex->rank, ex->world, ex->max_len, (cudaStream_t)stream);

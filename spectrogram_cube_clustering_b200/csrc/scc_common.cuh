@@ -587,28 +587,21 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
 }
 
 // Grid-wide barrier + all-reduce of a short per-CTA statistics vector INSIDE a kernel whose CTAs are all
-// co-resident (cooperative launch): every CTA publishes its S doubles, takes a ticket, waits until the
-// whole grid has, and then sums all slots itself in the same fixed order (thread t: column t % SP, rows
-// t / SP, t / SP + R, ...; row groups combined in order) — every CTA ends with the bit-identical vector in
-// out_s (shared memory, S doubles).  `counter` must be 0 on entry; the caller resets it once no CTA can
-// still be waiting (e.g. in the kernel's final grid_publish).  scratch: NT doubles.
+// co-resident (cooperative launch): every CTA publishes its S doubles and takes a ticket.
+//   * single GPU (ex == nullptr): every CTA waits until the whole grid has arrived and then sums all slots
+//     itself in the same fixed order (thread t: column t % SP, rows t / SP, t / SP + R, ...; row groups combined
+//     in order) — every CTA ends with the bit-identical vector in out_s (shared memory, S doubles);
+//   * multi GPU (ex != nullptr): the CTA that arrives LAST sums the slots, pushes the vector to every rank's
+//     exchange window over NVLink, waits for the world's vectors, sums them in rank order, stores the result
+//     behind the slots and releases a ready flag (an epoch number); the other CTAs wait on that flag only —
+//     the collective runs inside the compute kernel, between its two passes.
+// `counter[0]` (tickets) must be 0 on entry and is reset by the caller once no CTA can still be waiting;
+// `counter[1]` is the ready epoch (monotonic).  scratch: NT doubles.
 template <int NT>
-__device__ __forceinline__ void grid_barrier_sum(const double* cta_stats, int S, double* slots, unsigned int* counter,
-                                                 double* out_s, double* scratch) {
+__device__ __forceinline__ void grid_sum_slots(const double* slots, int S, double* out_s, double* scratch) {
     const int tid = threadIdx.x;
     const int SP = (S + 1) & ~1;
     const int G = gridDim.x;
-    double* mine = slots + (size_t)blockIdx.x * SP;
-    for (int s = tid; s < SP; s += NT) __stcg(mine + s, (s < S) ? cta_stats[s] : 0.0);
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int seen;
-        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
-        ++seen;
-        while (seen < (unsigned int)G)
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-    }
-    __syncthreads();
     const int R = NT / SP;                        // SP <= NT
     const int c = tid % SP, r = tid / SP;
     double acc = 0.0;
@@ -632,6 +625,57 @@ __device__ __forceinline__ void grid_barrier_sum(const double* cta_stats, int S,
         out_s[tid] = t;
     }
     __syncthreads();
+}
+
+template <int NT>
+__device__ __forceinline__ void grid_barrier_sum(const double* cta_stats, int S, double* slots, unsigned int* counter,
+                                                 double* out_s, double* scratch, const PeerCtx* ex = nullptr) {
+    __shared__ unsigned int s_ticket;
+    const int tid = threadIdx.x;
+    const int SP = (S + 1) & ~1;
+    const int G = gridDim.x;
+    const bool multi = ex && ex->windows;
+    unsigned int epoch = 0;
+    if (multi && tid == 0)          // read before this CTA's ticket: nobody can advance it until all tickets are in
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(epoch) : "l"(counter + 1) : "memory");
+    double* mine = slots + (size_t)blockIdx.x * SP;
+    for (int s = tid; s < SP; s += NT) __stcg(mine + s, (s < S) ? cta_stats[s] : 0.0);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int seen;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
+        s_ticket = seen;
+        if (!multi) {
+            ++seen;
+            while (seen < (unsigned int)G)
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        }
+    }
+    __syncthreads();
+    if (!multi) {
+        grid_sum_slots<NT>(slots, S, out_s, scratch);
+        return;
+    }
+    double* global_vec = slots + (size_t)G * SP;                    // [S] the world's sum, behind the slots
+    if (s_ticket == (unsigned int)G - 1) {                          // last CTA of this GPU: local sum, then the exchange
+        grid_sum_slots<NT>(slots, S, out_s, scratch);
+        peer_push(*ex, (tid < S) ? out_s[tid] : 0.0, S);
+        __syncthreads();
+        peer_pull(*ex, out_s, S);                                   // rank-ordered sum of every GPU's vector
+        if (tid < S) __stcg(global_vec + tid, out_s[tid]);
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + 1), "r"(epoch + 1u) : "memory");
+    } else {
+        if (tid == 0) {
+            unsigned int now;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(counter + 1) : "memory");
+            } while (now != epoch + 1u);
+        }
+        __syncthreads();
+        if (tid < S) out_s[tid] = __ldcg(global_vec + tid);
+        __syncthreads();
+    }
 }
 
 // Stand-alone fixed-order reduction of per-CTA partial slots, for statistics vectors too long

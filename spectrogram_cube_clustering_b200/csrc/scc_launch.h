@@ -97,7 +97,7 @@ int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float 
                 const ExchangeDesc* push = nullptr, float* p_out = nullptr);
 int dec_step(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals, float scale,
              float* q, int32_t* labels, const int32_t* labels_prev, double* f_stats, float* p_out, float* dz,
-             double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
+             double* stats, void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* ex = nullptr);
 int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* grad_q,
                  float* dz, double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
 int kmeans_step(const float* z, int64_t n, int d, const float* centers, int K, int32_t* labels, float* mindist,

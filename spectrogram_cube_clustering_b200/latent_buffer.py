@@ -167,6 +167,20 @@ class LatentBuffer:
         to every rank, the gradient kernel pulls it in its prologue and pushes its own statistics, and
         one small finish kernel collects them — three launches per step, no separate collective."""
         K = mu.shape[0]
+        one_kernel = getattr(ops, "dec_step_supported", lambda d, k: False)(self.d, K)
+        if one_kernel and (self.world == 1 or self.exchange is not None):
+            # the whole step in one cooperative kernel; with a peer exchange the all-reduce of f runs inside it
+            # (between its two passes) and a one-CTA finish kernel collects the gradient statistics
+            prev = self.labels
+            out_labels = self._labels_spare if self._labels_spare is not None else torch.empty(
+                self.n_local, dtype=torch.int32, device=self.z.device)
+            r = ops.dec_step(self.z, mu, alpha, round_decimals, gamma / self.n_total, want_q=False, want_labels=True,
+                             want_p=want_p, want_dz=want_dz, labels_prev=prev, out_labels=out_labels,
+                             exchange=self.exchange.desc if (self.exchange is not None and self.world > 1) else None)
+            self._labels_spare, self.labels = self.labels, r["labels"]
+            st, stats = r["f"], r["stats"]
+            return DecStepResult(loss=stats[0], dmu=stats[2:].view(K, self.d), f=st[:K], n_changed=st[K], dz=r["dz"],
+                                 p=r["p"])
         if self.exchange is not None and self.world > 1:
             ex = self.exchange.desc
             prev = self.labels

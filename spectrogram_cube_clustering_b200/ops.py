@@ -175,10 +175,13 @@ def dec_step_supported(d: int, K: int) -> bool:
 
 
 def dec_step(z, mu, alpha=1.0, round_decimals=0, scale=1.0, want_q=True, want_labels=True, want_p=True, want_dz=True,
-             labels_prev=None, out_q=None, out_labels=None, out_p=None, out_dz=None, out_f=None, out_stats=None):
+             labels_prev=None, out_q=None, out_labels=None, out_p=None, out_dz=None, out_f=None, out_stats=None,
+             exchange=None):
     """The whole DEC step of one batch in ONE (cooperative) kernel launch — assign pass, grid-wide all-reduce of
     f, target + KL-gradient pass.  -> dict(q, labels, f [K+1 float64: f_j, label changes], p, dz,
-    stats [K*d+2 float64: loss, sum_i s_i, dmu]).  networks.py:279-288 + models.py:1302-1322 + 1124-1127."""
+    stats [K*d+2 float64: loss, sum_i s_i, dmu]).  networks.py:279-288 + models.py:1302-1322 + 1124-1127.
+    With ``exchange`` (a peer-exchange descriptor, one process per GPU) f is all-reduced over the GPUs inside
+    the kernel and the statistics are collected by a one-CTA finish kernel: ``scale`` must be gamma / N_total."""
     lib = _lib.load()
     _require(z, "z"); _require(mu, "mu")
     n, d = z.shape
@@ -193,10 +196,12 @@ def dec_step(z, mu, alpha=1.0, round_decimals=0, scale=1.0, want_q=True, want_la
     f = out_f if out_f is not None else torch.empty(K + 1, dtype=torch.float64, device=dev)
     stats = out_stats if out_stats is not None else torch.empty(K * d + 2, dtype=torch.float64, device=dev)
     ws = workspace(dev, d, K)
-    rc = lib.scc_dec_step(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), int(round_decimals), float(scale),
-                          _ptr(q), _ptr(labels), _ptr(labels_prev), f.data_ptr(), _ptr(p), _ptr(dz), stats.data_ptr(),
-                          ws.data_ptr(), ws.numel(), _stream())
+    rc = lib.scc_dec_step_ex(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), int(round_decimals), float(scale),
+                             _ptr(q), _ptr(labels), _ptr(labels_prev), f.data_ptr(), _ptr(p), _ptr(dz),
+                             stats.data_ptr(), ws.data_ptr(), ws.numel(), _ex(exchange), _stream())
     _lib.check(rc, "scc_dec_step")
+    if exchange is not None:        # the kernel's last CTA pushed the statistics: collect the world's sum
+        peer_finish(stats, exchange)
     return dict(q=q, labels=labels, f=f, p=p, dz=dz, stats=stats)
 
 
