@@ -1,3 +1,5 @@
+"""One-kernel step (ops.dec_step) vs the two-kernel chain at the headline shape, both replayed as 16-step CUDA graphs
+over 4 rotating input sets (python tools/time_step.py)."""
 import sys, os, torch
 sys.path.insert(0, os.getcwd())
 from spectrogram_cube_clustering_b200 import ops, synth
