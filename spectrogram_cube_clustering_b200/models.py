@@ -16,6 +16,7 @@ control block every ``poll_interval`` iterations.
 from __future__ import annotations
 
 import math
+import os
 import warnings
 
 import numpy as np
@@ -322,6 +323,32 @@ def gmm(z_array, n_clusters, means_init=None, weights_init=None):
     with np.errstate(under="ignore"):
         labels = gm.fit_predict(buf)
     return labels, gm.means_
+
+
+def save_labels(label_list, savepath, serial=None):
+    """Append sample-wise labels to ``Labels.csv`` / ``Labels{serial}.csv`` (``utils.py:1181-1209``): a list of
+    dicts sharing one key set; the header row is written only when the file is created."""
+    import csv
+    fname = os.path.join(savepath, "Labels.csv" if serial is None else f"Labels{serial}.csv")
+    fresh = not os.path.exists(fname)
+    with open(fname, "w" if fresh else "a", newline="") as fh:
+        writer = csv.DictWriter(fh, list(label_list[0].keys()))
+        if fresh:
+            writer.writeheader()
+        writer.writerows(label_list)
+    return fname
+
+
+def gmm_fit(config, z_array, n_clusters):
+    """GMM initialisation plus the reference's on-disk side effects (``models.py:415-449``): ``Labels.csv``
+    (columns ``idx,label``), ``labels.npy`` and ``centroids.npy`` in ``config.savepath_run``.
+    Returns ``(labels [M], centroids [K, d])`` exactly as :func:`gmm`."""
+    labels, centroids = gmm(z_array, n_clusters)
+    rows = [{"idx": int(i), "label": int(lab)} for i, lab in enumerate(labels)]
+    save_labels(rows, config.savepath_run)
+    np.save(os.path.join(config.savepath_run, "labels"), labels)
+    np.save(os.path.join(config.savepath_run, "centroids"), centroids)
+    return labels, centroids
 
 
 # ----------------------------------------------------------------------------- DEC training loop
