@@ -24,7 +24,7 @@ def timeit(fn, reps=20):
 
 def main(d=9, K=8):
     print(f"d={d} K={K}   (median us, L2 flushed before each launch)")
-    print(f"{'N':>10} {'assign':>9} {'assign_noq':>10} {'target':>8} {'grad_p':>8} {'grad_f':>8} {'grad_f_nodz':>11} {'gmm_em':>9}")
+    print(f"{'N':>10} {'assign':>9} {'assign_noq':>10} {'target':>8} {'grad_p':>8} {'grad_f':>8} {'grad_f_nodz':>11} {'tgrad_p_out':>11} {'dec_step':>9} {'gmm_em':>9}")
     for n in (250_000, 1_000_000, 4_000_000, 16_000_000):
         z, mu = synth.latent_points(n, d, K, device=dev)
         q = torch.empty(n, K, device=dev); p = torch.empty(n, K, device=dev); dz = torch.empty(n, d, device=dev)
@@ -39,6 +39,12 @@ def main(d=9, K=8):
         t["grad_p"] = timeit(lambda: ops.dec_kl_grad(z, mu, 1.0, p=p, scale=1e-9, out_dz=dz, out_stats=st2))
         t["grad_f"] = timeit(lambda: ops.dec_kl_grad(z, mu, 1.0, f=st1, scale=1e-9, out_dz=dz, out_stats=st2))
         t["grad_f_nodz"] = timeit(lambda: ops.dec_kl_grad(z, mu, 1.0, f=st1, scale=1e-9, want_dz=False, out_stats=st2))
+        t["tgrad"] = timeit(lambda: ops.dec_target_kl_grad(z, mu, st1, 1.0, 5, 1e-9, out_p=p, out_dz=dz, out_stats=st2))
+        t["step"] = float("nan")
+        if ops.dec_step_supported(d, K):
+            stf = torch.empty(K + 1, dtype=torch.float64, device=dev)
+            t["step"] = timeit(lambda: ops.dec_step(z, mu, 1.0, 5, 1e-9, out_q=q, out_labels=lab, out_p=p, out_dz=dz,
+                                                    out_f=stf, out_stats=st2))
         if ops.gmm_supported(d, K):
             w0, mu0, cov0 = synth.gmm_initial_state(d, K, dev)
             params, pchol, ctrl = ops.gmm_pack_params(w0, mu0, cov0)
@@ -46,7 +52,7 @@ def main(d=9, K=8):
             t["gmm"] = timeit(lambda: ops.gmm_em_step(z, K, params, stats=stats), reps=8)
         else:
             t["gmm"] = float("nan")
-        print(f"{n:>10} {t['assign']:9.1f} {t['assign_noq']:10.1f} {t['target']:8.1f} {t['grad_p']:8.1f} {t['grad_f']:8.1f} {t['grad_f_nodz']:11.1f} {t['gmm']:9.1f}")
+        print(f"{n:>10} {t['assign']:9.1f} {t['assign_noq']:10.1f} {t['target']:8.1f} {t['grad_p']:8.1f} {t['grad_f']:8.1f} {t['grad_f_nodz']:11.1f} {t['tgrad']:11.1f} {t['step']:9.1f} {t['gmm']:9.1f}")
         del z, q, p, dz
 
 
