@@ -217,7 +217,6 @@ dec_assign_kernel(const DecArgs a) {
     constexpr int P = assign_ppt<D, KP>();
     constexpr int TILE = kDecTile * P;
     constexpr int S = assign_stages<D, KP>();
-    constexpr int NW = kDecThreads / 32;
     // CTA-level ring: a per-warp ring (WarpRing) was measured for this kernel too — its 6x more, 6x smaller
     // TMA copies lengthen the prologue by ~1.3 us and the short main loop gains nothing
     using Ring = ZRing<D, TILE, S, kDecThreads>;
@@ -901,7 +900,6 @@ dec_grad_tiled_kernel(const DecArgs a) {
 template <int D, int KP>
 constexpr size_t assign_smem() {
     constexpr int S = assign_stages<D, KP>();
-    constexpr int NW = kDecThreads / 32;
     return sizeof(float) * (S * kDecTile * assign_ppt<D, KP>() * RowLayout<D>::LD + 2 * ((KP * Pairs<D>::N + 1) & ~1)) +
            sizeof(double) * (KP + 1) + sizeof(uint64_t) * S;
 }

@@ -29,7 +29,7 @@ struct FinArgs {
 template <bool FROM_STATS>
 __global__ void __launch_bounds__(512, 1)
 gmm_finalize_kernel(const FinArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int d = a.d, K = a.K, LDA = d + 1, TRI = tri(d);
     double* mats = reinterpret_cast<double*>(smem_raw);       // [K][d*LDA]  L below, Y^T above
     __shared__ double nk_s[SCC_MAX_K];
