@@ -68,6 +68,25 @@ def test_argument_validation_without_gpu(lib):
     # kl_grad needs p or f
     assert lib.scc_dec_kl_grad(p(z), 4, 9, p(z), 8, 1.0, None, None, 0, 1.0, None, p(buf), p(buf), 1 << 30, None) == -1
     assert lib.scc_gmm_em_step(p(z), 4, 9, 8, None, p(buf), None, None, None, 1, p(buf), 1 << 30, None) == -1
+    # one-pass target + gradient: needs the column sums; bad rounding flag
+    assert lib.scc_dec_target_kl_grad(p(z), 4, 9, p(z), 8, 1.0, None, 0, 1.0, None, None, p(buf), p(buf), 1 << 30,
+                                      None, None, None) == -1
+    assert lib.scc_dec_target_kl_grad(p(z), 4, 9, p(z), 8, 1.0, p(buf), 3, 1.0, None, None, p(buf), p(buf), 1 << 30,
+                                      None, None, None) == -1
+    # one-kernel step: f_stats is mandatory; bad rounding flag; unsupported d; an empty batch is a no-op
+    assert lib.scc_dec_step(p(z), 4, 9, p(z), 8, 1.0, 0, 1.0, None, None, None, None, None, None, p(buf), p(buf),
+                            1 << 30, None) == -1
+    assert lib.scc_dec_step(p(z), 4, 9, p(z), 8, 1.0, 4, 1.0, None, None, None, p(buf), None, None, p(buf), p(buf),
+                            1 << 30, None) == -1
+    assert lib.scc_dec_step(p(z), 4, 7, p(z), 8, 1.0, 0, 1.0, None, None, None, p(buf), None, None, p(buf), p(buf),
+                            1 << 30, None) == -2
+    assert lib.scc_debug_set_timeline(None) == -2          # production build: the profiling stamps are compiled out
+
+
+def test_dec_step_supported_shapes():
+    from spectrogram_cube_clustering_b200 import ops
+    assert ops.dec_step_supported(9, 8) and ops.dec_step_supported(32, 4) and ops.dec_step_supported(10, 16)
+    assert not ops.dec_step_supported(32, 16) and not ops.dec_step_supported(12, 16) and not ops.dec_step_supported(7, 8)
 
 
 def test_ops_refuse_cpu_tensors():
