@@ -36,8 +36,20 @@ METRIC = "latent points/sec per DEC step (ClusteringLayer fwd+bwd + target distr
 UNIT = "points/s"
 N_PER_GPU, D, K, ALPHA, GAMMA = 1_000_000, 9, 8, 1.0, 1e-3
 N_SETS = 4                      # distinct input/output sets cycled so no step re-finds its data in L2
-GRAPH_STEPS = 16                # consecutive steps captured into one CUDA graph (a multiple of N_SETS)
+GRAPH_STEPS = 20                # consecutive steps captured into one CUDA graph (a multiple of N_SETS; divides the
+                                # driver's --steps 20, so a timed region is whole multi-step graph launches)
 WORKLOAD = "DEC fwd/bwd + target distribution, N=1M latent points per GPU, d=9, K=8, alpha=1 (BASELINE configs[1])"
+
+
+
+
+def workload_config(n_gpus: int) -> dict:
+    """The `config` object both arms print verbatim (same keys, same values) — what differs between the arms
+    (launch mode, parallelism, host) lives under `details`."""
+    return {"workload": WORKLOAD, "n_points_per_gpu": N_PER_GPU, "n_points_total": N_PER_GPU * n_gpus, "d": D, "K": K,
+            "alpha": ALPHA, "gamma": GAMMA, "round_decimals": 5,
+            "l2": f"GPU arm: inputs/outputs rotate over {N_SETS} sets ({N_SETS * 140} MB) > 126 MB L2, so no step "
+                  "re-finds its data in L2; reference arm: host memory"}
 
 
 _JSON_FD = None
@@ -174,8 +186,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_points": r["n"], "d": D, "K": K, "alpha": ALPHA,
-                   "host": "reference CPU path (PyTorch CPU + numpy), no GPU"},
+        "config": workload_config(args.gpus),
+        "details": {"host": "reference CPU path (PyTorch CPU autograd + numpy), no GPU; float64 as models.py:965 runs it",
+                    "n_points_sampled": r["n"]},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -271,7 +284,6 @@ def run_gpu(args):
             ops.dec_assign(s["z"], mu, ALPHA, 5, out_q=s["q"], out_labels=s["labels"], out_stats=s["st1"], push=ex)
             ops.dec_target_kl_grad(s["z"], mu, None, ALPHA, 5, scale, out_p=s["p"], out_dz=s["dz"],
                                    out_stats=s["st2"], pull_f=ex, push=ex)
-            ops.peer_finish(s["st2"], ex)
         else:
             k_assign(s); allreduce(s["st1"]); k_tgrad(s); allreduce(s["st2"])
 
@@ -516,7 +528,6 @@ def run_gpu(args):
             ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"], push=ex)
             ops.dec_target_kl_grad(zd, mud, None, ALPHA, 5, scale, out_p=sd["p"], out_dz=sd["dz"], out_stats=sd["st2"],
                                    pull_f=ex, push=ex)
-            ops.peer_finish(sd["st2"], ex)
         else:
             ops.dec_assign(zd, mud, ALPHA, 5, out_q=sd["q"], out_labels=sd["labels"], out_stats=sd["st1"])
             allreduce(sd["st1"])
@@ -549,12 +560,17 @@ def run_gpu(args):
            "h2d_bytes_per_step": int(zd2[0].numel() * 4 + mud.numel() * 4), "d2h_bytes_per_step": int(res_h.numel() * 8),
            "ms_per_step": e2e_ms, "api": ("ops.dec_step" if one_kernel else "ops.dec_assign + ops.dec_target_kl_grad") + " on a pinned host latent set "
                                          "(upload of step i+1 double-buffered behind step i's kernels); "
-                                         "loss, dmu, f, label-change count read back every step", "loss": loss_h}
+                                         "loss, dmu, f, label-change count (664 B) read back every step; the N-sized results "
+                                         "(q, labels, p, dz) stay on the device for the next kernels — the reference's "
+                                         "batch_eval hands q, labels, z to the host, which this contract does not time",
+           "loss": loss_h}
 
     dbg('e2e done')
     extra = {}
-    if world == 1 and not args.no_extra:
-        extra = extra_benchmarks(torch, ops, synth, dev, hbm_peak)
+    if not args.no_extra:
+        extra = extra_benchmarks(torch, ops, synth, dev, hbm_peak, world, rank, group, exchange)
+        if rank == 0 and world == 1 and not args.no_cpu:
+            extra.update(gmm_cpu_baselines(torch, synth, extra))
     if unfused_extra is not None:
         extra["dec_step_3_kernels"] = unfused_extra
     if two_extra is not None:
@@ -569,9 +585,9 @@ def run_gpu(args):
         parallelism = "single GPU"
     else:
         if one_kernel:
-            how = ("NVLink peer-memory exchange INSIDE the one-kernel step (f: pushed/pulled by the last CTA at the grid "
-                   "barrier between the two passes; gradient statistics: pushed by the kernel's last CTA, collected by a "
-                   "one-CTA finish kernel)")
+            how = ("NVLink peer-memory exchange INSIDE the one-kernel step, flag-in-data (f: pushed/pulled by the last "
+                   "CTA at the grid barrier between the two passes; gradient statistics: pushed/pulled by the kernel's "
+                   "last CTA in its tail) — one launch per step and GPU")
         elif fused_ex:
             how = ("NVLink peer-memory exchange fused into the kernels (push in the producer's last CTA, pull in the "
                    "consumer's prologue)")
@@ -585,9 +601,8 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_points_per_gpu": N_PER_GPU, "n_points_total": n_total, "d": D,
-                       "K": K, "alpha": ALPHA, "gamma": GAMMA, "round_decimals": 5,
-                       "parallelism": parallelism,
+            "config": workload_config(world),
+            "details": {"parallelism": parallelism,
                        "launch": (("one CUDA graph replay per step" if args.single_step_graphs else
                                    f"CUDA graph replays of {GRAPH_STEPS} consecutive steps (rotating over the {N_SETS} input sets), "
                                    "single-step graphs for the remainder")
@@ -596,12 +611,11 @@ def run_gpu(args):
                                             "target + KL-gradient pass)"] if one_kernel else (
                                            ["dec_assign", "dec_target", "dec_kl_grad"] if unfused else
                                            ["dec_assign", "dec_target_kl_grad"]),
-                       "l2": f"inputs/outputs rotate over {N_SETS} sets ({N_SETS * 140} MB) > 126 MB L2",
                        "timing": "CUDA events around the K steps, max over ranks; per-kernel durations from "
                                  "CUDA events around replays of single-kernel graphs over the same rotating sets"},
             "clocks": sampler.summary(), "e2e": e2e,
             "gpu_launches": ((1 if one_kernel else (3 if unfused else 2)) +
-                             (((1 if (fused_ex or one_kernel) else 2) if exchange is not None else 0)
+                             (((0 if (fused_ex or one_kernel) else 2) if exchange is not None else 0)
                               if world > 1 else 0)) * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu, "extra": extra,
@@ -620,111 +634,212 @@ def run_gpu(args):
         os._exit(0)
 
 
-def extra_benchmarks(torch, ops, synth, dev, hbm_peak):
-    """Secondary figures (not the headline): GMM EM iteration and the fused d=32 DEC pass."""
+def fp32_peak_tflops():
+    """148 SMs x 128 FP32 lanes x 2 FLOP x max SM clock: 74.5 TFLOP/s at 1965 MHz."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mhz = float(json.load(f)["sm_max_mhz"])
+    except Exception:
+        mhz = 1965.0
+    return 148 * 128 * 2 * mhz * 1e6 / 1e12
+
+
+def extra_benchmarks(torch, ops, synth, dev, hbm_peak, world=1, rank=0, group=None, exchange=None):
+    """Secondary figures (not the headline) — the other BASELINE.json configs, at EVERY world size:
+      configs[2]  GMM EM fit, 100 iterations, N = 10M TOTAL (strong scaling: N/world points per GPU), d=9 K=16
+      configs[3]  DEC refinement step on the 12.5M-point shard of a GPU (weak scaling: 100M points over 8 GPUs), d=32 K=16
+      configs[4]  DEC_training epoch on synthetic (N,1,4,101) spectrograms, 131072 per GPU
+    Each entry: whole-job points/s (max over ranks of the CUDA-event time), achieved HBM fraction and — for the
+    FP32-bound kernels — achieved fraction of the FP32 CUDA-core peak."""
+    import torch.distributed as dist
+    from spectrogram_cube_clustering_b200.latent_buffer import LatentBuffer
     out = {}
+    fp32_peak = fp32_peak_tflops()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     def timeit(fn, reps, flush=None):
         fn(); fn()
-        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tot = 0.0
         for _ in range(reps):
             if flush is not None:
                 flush.zero_()
+            barrier()
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()
-            tot += e0.elapsed_time(e1)
+            tot += max_over_ranks(e0.elapsed_time(e1))
         return tot / reps
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    def shard(n_total):
+        lo = rank * (n_total // world)
+        return n_total // world if rank < world - 1 else n_total - lo
+
     try:
-        # GMM EM iteration, BASELINE configs[2] shape on one GPU: N=10M d=9 K=16
-        n, d, k = 10_000_000, 9, 16
-        z, _ = synth.latent_points(n, d, k, rank=77, device=dev)
+        # ---- configs[2] shape: one fused EM iteration (statistics kernel + exchange + device finalize)
+        n_total, d, k = 10_000_000, 9, 16
+        n = shard(n_total)
+        z, _ = synth.latent_points(n, d, k, rank=77 + rank, device=dev)
+        buf = LatentBuffer(z, n_total=n_total, group=group, exchange=exchange)
         w0, mu0, cov0 = synth.gmm_initial_state(d, k, dev)
         params, pchol, ctrl = ops.gmm_pack_params(w0, mu0, cov0)
         means, weights, cov = mu0.clone(), w0.clone(), cov0.clone()
         stats = torch.empty(ops.gmm_stat_doubles(k, d), dtype=torch.float64, device=dev)
 
         def em():
-            ops.gmm_em_step(z, k, params, stats=stats, ctrl=ctrl)
-            ops.gmm_finalize(stats, n, means, weights, cov, pchol, params, ctrl, tol=0.0)
+            buf.gmm_em_pass(k, params, stats, ctrl=ctrl)
+            ops.gmm_finalize(stats, n_total, means, weights, cov, pchol, params, ctrl, tol=0.0)
         for _ in range(5):
             em()
         ms = timeit(em, 10)
         flops = 2.0 * k * (d * d + 4 * d)
-        out["gmm_em_iteration"] = {"workload": "fused E+M pass + device finalize, N=10M d=9 K=16 (configs[2] on 1 GPU)",
-                                   "points_per_s": n / (ms * 1e-3), "ms": ms,
-                                   "hbm_gbs": 4 * d * n / (ms * 1e-3) / 1e9, "hbm_frac": 4 * d * n / (ms * 1e-3) / 1e9 / hbm_peak,
-                                   "fp32_tflops_algorithmic": flops * n / (ms * 1e-3) / 1e12,
-                                   "bound": "fp32 FMA issue (SURVEY.md 8d), not HBM"}
-        del z
-        # fused latent-buffer DEC pass at the configs[3] per-GPU shard: N=12.5M d=32 K=16
-        n, d, k = 12_500_000, 32, 16
-        z, mu = synth.latent_points(n, d, k, rank=78, device=dev)
-        st1 = torch.empty(k + 1, dtype=torch.float64, device=dev)
-        st2 = torch.empty(k * d + 2, dtype=torch.float64, device=dev)
-
-        def fused():
-            ops.dec_assign(z, mu, 1.0, 0, want_q=False, want_labels=False, out_stats=st1)
-            ops.dec_kl_grad(z, mu, 1.0, f=st1, scale=1e-3 / n, want_dz=False, out_stats=st2)
-        ms = timeit(fused, 10)
-        out["dec_fused_d32"] = {"workload": "fused latent-buffer DEC step (assign + KL grads, centroid-only), "
-                                            "N=12.5M d=32 K=16 (configs[3] shard of one GPU)",
-                                "points_per_s": n / (ms * 1e-3), "ms": ms, "algorithmic_bytes_per_point": 8 * d,
-                                "hbm_gbs": 8 * d * n / (ms * 1e-3) / 1e9, "hbm_frac": 8 * d * n / (ms * 1e-3) / 1e9 / hbm_peak}
-        del z
-        n, d, k = 100_000_000 // 8, 9, 8
-        z, mu = synth.latent_points(n, d, k, rank=79, device=dev)
-        st1 = torch.empty(k + 1, dtype=torch.float64, device=dev)
-        st2 = torch.empty(k * d + 2, dtype=torch.float64, device=dev)
-        ms = timeit(fused, 10)
-        out["dec_fused_d9"] = {"workload": "fused latent-buffer DEC step (assign + KL grads, centroid-only), N=12.5M d=9 K=8",
-                               "points_per_s": n / (ms * 1e-3), "ms": ms, "algorithmic_bytes_per_point": 8 * d,
-                               "hbm_gbs": 8 * d * n / (ms * 1e-3) / 1e9, "hbm_frac": 8 * d * n / (ms * 1e-3) / 1e9 / hbm_peak}
-        del z
-        # BASELINE configs[2]: full-covariance EM fit, 100 iterations (tol=0), N=10M d=9 K=16, through the
-        # scikit-learn-style front end (device-resident loop, host polls every 25 iterations)
+        tf = flops * n_total / (ms * 1e-3) / 1e12
+        out["gmm_em_iteration"] = {"workload": f"fused E+M pass + exchange + device finalize, N=10M total ({n} per GPU), d=9 K=16 "
+                                               "(configs[2] shape, strong scaling), after 5 iterations",
+                                   "points_per_s": n_total / (ms * 1e-3), "ms": ms,
+                                   "hbm_gbs": 4 * d * n_total / (ms * 1e-3) / 1e9,
+                                   "hbm_frac": 4 * d * n_total / (ms * 1e-3) / 1e9 / (hbm_peak * world),
+                                   "fp32_tflops_algorithmic": tf, "fp32_frac": tf / (fp32_peak * world),
+                                   "bound": "fp32 FMA issue (SURVEY.md 8d: the FMA ceiling is 19.9 G points/s per GPU = 11 % "
+                                            "of HBM), not HBM"}
+        # ---- configs[2]: the whole fit through the scikit-learn-style front end (graph-captured EM iteration,
+        # convergence decided on the device, host polls every 25 iterations)
         from spectrogram_cube_clustering_b200.models import GaussianMixture, DEC_training
         from spectrogram_cube_clustering_b200.networks import DEC
         import warnings
-        n, d, k = 10_000_000, 9, 16
-        z, _ = synth.latent_points(n, d, k, rank=77, device=dev)
-        w0, mu0, cov0 = synth.gmm_initial_state(d, k, "cpu")
-        gm = GaussianMixture(k, max_iter=100, tol=0.0, weights_init=w0.numpy(), means_init=mu0.numpy(),
-                             covariances_init=cov0.numpy(), poll_interval=25)
-        torch.cuda.synchronize()
+        w0c, mu0c, cov0c = synth.gmm_initial_state(d, k, "cpu")
+        gm = GaussianMixture(k, max_iter=100, tol=0.0, weights_init=w0c.numpy(), means_init=mu0c.numpy(),
+                             covariances_init=cov0c.numpy(), poll_interval=25, group=group)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gm.fit(buf)                                    # warm-up fit (graph capture, workspaces)
+            barrier()
+            t0 = time.perf_counter()
+            gm.fit(buf)
+            barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        tf = flops * n_total * gm.n_iter_ / dt / 1e12
+        out["gmm_fit_100_iters"] = {"workload": f"GaussianMixture.fit, 100 EM iterations (tol=0), N=10M total ({n} per GPU), d=9 K=16 "
+                                                "(configs[2]; strong scaling over the GPUs)",
+                                    "seconds": dt, "points_per_s": n_total * gm.n_iter_ / dt, "ms": dt * 1e3 / max(gm.n_iter_, 1),
+                                    "n_iter": gm.n_iter_, "lower_bound": gm.lower_bound_, "graph": True,
+                                    "hbm_frac": 4 * d * n_total * gm.n_iter_ / dt / 1e9 / (hbm_peak * world),
+                                    "fp32_tflops_algorithmic": tf, "fp32_frac": tf / (fp32_peak * world)}
+        del z, buf, gm
+        # ---- configs[3]: fused latent-buffer DEC step on the 12.5M-point shard of every GPU (weak scaling)
+        for name, (d, k) in (("dec_fused_d32", (32, 16)), ("dec_fused_d9", (9, 8))):
+            n = 12_500_000
+            z, mu = synth.latent_points(n, d, k, rank=78 + rank, device=dev)
+            buf = LatentBuffer(z, n_total=n * world, group=group, exchange=exchange)
+            lane = 4 * k * d + 20 * k                       # SURVEY.md 8d: ~4Kd FMA + ~20K other lane-instructions / point
+
+            def fused():
+                buf.dec_step(mu, 1.0, 1e-3, 0)
+            ms = timeit(fused, 10)
+            res = {"workload": f"fused latent-buffer DEC step (assign + KL grads, centroid-only, stats all-reduced), "
+                               f"{n} points per GPU x {world} GPU(s), d={d} K={k}" +
+                               (" (configs[3]: 100M points over 8 GPUs)" if d == 32 else ""),
+                   "points_per_s": n * world / (ms * 1e-3), "ms": ms, "algorithmic_bytes_per_point": 8 * d,
+                   "hbm_gbs": 8 * d * n * world / (ms * 1e-3) / 1e9,
+                   "hbm_frac": 8 * d * n / (ms * 1e-3) / 1e9 / hbm_peak,
+                   "fp32_frac": 2.0 * lane * n / (ms * 1e-3) / 1e12 / fp32_peak}
+            if d == 32:
+                def fused_dz():
+                    buf.dec_step(mu, 1.0, 1e-3, 0, want_dz=True)
+                ms2 = timeit(fused_dz, 5)
+                res["with_dz"] = {"ms": ms2, "points_per_s": n * world / (ms2 * 1e-3), "algorithmic_bytes_per_point": 12 * d,
+                                  "hbm_frac": 12 * d * n / (ms2 * 1e-3) / 1e9 / hbm_peak}
+            out[name] = res
+            del z, buf
+        # ---- configs[4]: one DEC_training epoch on synthetic (N,1,4,101) spectrograms, B=4096, per GPU
+        nspec, bsz = 131072, 4096
+        x = synth.spectrograms(nspec, rank=rank, device=dev)
+        loader = synth.TensorBatches(x, bsz)
+        torch.manual_seed(0)                                # identical replicas on every rank
+        model = DEC(n_clusters=5).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        DEC_training(model, loader, opt, n_epochs=1, gamma=1e-3, tol=0.0, group=group)   # warm-up epoch (cuDNN autotune)
+        barrier()
+        t0 = time.perf_counter()
+        hist = DEC_training(model, loader, opt, n_epochs=1, gamma=1e-3, tol=0.0, group=group)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        out["dec_train_epoch"] = {"workload": f"DEC_training epoch, {nspec} synthetic (1,4,101) spectrograms per GPU x {world} GPU(s), "
+                                              f"B={bsz} per GPU, K=5, encoder/decoder stock torch fp32 (gradients averaged over the "
+                                              "ranks), clustering path fused (configs[4])",
+                                  "seconds": dt, "points_per_s": nspec * world / dt, "ms": dt * 1e3, "hbm_frac": 0.0,
+                                  "loss": hist["loss"][-1] if hist["loss"] else None}
+    except Exception as exc:  # pragma: no cover
+        import traceback
+        out["error"] = repr(exc) + " | " + traceback.format_exc()[-600:]
+    return out
+
+
+def gmm_cpu_baselines(torch, synth, extra):
+    """Reference CPU figures for the metric's GMM half: scikit-learn's `_e_step` + `_m_step` on a
+    bounded sample of the configs[2] shape from the same explicit state, and the whole `models.gmm` call of
+    configs[0] (N=10k, d=9, K=8: KMeans(n_init=100) + EM) — reference formulation on the host cores beside this
+    package's `models.gmm` on the GPU."""
+    import warnings
+    import numpy as np
+    out = {}
+    cores = len(os.sched_getaffinity(0))
+    try:
+        from sklearn.mixture import GaussianMixture as SkGM
+        from sklearn.cluster import KMeans as SkKM
+        n, d, k = 200_000, 9, 16
+        z, _ = synth.latent_points(n, d, k, rank=77)
+        X = z.numpy().astype(np.float64)                    # the reference runs float64 (models.py:66-71, 965)
+        w0, mu0, cov0 = [t.numpy() for t in synth.gmm_initial_state(d, k, "cpu")]
+        sk = SkGM(k, weights_init=w0, means_init=mu0, precisions_init=np.linalg.inv(cov0), max_iter=1, tol=0.0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sk.fit(X)                                       # sets the explicit state + warm-up
+        best = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            _, log_resp = sk._e_step(X)
+            sk._m_step(X, log_resp)
+            best = min(best, time.perf_counter() - t0)
+        ours = extra.get("gmm_em_iteration", {}).get("points_per_s")
+        out["gmm_em_iteration_cpu"] = {"workload": f"scikit-learn _e_step + _m_step, float64, {n} points (sample of configs[2]: d=9 K=16)",
+                                       "points_per_s": n / best, "seconds": best, "cores": cores, "kind": "reference (scikit-learn)",
+                                       "gpu_over_cpu": (ours / (n / best)) if ours else None}
+        # configs[0]: full models.gmm, reference formulation (models.py:365-413) vs this package
+        n, d, k = 10_000, 9, 8
+        z, _ = synth.latent_points(n, d, k, rank=5)
+        Xc = z.numpy().astype(np.float64)
         t0 = time.perf_counter()
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            gm.fit(z)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        out["gmm_fit_100_iters"] = {"workload": "GaussianMixture.fit, 100 EM iterations, N=10M d=9 K=16 (configs[2] on 1 GPU)",
-                                    "seconds": dt, "points_per_s": n * gm.n_iter_ / dt, "ms": dt * 1e3 / max(gm.n_iter_, 1),
-                                    "n_iter": gm.n_iter_, "lower_bound": gm.lower_bound_,
-                                    "hbm_frac": 4 * d * n * gm.n_iter_ / dt / 1e9 / hbm_peak}
-        del z, gm
-        # BASELINE configs[4]: one DEC_training epoch on synthetic (N,1,4,101) spectrograms, B=4096
-        nspec, bsz = 131072, 4096
-        x = synth.spectrograms(nspec, device=dev)
-        loader = synth.TensorBatches(x, bsz)
-        model = DEC(n_clusters=5).to(dev)
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-        DEC_training(model, loader, opt, n_epochs=1, gamma=1e-3, tol=0.0)          # warm-up epoch (cuDNN autotune)
+            km = SkKM(n_clusters=k, max_iter=1000, n_init=100, random_state=2009).fit(Xc)
+            _, counts = np.unique(km.labels_, return_counts=True)
+            SkGM(n_components=k, max_iter=1000, n_init=1, weights_init=counts / n, means_init=km.cluster_centers_).fit_predict(Xc)
+        t_ref = time.perf_counter() - t0
+        from spectrogram_cube_clustering_b200.models import gmm
+        gmm(z.numpy(), k)                                   # warm-up (workspaces)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        hist = DEC_training(model, loader, opt, n_epochs=1, gamma=1e-3, tol=0.0)
+        gmm(z.numpy(), k)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        out["dec_train_epoch"] = {"workload": f"DEC_training epoch, {nspec} synthetic (1,4,101) spectrograms, B={bsz}, K=5, "
-                                              "encoder/decoder stock torch fp32, clustering path fused (configs[4] on 1 GPU)",
-                                  "seconds": dt, "points_per_s": nspec / dt, "ms": dt * 1e3, "hbm_frac": 0.0,
-                                  "loss": hist["loss"][-1] if hist["loss"] else None}
+        t_gpu = time.perf_counter() - t0
+        out["gmm_c1"] = {"workload": "models.gmm(z, 8): KMeans(n_init=100, max_iter=1000) seeding + full-covariance EM, "
+                                     "N=10k d=9 K=8 (configs[0]); host array in, labels + centroids out",
+                         "seconds": t_gpu, "reference_seconds": t_ref, "reference_cores": cores,
+                         "reference": "scikit-learn KMeans + GaussianMixture exactly as Cluster/models.py:386-411 calls them",
+                         "speedup": t_ref / t_gpu}
     except Exception as exc:  # pragma: no cover
-        out["error"] = repr(exc)
-    del flush
+        out["gmm_cpu_error"] = repr(exc)
     return out
 
 

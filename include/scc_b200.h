@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SCC_ABI_VERSION 1
+#define SCC_ABI_VERSION 2
 #define SCC_MAX_D 32
 #define SCC_MAX_K 16
 
@@ -160,6 +160,36 @@ int scc_kmeans_step(const float* z, int64_t n, int d,
                     int32_t* labels, float* mindist, double* stats,
                     void* workspace, size_t workspace_bytes, scc_stream_t stream);
 
+/*
+ * Batched Lloyd iterations — the `n_init` restarts of KMeans(n_clusters, n_init=100, max_iter=1000)
+ * (Cluster/models.py:386-394, 565-572) advance TOGETHER: one launch scans z against restarts x K centres
+ * (grid.y = restart), then scc_kmeans_batch_update moves every restart's centres and decides its
+ * convergence on the device; the host polls the `done` flags every few iterations instead of once per
+ * restart and iteration.
+ *   centers [restarts, K, d] float32;  stats [restarts, K*d + 2 + K] float64 (layout of scc_kmeans_step)
+ *   done    [restarts] uint8 or NULL: restarts whose flag is set are skipped (their stats are left untouched)
+ *   labels  [restarts, n] int32 or NULL;  mindist [restarts, n] float32 or NULL (k-means++ sampling)
+ *   workspace: scc_kmeans_batch_workspace_bytes(d, K, restarts) bytes, zeroed once (scc_workspace_init)
+ * scc_kmeans_batch_update: c_j += shift_j / count_j (an empty cluster keeps its centre), n_iter += 1,
+ *   inertia[r] = stats[r][0], done[r] = 1 once sum_j ||shift_j / count_j||^2 <= shift_tol
+ *   (scikit-learn's stop rule: shift_tol = tol * mean feature variance).  n_iter, inertia nullable.
+ */
+size_t scc_kmeans_batch_workspace_bytes(int d, int K, int restarts);
+int scc_kmeans_batch_step(const float* z, int64_t n, int d, const float* centers, int K, int restarts,
+                          const unsigned char* done, int32_t* labels, float* mindist, double* stats,
+                          void* workspace, size_t workspace_bytes, scc_stream_t stream);
+int scc_kmeans_batch_update(float* centers, const double* stats, int d, int K, int restarts, double shift_tol,
+                            unsigned char* done, int32_t* n_iter, double* inertia, scc_stream_t stream);
+
+/*
+ * Distance scan  D_ij = (sum_c |z_ic - mu_jc|^p)^(1/p),  out [n, K] float32 — the scan behind
+ * utils.fractional_distance / utils.distance_matrix (Cluster/utils.py:866-869, 635-643) that the
+ * reference's CDF/PDF/inertia analyses repeat per centroid (plotting.py:189,243,352; p = 2 gives the
+ * Euclidean distances of utils.measure_class_inertia, utils.py:1024-1029).  Any d in [1,32], K in [1,16], p > 0.
+ */
+int scc_dec_distances(const float* z, int64_t n, int d, const float* mu, int K, float p, float* out,
+                      scc_stream_t stream);
+
 /* ------------------------------------------------------------------------- *
  * GMM stage (full covariance)
  * ------------------------------------------------------------------------- */
@@ -255,12 +285,15 @@ size_t scc_peer_window_bytes(int max_len);
 
 /*
  * Fused form: the exchange rides on the kernels that produce / consume the statistics, so a sharded
- * DEC step is  assign_ex(push) -> target_ex(pull) -> kl_grad_ex(push) -> peer_finish  — four launches,
- * no separate collective.  `push`: the LAST thread block of the statistics kernel ships the reduced
- * vector to every rank's window and raises the sequence flag (peer stores over NVLink in the same
- * kernel as the compute).  `pull`: the consuming kernel waits for the world's flags in its prologue
- * and sums the slots in rank order.  Every push must be matched by exactly one pull (target_ex /
- * kl_grad_ex with pull_f / scc_peer_finish) on every rank before the next-but-one push.
+ * DEC step is  assign_ex(push) -> target_kl_grad(pull_f, push)  — two launches, no separate collective.
+ * `push` on scc_dec_assign_ex: the LAST thread block of the kernel ships the reduced vector to every rank's
+ * window (peer stores over NVLink in the same kernel as the compute; vectors of <= 1024 doubles travel
+ * flag-in-data, longer ones behind a system fence + sequence flag); it must be matched by exactly one pull
+ * on every rank (target_ex / kl_grad_ex / target_kl_grad with pull_f, or scc_peer_finish) before the
+ * next-but-one push.  `pull`: the consuming kernel waits for the world's vectors in its prologue and sums
+ * them in rank order.  `push` on the GRADIENT kernels (scc_dec_kl_grad_ex, scc_dec_target_kl_grad,
+ * scc_dec_step_ex) is a complete all-reduce: the last thread block pushes, waits for the world and overwrites
+ * `stats` with the rank-ordered sum before the kernel ends.
  */
 typedef struct scc_exchange {
     void* const* windows;   /* DEVICE array of `world` window pointers (see scc_peer_allreduce) */
@@ -307,11 +340,12 @@ int scc_dec_step(const float* z, int64_t n, int d, const float* mu, int K, float
                  float scale, float* q, int32_t* labels, const int32_t* labels_prev, double* f_stats,
                  float* p_out, float* dz, double* stats, void* workspace, size_t workspace_bytes,
                  scc_stream_t stream);
-/* Multi-GPU form: the all-reduce of f over the GPUs runs INSIDE the kernel, between its two passes — the last
- * CTA to reach the grid barrier pushes this GPU's f to every rank's exchange window (NVLink peer stores), waits
- * for the world's vectors and releases the other CTAs with the rank-ordered sum; the kernel's last CTA pushes
- * the final statistics, which scc_peer_finish(stats, K*d+2, ex) then collects.  scale = gamma / N_total;
- * f_stats receives the all-reduced f.  Every rank must launch it (an empty shard, n == 0, included). */
+/* Multi-GPU form: BOTH all-reduces run INSIDE the kernel — the last CTA to reach the grid barrier between the
+ * two passes pushes this GPU's f to every rank's exchange window (NVLink peer stores, flag-in-data), waits for
+ * the world's vectors and releases the other CTAs with the rank-ordered sum; the kernel's last CTA does the
+ * same with the final statistics, so `stats` holds the world's loss / dL/dmu when the kernel ends (one launch
+ * per step and GPU, no separate collective).  scale = gamma / N_total; f_stats receives the all-reduced f.
+ * Every rank must launch it (an empty shard, n == 0, included). */
 int scc_dec_step_ex(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
                     float scale, float* q, int32_t* labels, const int32_t* labels_prev, double* f_stats,
                     float* p_out, float* dz, double* stats, void* workspace, size_t workspace_bytes,

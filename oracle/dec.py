@@ -50,10 +50,11 @@ def column_sums(q):
     return np.sum(np.asarray(q, dtype=np.float64), axis=0)
 
 
-def target_distribution(q, round_to=5):
-    """models.py:1320-1322.  ``round_to=None`` gives the unrounded p."""
+def target_distribution(q, round_to=5, f=None):
+    """models.py:1320-1322.  ``round_to=None`` gives the unrounded p.  ``f``: column sums of the WHOLE
+    q when only a row block is passed (chunked evaluation of large sets); default = np.sum(q, axis=0)."""
     q = np.asarray(q, dtype=np.float64)
-    p = q ** 2 / np.sum(q, axis=0)                               # :1320
+    p = q ** 2 / (np.sum(q, axis=0) if f is None else f)         # :1320
     p = np.transpose(np.transpose(p) / np.sum(p, axis=1))        # :1321
     return p if round_to is None else np.round(p, round_to)      # :1322
 
@@ -119,6 +120,25 @@ def delta_label(labels, labels_prev):
     """models.py:1098-1099."""
     labels = np.asarray(labels)
     return np.sum(labels != np.asarray(labels_prev)).astype(np.float32) / labels.shape[0]
+
+
+def dec_step_chunked(z, mu, alpha=1.0, gamma=1e-3, round_to=5, chunk=100_000):
+    """:func:`dec_step` for sets too large for the [N, K, d] temporaries of the reference formulation
+    (BASELINE sizes: 1M points): the same functions applied to row blocks, with the one global
+    quantity — the column sums f — accumulated over all blocks first.  Same outputs as dec_step."""
+    z = np.asarray(z)
+    n = z.shape[0]
+    blocks = [(s, min(s + chunk, n)) for s in range(0, n, chunk)]
+    q = np.concatenate([soft_assign(z[a:b], mu, alpha) for a, b in blocks])
+    labels = labels_from_q(q)
+    q_r = q if round_to is None else round_decimals(q, round_to)
+    f = column_sums(q_r)
+    p = np.concatenate([target_distribution(q_r[a:b], round_to, f=f) for a, b in blocks])
+    loss, dmu, dz = 0.0, 0.0, []
+    for a, b in blocks:
+        l, g, m = kl_grads(z[a:b], mu, p[a:b], alpha, gamma / n)
+        loss += l; dmu = dmu + m; dz.append(g)
+    return dict(q=q, q_rounded=q_r, labels=labels, f=f, p=p, loss=loss, dz=np.concatenate(dz), dmu=dmu)
 
 
 def dec_step(z, mu, alpha=1.0, gamma=1e-3, round_to=5):

@@ -66,6 +66,12 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "scc_kmeans_step": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_size_t, c_void_p]),
+    "scc_kmeans_batch_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "scc_kmeans_batch_step": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scc_kmeans_batch_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    "scc_dec_distances": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "scc_dec_assign_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "scc_dec_target_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

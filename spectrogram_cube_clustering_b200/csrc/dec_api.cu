@@ -171,7 +171,7 @@ static void fill_exchange(DecArgs& a, const ExchangeDesc* push, int do_push, con
     if (!e) return;
     a.ex_windows = reinterpret_cast<unsigned char* const*>(e->windows);
     a.ex_rank = e->rank; a.ex_world = e->world; a.ex_max_len = e->max_len;
-    a.ex_push = (push && push->windows && do_push) ? 1 : 0;
+    a.ex_push = (push && push->windows) ? do_push : 0;
     a.ex_pull_f = (pull_f && pull_f->windows) ? 1 : 0;
 }
 
@@ -225,14 +225,15 @@ int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float 
     if (dz && (reinterpret_cast<uintptr_t>(dz) & 15u)) return SCC_ERR_MISALIGNED;
     if (n == 0) {
         SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (K * d + 2), st));
-        if (push && push->windows) return peer_push_only(stats, K * d + 2, push->windows, push->rank, push->world, push->max_len, st);
+        if (push && push->windows)      // an empty shard still takes part in the (in-kernel) all-reduce
+            return peer_allreduce(stats, K * d + 2, stats, push->windows, push->rank, push->world, push->max_len, st);
         return SCC_OK;
     }
     DecArgs a{};
     a.z = z; a.n = n; a.mu = mu; a.K = K; a.alpha = alpha; a.round5 = round_decimals == 5;
     a.p = p; a.p_out = p_out; a.f_cols = f_cols; a.scale = scale; a.dz = dz; a.stats = stats;
     fill_reduction(a, ws);
-    fill_exchange(a, push, 1, p ? nullptr : pull_f);
+    fill_exchange(a, push, /*push + collect in the kernel's tail=*/2, p ? nullptr : pull_f);
     return dec_grad_dispatch(a, d, p ? MODE_KL : MODE_KLF, st);
 }
 
@@ -257,7 +258,7 @@ int dec_step(const float* z, int64_t n, int d, const float* mu, int K, float alp
     a.q = q; a.labels = labels; a.labels_prev = labels_prev; a.f_out = f_stats;
     a.p_out = p_out; a.scale = scale; a.dz = dz; a.stats = stats;
     fill_reduction(a, ws);
-    fill_exchange(a, ex, /*push the final statistics=*/1, nullptr);
+    fill_exchange(a, ex, /*all-reduce the final statistics in the kernel's tail=*/2, nullptr);
     return dec_grad_dispatch(a, d, MODE_STEP, st);
 }
 
@@ -274,6 +275,125 @@ int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float
     a.grad_q = grad_q; a.scale = 1.f; a.dz = dz; a.stats = stats;
     fill_reduction(a, ws);
     return dec_grad_dispatch(a, d, MODE_GENERIC, st);
+}
+
+// ---------------------------------------------------------------------------
+// Batched Lloyd iterations: R restarts of KMeans(n_init=R) advance together — one launch scans z against
+// R x K centres (grid.y = restart), a second tiny launch moves the centres and decides convergence per
+// restart on the device (sklearn: total squared centre shift <= tol * mean feature variance).
+// ---------------------------------------------------------------------------
+static size_t kmeans_batch_header(int R) { return ((size_t)R * 2 * sizeof(unsigned int) + 255) & ~(size_t)255; }
+
+size_t kmeans_batch_workspace_bytes(int d, int K, int R) {
+    if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K || R < 1) return 0;
+    const size_t sp = (size_t)((K * d + 2 + K + 1) & ~1);
+    return kmeans_batch_header(R) + sizeof(double) * (size_t)R * kBatchGridX * sp;
+}
+
+int kmeans_batch_step(const float* z, int64_t n, int d, const float* centers, int K, int R, const unsigned char* done,
+                      int32_t* labels, float* mindist, double* stats, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if ((!z && n > 0) || !centers || !stats || n < 0 || R < 1 || R > 65535) return SCC_ERR_INVALID;
+    if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return SCC_ERR_INVALID;
+    if (!dec_supported(d, K)) return SCC_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(z) & 15u) != 0) return SCC_ERR_MISALIGNED;
+    if (!ws || ws_bytes < kmeans_batch_workspace_bytes(d, K, R)) return SCC_ERR_WORKSPACE;
+    if (n == 0) { SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)R * (K * d + 2 + K), st)); return SCC_OK; }
+    DecArgs a{};
+    a.z = z; a.n = n; a.mu = centers; a.K = K; a.alpha = 1.0f; a.scale = 1.f;
+    a.labels = labels; a.mindist = mindist; a.stats = stats;
+    a.batch = R; a.batch_done = done;
+    a.counter = reinterpret_cast<unsigned int*>(ws);
+    a.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + kmeans_batch_header(R));
+    a.timeline = nullptr;
+    return dec_grad_dispatch(a, d, MODE_KMEANS, st);
+}
+
+__global__ void __launch_bounds__(128)
+kmeans_batch_update_kernel(float* __restrict__ centers, const double* __restrict__ stats, int d, int K, double thresh,
+                           unsigned char* __restrict__ done, int32_t* __restrict__ n_iter, double* __restrict__ inertia) {
+    const int r = blockIdx.x;
+    if (done[r]) return;
+    __shared__ double red[128];
+    const int S = K * d + 2 + K;
+    const double* st = stats + (size_t)r * S;
+    float* c = centers + (size_t)r * K * d;
+    double sh = 0.0;
+    for (int o = threadIdx.x; o < K * d; o += blockDim.x) {
+        const double cnt = st[2 + K * d + o / d];
+        const double step = cnt > 0.0 ? st[2 + o] / cnt : 0.0;      // an empty cluster keeps its centre
+        c[o] = (float)((double)c[o] + step);
+        sh += step * step;
+    }
+    red[threadIdx.x] = sh;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int t = 0; t < (int)blockDim.x; ++t) tot += red[t];
+        if (inertia) inertia[r] = st[0];                             // inertia of the centres the scan used
+        if (n_iter) n_iter[r] += 1;
+        if (tot <= thresh) done[r] = 1;
+    }
+}
+
+int kmeans_batch_update(float* centers, const double* stats, int d, int K, int R, double thresh, unsigned char* done,
+                        int32_t* n_iter, double* inertia, cudaStream_t st) {
+    if (!centers || !stats || !done || R < 1) return SCC_ERR_INVALID;
+    if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return SCC_ERR_INVALID;
+    kmeans_batch_update_kernel<<<R, 128, 0, st>>>(centers, stats, d, K, thresh, done, n_iter, inertia);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// dec_distances: D_ij = (sum_c |z_ic - mu_jc|^p)^(1/p) for every point and centroid — the scan behind
+// utils.fractional_distance / distance_matrix (utils.py:866-869, 635-643) and, with p = 2 squared and summed,
+// utils.measure_class_inertia (utils.py:1024-1029).  HBM-bound: reads z once, writes [n, K].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dec_distances_kernel(const float* __restrict__ z, int64_t n, int d, const float* __restrict__ mu, int K, float p,
+                     float* __restrict__ out) {
+    extern __shared__ float dist_smem[];
+    float* mu_s = dist_smem;                       // [K*d]
+    float* rows = dist_smem + K * d;               // [256][d+1] (odd-ish stride: conflict-free row reads)
+    const int ld = d + 1;
+    for (int i = threadIdx.x; i < K * d; i += 256) mu_s[i] = mu[i];
+    const float inv_p = 1.f / p;
+    const bool p2 = (p == 2.f), p1 = (p == 1.f);
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += (int64_t)gridDim.x * 256) {
+        const int np = (int)((n - base < 256) ? (n - base) : 256);
+        __syncthreads();
+        for (int f = threadIdx.x; f < np * d; f += 256) {
+            const int row = f / d, c = f - row * d;
+            rows[row * ld + c] = ldg_stream(z + base * d + f);
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < np) {
+            const float* x = rows + threadIdx.x * ld;
+            for (int j = 0; j < K; ++j) {
+                float acc = 0.f;
+                for (int c = 0; c < d; ++c) {
+                    const float df = fabsf(x[c] - mu_s[j * d + c]);
+                    acc += p2 ? df * df : (p1 ? df : powf(df, p));
+                }
+                out[(base + threadIdx.x) * K + j] = p2 ? sqrtf(acc) : (p1 ? acc : powf(acc, inv_p));
+            }
+        }
+    }
+}
+
+int dec_distances(const float* z, int64_t n, int d, const float* mu, int K, float p, float* out, cudaStream_t st) {
+    if ((!z && n > 0) || !mu || (!out && n > 0) || n < 0 || !(p > 0.f)) return SCC_ERR_INVALID;
+    if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return SCC_ERR_INVALID;
+    if (n == 0) return SCC_OK;
+    int dev = 0, sms = 0;
+    SCC_CUDA(cudaGetDevice(&dev));
+    SCC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t grid = (n + 255) / 256;
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    const size_t smem = sizeof(float) * ((size_t)K * d + 256 * (size_t)(d + 1));
+    dec_distances_kernel<<<(unsigned)grid, 256, smem, st>>>(z, n, d, mu, K, p, out);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
 }
 
 int kmeans_step(const float* z, int64_t n, int d, const float* centers, int K, int32_t* labels, float* mindist,

@@ -21,6 +21,7 @@ namespace scc {
 
 constexpr int kDecThreads = 256;
 constexpr int kDecTile = 256;
+constexpr int kBatchGridX = 296;       // grid.x bound of a batched (grid.y = restarts) Lloyd launch
 
 // doubles of reduction scratch for an NV-long statistics vector: cta_reduce needs
 // [num_warps][round_up(NV, 32)], grid_publish needs 2 * kDecThreads
@@ -502,6 +503,31 @@ __device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, flo
 }
 
 // ---------------------------------------------------------------------------
+// Batched Lloyd step (MODE_KMEANS only): gridDim.y independent restarts scan the SAME z against their own
+// centres (KMeans(n_init=100), models.py:386-394).  blockIdx.y selects the restart: centres, statistics,
+// partial slots, ticket counter and the optional per-point outputs are offset; restarts whose `done` flag is
+// set (converged earlier) return at once.  Everything else in the kernel is unchanged: it only ever uses
+// blockIdx.x / gridDim.x.  Returns false when this CTA has nothing to do.
+// ---------------------------------------------------------------------------
+template <int MODE, int D>
+__device__ __forceinline__ bool batch_view(DecArgs& a, int K) {
+    if constexpr (MODE == MODE_KMEANS) {
+        if (a.batch > 0) {
+            const int r = blockIdx.y;
+            if (a.batch_done && a.batch_done[r]) return false;
+            const int S = K * D + 2 + K;
+            a.mu += (size_t)r * K * D;
+            a.stats += (size_t)r * S;
+            a.partials += (size_t)r * gridDim.x * ((S + 1) & ~1);
+            a.counter += 2 * r;
+            if (a.labels) a.labels += (size_t)r * a.n;
+            if (a.mindist) a.mindist += (size_t)r * a.n;
+        }
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------
 // dec_grad, REG variant.  Per-thread accumulators: loss, sum s, W_j = sum_i c_ij,
 // B_jc = sum_i c_ij (z_ic - c0_c);  dmu_jc = -cs (B_jc - W_j (mu_jc - c0_c)).
 // For odd D the pad lane of the last float2 pair of the centred point is the constant 1, so W_j
@@ -510,7 +536,7 @@ __device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, flo
 // ---------------------------------------------------------------------------
 template <int D, int KP, bool EXACT, bool ALPHA1, int MODE>
 __global__ void __launch_bounds__(kDecThreads, (2 + KP + 2 * KP * Pairs<D>::N) <= 100 ? 2 : 1)
-dec_grad_reg_kernel(const DecArgs a) {
+dec_grad_reg_kernel(const DecArgs a_in) {
     constexpr int S = dec_stages<D>();
     constexpr int DP2 = Pairs<D>::N;
     constexpr bool kPadW = (D & 1) != 0;
@@ -534,11 +560,14 @@ dec_grad_reg_kernel(const DecArgs a) {
     double* cta_stats = scratch + reduce_scratch(NV);                        // [NV]  (>= K*D + 2 + K)
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NV);            // [NW][S]
 
-    const int K = EXACT ? KP : a.K;
-    const float cs = grad_fold_scale<MODE>(a.scale, a.alpha);
+    const int K = EXACT ? KP : a_in.K;
     Ring ring;
-    ring.init(ring_buf, bars, a.z, a.n);
+    ring.init(ring_buf, bars, a_in.z, a_in.n);
     pdl_wait();                         // no global access before this point (see scc_common.cuh)
+    DecArgs a_view = a_in;
+    if (!batch_view<MODE, D>(a_view, K)) return;
+    const DecArgs& a = (MODE == MODE_KMEANS) ? a_view : a_in;
+    const float cs = grad_fold_scale<MODE>(a.scale, a.alpha);
     SCC_TL(a.timeline, 0);
     const int G = gridDim.x;
 #pragma unroll
@@ -727,7 +756,7 @@ dec_grad_reg_kernel(const DecArgs a) {
     __syncthreads();
     const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
     const bool last = grid_publish<kDecThreads, 25>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials,
-                                                    a.counter, a.stats, scratch, &push);
+                                                    a.counter, a.stats, scratch, &push, a.ex_push);
     if (MODE == MODE_STEP && last && threadIdx.x == 0) a.counter[1] = 0u;    // every CTA is past the pass-1 barrier
     SCC_TL(a.timeline, 5);
 }
@@ -741,7 +770,7 @@ dec_grad_reg_kernel(const DecArgs a) {
 // ---------------------------------------------------------------------------
 template <int D, int KP, bool EXACT, bool ALPHA1, int MODE>
 __global__ void __launch_bounds__(kDecThreads)
-dec_grad_tiled_kernel(const DecArgs a) {
+dec_grad_tiled_kernel(const DecArgs a_in) {
     static_assert(D % 4 == 0 && KP % 4 == 0, "tiled variant needs 4-aligned shapes");
     constexpr int S = 2;
     using Ring = ZRing<D, kDecTile, S, kDecThreads>;
@@ -767,12 +796,15 @@ dec_grad_tiled_kernel(const DecArgs a) {
     double* cta_stats = small_s + NSM;                       // [NS + KP]
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NS + KP);
 
-    const int K = EXACT ? KP : a.K;
-    const float cs = grad_fold_scale<MODE>(a.scale, a.alpha);
+    const int K = EXACT ? KP : a_in.K;
     Ring ring;
-    ring.init(ring_buf, bars, a.z, a.n);
+    ring.init(ring_buf, bars, a_in.z, a_in.n);
     __syncthreads();
     pdl_wait();                         // no global access before this point (see scc_common.cuh)
+    DecArgs a_view = a_in;
+    if (!batch_view<MODE, D>(a_view, K)) return;
+    const DecArgs& a = (MODE == MODE_KMEANS) ? a_view : a_in;
+    const float cs = grad_fold_scale<MODE>(a.scale, a.alpha);
     const int G = gridDim.x;
 #pragma unroll
     for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
@@ -891,7 +923,7 @@ dec_grad_tiled_kernel(const DecArgs a) {
     __syncthreads();
     const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
     grid_publish<kDecThreads>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials, a.counter, a.stats,
-                              scratch, &push);
+                              scratch, &push, a.ex_push);
 }
 
 // ---------------------------------------------------------------------------
@@ -939,9 +971,10 @@ static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t 
     if (grid < 0) return (int)grid;
     if (grid > kMaxDecGrid) grid = kMaxDecGrid;
     if (grid > num_tiles) grid = num_tiles;
+    if (args.batch > 0 && grid > kBatchGridX) grid = kBatchGridX;    // R restarts share the machine (workspace bound)
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
+    cfg.gridDim = dim3((unsigned)grid, args.batch > 0 ? (unsigned)args.batch : 1u);
     cfg.blockDim = dim3(kDecThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;

@@ -54,7 +54,9 @@ int persistent_grid(const void* kernel, int threads, size_t smem, int max_ctas_p
 
 size_t workspace_bytes(int d, int K) {
     if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return 0;
-    const size_t dec = (size_t)kMaxDecGrid * (size_t)((K * d + 2 + K + 1) & ~1);   // even slot stride (grid_publish)
+    // per CTA: the tail's slot (grid_publish, even stride; MODE_KMEANS appends K counts) and — one-kernel step —
+    // the pass-1 slot behind all tail slots; then the world's f vector behind those (grid_barrier_sum)
+    const size_t dec = (size_t)kMaxDecGrid * (size_t)(((K * d + 2 + K + 1) & ~1) + ((K + 2) & ~1)) + (size_t)(K + 2);
     const size_t gmm = (size_t)kMaxGmmGrid * (size_t)SCC_GMM_STAT_DOUBLES(K, d);
     return kWorkspaceHeader + sizeof(double) * (dec > gmm ? dec : gmm) + (size_t)(64 << 10);   // + staged GMM params
 }
@@ -134,6 +136,28 @@ int scc_kmeans_step(const float* z, int64_t n, int d, const float* centers, int 
                     double* stats, void* workspace, size_t workspace_bytes, scc_stream_t stream) {
     return scc::kmeans_step(z, n, d, centers, K, labels, mindist, stats, workspace, workspace_bytes,
                             (cudaStream_t)stream);
+}
+
+size_t scc_kmeans_batch_workspace_bytes(int d, int K, int restarts) {
+    return scc::kmeans_batch_workspace_bytes(d, K, restarts);
+}
+
+int scc_kmeans_batch_step(const float* z, int64_t n, int d, const float* centers, int K, int restarts,
+                          const unsigned char* done, int32_t* labels, float* mindist, double* stats, void* workspace,
+                          size_t workspace_bytes, scc_stream_t stream) {
+    return scc::kmeans_batch_step(z, n, d, centers, K, restarts, done, labels, mindist, stats, workspace,
+                                  workspace_bytes, (cudaStream_t)stream);
+}
+
+int scc_kmeans_batch_update(float* centers, const double* stats, int d, int K, int restarts, double shift_tol,
+                            unsigned char* done, int32_t* n_iter, double* inertia, scc_stream_t stream) {
+    return scc::kmeans_batch_update(centers, stats, d, K, restarts, shift_tol, done, n_iter, inertia,
+                                    (cudaStream_t)stream);
+}
+
+int scc_dec_distances(const float* z, int64_t n, int d, const float* mu, int K, float p, float* out,
+                      scc_stream_t stream) {
+    return scc::dec_distances(z, n, d, mu, K, p, out, (cudaStream_t)stream);
 }
 
 static const scc::ExchangeDesc* as_desc(const scc_exchange* e, scc::ExchangeDesc* tmp) {

@@ -392,11 +392,23 @@ __device__ __forceinline__ void warp_copy_rows_out(const float* __restrict__ src
 }
 
 // ----------------------------------------------------------------------------
-// Peer-memory exchange window (see peer_exchange.cu): header {seq, flags[2][16]} then
-// slots[2][16][max_len] float64.  `push` runs in the LAST CTA of a statistics kernel (fused into
-// its tail), `pull` in the prologue of the kernel that consumes the all-reduced vector.
+// Peer-memory exchange window (see peer_exchange.cu).  Layout, identical on every rank:
+//   [0, 512)            header {seq, flags[2][16]}
+//   fence/flag slots    double [2 parity][16 src rank][max_len]          (vectors longer than kPeerLLMax)
+//   LL cells            uint64 [2 parity][16 src rank][2 * ll_len]       (ll_len = min(max_len, kPeerLLMax))
+// Short vectors (every DEC statistic: K+1 and K*d+2 doubles) travel "flag in data" (LL): each double is
+// shipped as two naturally aligned 8-byte words {32 data bits, 32-bit sequence number}, written with plain
+// relaxed system-scope stores (an aligned 8-byte scalar store is single-copy atomic, also over NVLink).  The
+// receiver polls the words themselves until they carry the sequence number of this exchange: no
+// __threadfence_system, no separate flag round trip.  Cells are double-buffered by sequence parity (a rank
+// can be at most one exchange ahead of the slowest: to start exchange n+2 it needs everybody's n+1 data,
+// which a rank only sends after it has consumed exchange n), and a stale cell carries seq - 2.
+// Long vectors (GMM moments) keep the bandwidth-friendlier fence + flag protocol.
+// `push` runs in ONE CTA (the last CTA of a statistics kernel, or a one-CTA exchange kernel); `pull` in
+// the same CTA right after it (complete all-reduce inside the kernel) or in every CTA of the consumer.
 // ----------------------------------------------------------------------------
 constexpr int kPeerMaxWorld = 16;
+constexpr int kPeerLLMax = 1024;
 constexpr size_t kPeerHeaderBytes = 512;
 struct PeerHeader {
     unsigned int seq;
@@ -408,6 +420,11 @@ struct PeerCtx {                    // by value inside kernel argument structs
     int rank, world, max_len;
 };
 
+__host__ __device__ __forceinline__ int peer_ll_len(int max_len) { return max_len < kPeerLLMax ? max_len : kPeerLLMax; }
+__host__ __device__ __forceinline__ size_t peer_ll_offset(int max_len) {
+    return kPeerHeaderBytes + sizeof(double) * 2 * kPeerMaxWorld * (size_t)max_len;
+}
+
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -416,38 +433,102 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ double* peer_slot(unsigned char* window, int parity, int src_rank, int max_len) {
     return reinterpret_cast<double*>(window + kPeerHeaderBytes) + ((size_t)parity * kPeerMaxWorld + src_rank) * max_len;
 }
-
-// All threads of ONE CTA: push vals[0..len) (thread tid holds element tid, len <= blockDim) to every
-// rank's window and publish the sequence flag.  Advances the local sequence number.
-__device__ __forceinline__ void peer_push(const PeerCtx& ex, double my_val, int len) {
-    PeerHeader* me = reinterpret_cast<PeerHeader*>(ex.windows[ex.rank]);
-    const unsigned int seq = me->seq + 1u;
-    const int parity = seq & 1u;
-    if ((int)threadIdx.x < len)
-        for (int r = 0; r < ex.world; ++r) peer_slot(ex.windows[r], parity, ex.rank, ex.max_len)[threadIdx.x] = my_val;
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < ex.world)
-        st_release_sys(&reinterpret_cast<PeerHeader*>(ex.windows[threadIdx.x])->flags[parity][ex.rank], seq);
-    if (threadIdx.x == 0) me->seq = seq;
+__device__ __forceinline__ unsigned long long* peer_ll_slot(unsigned char* window, int parity, int src_rank, int max_len) {
+    return reinterpret_cast<unsigned long long*>(window + peer_ll_offset(max_len)) +
+           ((size_t)parity * kPeerMaxWorld + src_rank) * 2 * peer_ll_len(max_len);
 }
 
-// All threads of a CTA: wait for the exchange most recently pushed by the preceding kernel and write
-// the rank-ordered sum of the `len` doubles to dst (shared or global).  Ends with __syncthreads().
-__device__ __forceinline__ void peer_pull(const PeerCtx& ex, double* dst, int len) {
-    const PeerHeader* me = reinterpret_cast<const PeerHeader*>(ex.windows[ex.rank]);
-    const unsigned int seq = me->seq;
+// All threads of ONE CTA: ship src[0..len) (shared or global memory, already visible to the CTA) to every
+// rank's window (own window included).  Advances the local sequence number and returns it.  Ends with a
+// CTA barrier, so src may be overwritten afterwards.  Kept out of line: it runs once per kernel, in one CTA,
+// and must not weigh on the register allocation of the streaming loops.
+static __device__ __noinline__ unsigned int peer_push(const PeerCtx& ex, const double* src, int len) {
+    PeerHeader* me = reinterpret_cast<PeerHeader*>(ex.windows[ex.rank]);
+    const unsigned int seq = ld_relaxed_gpu_u32(&me->seq) + 1u;
     const int parity = seq & 1u;
-    if ((int)threadIdx.x < ex.world)
-        while (ld_acquire_sys(&me->flags[parity][threadIdx.x]) != seq) {}
-    __syncthreads();
-    for (int i = threadIdx.x; i < len; i += blockDim.x) {
-        double acc = 0.0;
-        for (int r = 0; r < ex.world; ++r) acc += __ldcv(peer_slot(ex.windows[ex.rank], parity, r, ex.max_len) + i);
-        dst[i] = acc;
+    const int nt = blockDim.x, tid = threadIdx.x;
+    if (len <= kPeerLLMax) {
+        const int nw = 2 * len;
+        for (int w = tid; w < nw * ex.world; w += nt) {
+            const int r = w / nw, e = w - r * nw;
+            const double v = src[e >> 1];
+            const unsigned int word = (e & 1) ? (unsigned int)__double2hiint(v) : (unsigned int)__double2loint(v);
+            st_relaxed_sys_u64(peer_ll_slot(ex.windows[r], parity, ex.rank, ex.max_len) + e,
+                               ((unsigned long long)seq << 32) | word);
+        }
+        __syncthreads();                            // every thread has read me->seq and src
+    } else {
+        for (int w = tid; w < len * ex.world; w += nt) {
+            const int r = w / len, i = w - r * len;
+            peer_slot(ex.windows[r], parity, ex.rank, ex.max_len)[i] = src[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < ex.world)
+            st_release_sys(&reinterpret_cast<PeerHeader*>(ex.windows[tid])->flags[parity][ex.rank], seq);
+    }
+    if (tid == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&me->seq), "r"(seq) : "memory");
+    return seq;
+}
+
+// All threads of a CTA: wait for exchange `seq` (0: the one most recently pushed on this GPU by a preceding
+// kernel) and write the rank-ordered sum of the `len` doubles to dst (shared or global).  Ends with a CTA barrier.
+static __device__ __noinline__ void peer_pull(const PeerCtx& ex, double* dst, int len, unsigned int seq = 0u) {
+    PeerHeader* me = reinterpret_cast<PeerHeader*>(ex.windows[ex.rank]);
+    if (seq == 0u) seq = ld_relaxed_gpu_u32(&me->seq);
+    const int parity = seq & 1u;
+    const int nt = blockDim.x, tid = threadIdx.x;
+    if (len <= kPeerLLMax) {
+        const unsigned long long* base = peer_ll_slot(ex.windows[ex.rank], parity, 0, ex.max_len);
+        const size_t rstride = 2 * (size_t)peer_ll_len(ex.max_len);
+        for (int i = tid; i < len; i += nt) {
+            double acc = 0.0;
+            for (int r0 = 0; r0 < ex.world; r0 += 4) {              // 8 polls in flight, summed in rank order
+                unsigned long long lo[4], hi[4];
+                bool ok;
+                do {
+                    ok = true;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (r0 + u < ex.world) {
+                            const unsigned long long* c = base + (size_t)(r0 + u) * rstride + 2 * i;
+                            lo[u] = ld_relaxed_sys_u64(c);
+                            hi[u] = ld_relaxed_sys_u64(c + 1);
+                            ok = ok && (unsigned int)(lo[u] >> 32) == seq && (unsigned int)(hi[u] >> 32) == seq;
+                        }
+                    }
+                } while (!ok);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (r0 + u < ex.world) acc += __hiloint2double((int)(unsigned int)hi[u], (int)(unsigned int)lo[u]);
+            }
+            dst[i] = acc;
+        }
+    } else {
+        if (tid < ex.world)
+            while (ld_acquire_sys(&me->flags[parity][tid]) != seq) {}
+        __syncthreads();
+        for (int i = tid; i < len; i += nt) {
+            double acc = 0.0;
+            for (int r = 0; r < ex.world; ++r) acc += __ldcv(peer_slot(ex.windows[ex.rank], parity, r, ex.max_len) + i);
+            dst[i] = acc;
+        }
     }
     __syncthreads();
 }
@@ -519,10 +600,13 @@ __device__ __forceinline__ void ldcg_f64x2(const double* p, double& a, double& b
 // `counter` must be 0 on entry and is reset.  scratch: NT doubles of shared memory.
 // `partials` needs gridDim.x * ((S + 1) & ~1) doubles.
 // Returns true in the CTA that arrived last (after `out` is complete).
+// `push` (optional, multi-GPU): mode 1 = the last CTA ships the reduced vector to every rank's exchange
+// window (a later kernel pulls); mode 2 = it also waits for the world's vectors and overwrites `out` with
+// their rank-ordered sum — the all-reduce completes inside this kernel.
 template <int NT, int U = 16>
 __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, double* partials,
                                              unsigned int* counter, double* out, double* scratch,
-                                             const PeerCtx* push = nullptr) {
+                                             const PeerCtx* push = nullptr, int push_mode = 1) {
     __shared__ int s_last;
     const int tid = threadIdx.x;
     const int SP = (S + 1) & ~1;                  // slot stride: even, so slots stay 16-byte aligned
@@ -568,7 +652,6 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
             for (int rr = 0; rr < R; ++rr) t += scratch[rr * 2 * C + tid];
             out[tid] = t;
         }
-        if (push && push->windows) peer_push(*push, t, S);      // fused tail: ship the vector to every rank
     } else {
         for (int s = tid; s < S; s += NT) {
             double acc = 0.0;
@@ -581,6 +664,11 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
             }
             out[s] = acc;
         }
+    }
+    if (push && push->windows && push_mode) {       // fused tail: ship the vector to every rank (any length)
+        __syncthreads();                            // out[] (global) is complete and visible to the CTA
+        const unsigned int seq = peer_push(*push, out, S);
+        if (push_mode == 2) peer_pull(*push, out, S, seq);
     }
     if (tid == 0) *counter = 0u;
     return true;
@@ -659,9 +747,8 @@ __device__ __forceinline__ void grid_barrier_sum(const double* cta_stats, int S,
     double* global_vec = slots + (size_t)G * SP;                    // [S] the world's sum, behind the slots
     if (s_ticket == (unsigned int)G - 1) {                          // last CTA of this GPU: local sum, then the exchange
         grid_sum_slots<NT>(slots, S, out_s, scratch);
-        peer_push(*ex, (tid < S) ? out_s[tid] : 0.0, S);
-        __syncthreads();
-        peer_pull(*ex, out_s, S);                                   // rank-ordered sum of every GPU's vector
+        const unsigned int seq = peer_push(*ex, out_s, S);
+        peer_pull(*ex, out_s, S, seq);                              // rank-ordered sum of every GPU's vector
         if (tid < S) __stcg(global_vec + tid, out_s[tid]);
         __syncthreads();
         if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + 1), "r"(epoch + 1u) : "memory");

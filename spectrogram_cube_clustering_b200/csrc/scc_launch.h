@@ -50,8 +50,12 @@ struct DecArgs {
     // optional fused multi-GPU exchange (windows == nullptr: none)
     unsigned char* const* ex_windows;
     int ex_rank, ex_world, ex_max_len;
-    int ex_push;               // last CTA pushes the reduced stats to every rank's window
+    int ex_push;               // 1: last CTA pushes the reduced stats to every rank's window; 2: and collects the
+                               // world's sum into `stats` itself (all-reduce complete when the kernel ends)
     int ex_pull_f;             // f_cols are pulled from the exchange pushed by the preceding assign kernel
+    // batched Lloyd step (MODE_KMEANS): `batch` > 0 restarts over the same z, see batch_view()
+    int batch;
+    const unsigned char* batch_done;
     unsigned long long* timeline;   // profiling builds (-DSCC_TIMELINE): [grid][8] %globaltimer stamps, or NULL
 };
 
@@ -102,6 +106,12 @@ int dec_backward(const float* z, int64_t n, int d, const float* mu, int K, float
                  float* dz, double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
 int kmeans_step(const float* z, int64_t n, int d, const float* centers, int K, int32_t* labels, float* mindist,
                 double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t kmeans_batch_workspace_bytes(int d, int K, int R);
+int kmeans_batch_step(const float* z, int64_t n, int d, const float* centers, int K, int R, const unsigned char* done,
+                      int32_t* labels, float* mindist, double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
+int kmeans_batch_update(float* centers, const double* stats, int d, int K, int R, double thresh, unsigned char* done,
+                        int32_t* n_iter, double* inertia, cudaStream_t st);
+int dec_distances(const float* z, int64_t n, int d, const float* mu, int K, float p, float* out, cudaStream_t st);
 
 size_t peer_window_bytes(int max_len);
 int peer_allreduce(const double* local, int len, double* out, void* const* windows_dev, int rank, int world,

@@ -78,7 +78,9 @@ class LatentBuffer:
         self.world = 1 if group is None else torch.distributed.get_world_size(group)
         self.rank = 0 if group is None else torch.distributed.get_rank(group)
         self.n_total = int(n_total) if n_total is not None else self._sum_int(self.n_local)
+        self._row_offset = None     # global index of this shard's first row (lazy: one all-gather)
         self.labels = None          # int32 [n_local] of the last assign pass
+        self.assign_stats = None    # float64 [K+1] of the last batch_eval pass (f_j, label changes)
         self._labels_spare = None
         self.exchange = exchange    # optional NVLink peer-memory exchange (else NCCL / gloo all_reduce)
 
@@ -95,6 +97,19 @@ class LatentBuffer:
             blk = blk.pin_memory()
         return cls(blk.to(device, non_blocking=True), n_total=zt.shape[0], group=group)
 
+    @property
+    def row_offset(self) -> int:
+        """Global row index of the first local row (rank-ordered contiguous blocks)."""
+        if self._row_offset is None:
+            if self.group is None or self.world == 1:
+                self._row_offset = 0
+            else:
+                sizes = torch.zeros(self.world, dtype=torch.int64, device=self.z.device)
+                sizes[self.rank] = self.n_local
+                torch.distributed.all_reduce(sizes, group=self.group)
+                self._row_offset = int(sizes[:self.rank].sum().item())
+        return self._row_offset
+
     def _sum_int(self, v: int) -> int:
         if self.group is None:
             return int(v)
@@ -104,8 +119,8 @@ class LatentBuffer:
 
     def _allreduce(self, t: torch.Tensor) -> torch.Tensor:
         if self.group is not None and self.world > 1:
-            if self.exchange is not None:
-                self.exchange.all_reduce(t)
+            if self.exchange is not None and t.dtype == torch.float64 and t.numel() <= self.exchange.max_len:
+                self.exchange.all_reduce(t.view(-1))
             else:
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
         return t
@@ -164,8 +179,9 @@ class LatentBuffer:
                  want_dz: bool = False, want_p: bool = False) -> DecStepResult:
         """Fused latent-buffer DEC step: assign -> (allreduce f) -> KL gradients -> (allreduce dmu).
         With a peer exchange the collectives ride on the kernels: the assign kernel's last CTA pushes f
-        to every rank, the gradient kernel pulls it in its prologue and pushes its own statistics, and
-        one small finish kernel collects them — three launches per step, no separate collective."""
+        to every rank, the gradient kernel pulls it in its prologue and its last CTA all-reduces the gradient
+        statistics in its tail — two launches per step (one for the register-blocked shapes), no separate
+        collective."""
         K = mu.shape[0]
         one_kernel = getattr(ops, "dec_step_supported", lambda d, k: False)(self.d, K)
         if one_kernel and (self.world == 1 or self.exchange is not None):
@@ -191,7 +207,7 @@ class LatentBuffer:
             self._labels_spare, self.labels = self.labels, labels
             stats, p_out, dz = ops.dec_target_kl_grad(self.z, mu, None, alpha, round_decimals, gamma / self.n_total,
                                                       want_p=want_p, want_dz=want_dz, pull_f=ex, push=ex)
-            ops.peer_finish(stats, ex)
+            # (push on a gradient kernel = complete all-reduce: its last CTA also collects the world's sum)
             # st holds only this shard's f; the all-reduced f is not needed by the caller of a fused step,
             # the label-change count is: exchange it with the (tiny) standalone kernel
             self.exchange.all_reduce(st)

@@ -2,7 +2,8 @@
 
 ``ClusteringLayer`` keeps the reference constructor, the ``weights`` parameter
 ([K, d], state-dict key ``clustering.weights``) and the ``forward(x) -> q``
-contract (``networks.py:251-288``) but runs the fused sm_100a kernels: forward
+contract (``networks.py:251-288``) but runs the fused sm_100a kernels through the
+registered custom ops ``torch.ops.scc_b200.soft_assign`` / ``dec_kl_loss``: forward
 is one ``dec_assign`` launch, backward one ``dec_backward`` launch (the
 reference builds a [B,K,d] temporary and ~15 autograd nodes).  ``DEC`` wires it
 behind the stock-torch encoder / decoder exactly like ``networks.py:291-323``
@@ -24,63 +25,35 @@ def _pad_cols(t: torch.Tensor, width: int) -> torch.Tensor:
     return t if t.shape[1] == width else F.pad(t, (0, width - t.shape[1]))
 
 
-class _SoftAssign(torch.autograd.Function):
-    """q = softassign(x, weights); saves only x and weights (q is recomputed in backward)."""
-
-    @staticmethod
-    def forward(ctx, x, weights, alpha):
-        if not x.is_cuda:
-            raise SccError("ClusteringLayer needs CUDA tensors: the B200 path has no CPU fallback")
-        d = x.shape[1]
-        dp = ops.padded_dim(d)                      # zero-padding z and mu is exact for distances
-        x32 = _pad_cols(x.detach().to(torch.float32), dp).contiguous()
-        w32 = _pad_cols(weights.detach().to(device=x.device, dtype=torch.float32), dp).contiguous()
-        q, _, _ = ops.dec_assign(x32, w32, alpha, 0, want_labels=False)
-        ctx.save_for_backward(x32, w32)
-        ctx.alpha, ctx.d = alpha, d
-        ctx.x_dtype, ctx.w_dtype = x.dtype, weights.dtype
-        return q.to(x.dtype)
-
-    @staticmethod
-    def backward(ctx, grad_q):
-        x32, w32 = ctx.saved_tensors
-        g32 = grad_q.to(torch.float32).contiguous()
-        dz, dmu = ops.dec_backward(x32, w32, g32, ctx.alpha, want_dz=ctx.needs_input_grad[0])
-        gx = dz[:, :ctx.d].to(ctx.x_dtype) if dz is not None else None
-        gw = dmu[:, :ctx.d].to(ctx.w_dtype) if ctx.needs_input_grad[1] else None
-        return gx, gw, None
+def _operands(x, weights):
+    """float32, contiguous, padded to an instantiated latent dimension (zero-padding z and mu is exact)."""
+    if not x.is_cuda:
+        raise SccError("the clustering layer needs CUDA tensors: the B200 path has no CPU fallback")
+    dp = ops.padded_dim(x.shape[1])
+    x32 = _pad_cols(x.to(torch.float32), dp).contiguous()
+    w32 = _pad_cols(weights.to(device=x.device, dtype=torch.float32), dp).contiguous()
+    return x32, w32
 
 
-class _FusedKLLoss(torch.autograd.Function):
-    """scale * KL(p || softassign(z, weights)) with loss, dL/dz and dL/dweights from ONE launch
-    (``scc_dec_kl_grad``) — the fused form of ``gamma * KLDivLoss('sum')(log q, p) / B`` + backward
-    (``models.py:1124-1127``)."""
-
-    @staticmethod
-    def forward(ctx, z, weights, p, alpha, scale):
-        if not z.is_cuda:
-            raise SccError("dec_kl_loss needs CUDA tensors: the B200 path has no CPU fallback")
-        d = z.shape[1]
-        dp = ops.padded_dim(d)
-        z32 = _pad_cols(z.detach().to(torch.float32), dp).contiguous()
-        w32 = _pad_cols(weights.detach().to(device=z.device, dtype=torch.float32), dp).contiguous()
-        p32 = p.detach().to(device=z.device, dtype=torch.float32).contiguous()
-        stats, dz = ops.dec_kl_grad(z32, w32, alpha, p=p32, scale=scale, want_dz=True)
-        K = w32.shape[0]
-        ctx.save_for_backward(dz[:, :d].to(z.dtype), stats[2:].view(K, dp)[:, :d].to(weights.dtype))
-        return stats[0].to(z.dtype)
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        dz, dmu = ctx.saved_tensors
-        return grad_out * dz, grad_out * dmu, None, None, None
+def soft_assign(x, weights, alpha=1.0):
+    """q = Student's-t soft assignment of x [B, d] to the centroids weights [K, d] (``networks.py:279-288``) through
+    ``torch.ops.scc_b200.soft_assign``: forward is one ``scc_dec_assign`` launch, backward one
+    ``scc_dec_backward`` launch (q is recomputed, only x and weights are saved).  The casts / padding around the op
+    are ordinary differentiable torch ops, so gradients arrive in the callers' dtypes (float64 for the reference's
+    ``model.double()``)."""
+    x32, w32 = _operands(x, weights)
+    return torch.ops.scc_b200.soft_assign(x32, w32, float(alpha)).to(x.dtype)
 
 
 def dec_kl_loss(z, weights, p, alpha=1.0, scale=1.0):
     """Fused clustering loss: ``scale * sum_ij p_ij (log p_ij - log q_ij)`` with q recomputed from
     (z, weights); differentiable w.r.t. z and weights.  ``scale = gamma / batch_size`` reproduces
-    ``models.py:1124-1125``."""
-    return _FusedKLLoss.apply(z, weights, p, float(alpha), float(scale))
+    ``models.py:1124-1125``.  One ``scc_dec_kl_grad`` launch yields loss, dL/dz and dL/dweights
+    (``torch.ops.scc_b200.dec_kl_loss``); backward only scales them."""
+    z32, w32 = _operands(z, weights)
+    p32 = p.detach().to(device=z.device, dtype=torch.float32).contiguous()
+    loss, _, _ = torch.ops.scc_b200.dec_kl_loss(z32, w32, p32, float(alpha), float(scale))
+    return loss.to(z.dtype)
 
 
 class ClusteringLayer(nn.Module):
@@ -109,7 +82,7 @@ class ClusteringLayer(nn.Module):
     def forward(self, x):
         if x.dim() != 2 or x.shape[1] != self.weights.shape[1]:
             raise ValueError(f"expected x of shape [B, {self.weights.shape[1]}], got {tuple(x.shape)}")
-        return _SoftAssign.apply(x, self.weights, float(self.alpha))
+        return soft_assign(x, self.weights, float(self.alpha))
 
     def extra_repr(self):
         return f"n_clusters={self.n_clusters}, n_features={self.n_features}, alpha={self.alpha}"

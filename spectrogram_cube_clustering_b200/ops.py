@@ -180,8 +180,9 @@ def dec_step(z, mu, alpha=1.0, round_decimals=0, scale=1.0, want_q=True, want_la
     """The whole DEC step of one batch in ONE (cooperative) kernel launch — assign pass, grid-wide all-reduce of
     f, target + KL-gradient pass.  -> dict(q, labels, f [K+1 float64: f_j, label changes], p, dz,
     stats [K*d+2 float64: loss, sum_i s_i, dmu]).  networks.py:279-288 + models.py:1302-1322 + 1124-1127.
-    With ``exchange`` (a peer-exchange descriptor, one process per GPU) f is all-reduced over the GPUs inside
-    the kernel and the statistics are collected by a one-CTA finish kernel: ``scale`` must be gamma / N_total."""
+    With ``exchange`` (a peer-exchange descriptor, one process per GPU) f and the gradient statistics are
+    all-reduced over the GPUs INSIDE the kernel (flag-in-data exchange over NVLink peer memory, at the grid
+    barrier and in the kernel's tail): ``scale`` must be gamma / N_total."""
     lib = _lib.load()
     _require(z, "z"); _require(mu, "mu")
     n, d = z.shape
@@ -199,9 +200,7 @@ def dec_step(z, mu, alpha=1.0, round_decimals=0, scale=1.0, want_q=True, want_la
     rc = lib.scc_dec_step_ex(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), int(round_decimals), float(scale),
                              _ptr(q), _ptr(labels), _ptr(labels_prev), f.data_ptr(), _ptr(p), _ptr(dz),
                              stats.data_ptr(), ws.data_ptr(), ws.numel(), _ex(exchange), _stream())
-    _lib.check(rc, "scc_dec_step")
-    if exchange is not None:        # the kernel's last CTA pushed the statistics: collect the world's sum
-        peer_finish(stats, exchange)
+    _lib.check(rc, "scc_dec_step")      # with an exchange both all-reduces (f, statistics) completed inside the kernel
     return dict(q=q, labels=labels, f=f, p=p, dz=dz, stats=stats)
 
 
@@ -232,6 +231,72 @@ def kmeans_step(z, centers, labels=None, mindist=None, out_stats=None):
                              stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "scc_kmeans_step")
     return stats
+
+
+_batch_workspaces: dict = {}
+
+
+def _kmeans_batch_workspace(device, d: int, K: int, R: int) -> torch.Tensor:
+    lib = _lib.load()
+    key = (torch.device(device).index, _stream(), d, K, R)
+    ws = _batch_workspaces.get(key)
+    if ws is None:
+        nbytes = lib.scc_kmeans_batch_workspace_bytes(d, K, R)
+        if nbytes == 0:
+            raise ValueError(f"unsupported shape d={d}, K={K}, restarts={R}")
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)        # ticket counters start at zero
+        _batch_workspaces[key] = ws
+    return ws
+
+
+def kmeans_batch_step(z, centers, done=None, labels=None, mindist=None, out_stats=None):
+    """One Lloyd scan of R restarts at once: centers [R, K, d] -> stats float64 [R, K*d+2+K] (per restart:
+    inertia, 0, shift[K,d], count[K]); restarts with ``done[r] != 0`` are skipped.  models.py:386-394."""
+    lib = _lib.load()
+    _require(z, "z"); _require(centers, "centers")
+    if centers.dim() != 3 or centers.shape[2] != z.shape[1]:
+        raise ValueError("centers must be [restarts, K, d]")
+    n, d = z.shape
+    R, K = centers.shape[0], centers.shape[1]
+    if done is not None:
+        _require(done, "done", torch.uint8)
+    if labels is not None:
+        _require(labels, "labels", torch.int32)
+    if mindist is not None:
+        _require(mindist, "mindist")
+    stats = out_stats if out_stats is not None else torch.zeros(R, K * d + 2 + K, dtype=torch.float64, device=z.device)
+    ws = _kmeans_batch_workspace(z.device, d, K, R)
+    rc = lib.scc_kmeans_batch_step(z.data_ptr(), n, d, centers.data_ptr(), K, R, _ptr(done), _ptr(labels),
+                                   _ptr(mindist), stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "scc_kmeans_batch_step")
+    return stats
+
+
+def kmeans_batch_update(centers, stats, shift_tol, done, n_iter=None, inertia=None):
+    """Move every unfinished restart's centres (c += shift / count), count the iteration and raise ``done[r]`` once
+    the total squared centre shift is <= shift_tol (scikit-learn's rule) — on the device, no host sync."""
+    lib = _lib.load()
+    _require(centers, "centers"); _require(stats, "stats", torch.float64); _require(done, "done", torch.uint8)
+    R, K, d = centers.shape
+    rc = lib.scc_kmeans_batch_update(centers.data_ptr(), stats.data_ptr(), d, K, R, float(shift_tol), done.data_ptr(),
+                                     _ptr(n_iter), _ptr(inertia), _stream())
+    _lib.check(rc, "scc_kmeans_batch_update")
+
+
+def dec_distances(z, mu, p=2.0, out=None):
+    """D_ij = (sum_c |z_ic - mu_jc|^p)^(1/p)  -> [n, K] float32 (utils.py:866-869 for every centroid at once)."""
+    lib = _lib.load()
+    _require(z, "z"); _require(mu, "mu")
+    n, d = z.shape
+    K = mu.shape[0]
+    if mu.shape[1] != d:
+        raise ValueError("mu and z disagree on the latent dimension")
+    if not p > 0:
+        raise ValueError("p must be positive")
+    out = out if out is not None else torch.empty(n, K, dtype=torch.float32, device=z.device)
+    _lib.check(lib.scc_dec_distances(z.data_ptr(), n, d, mu.data_ptr(), K, float(p), out.data_ptr(), _stream()),
+               "scc_dec_distances")
+    return out
 
 
 # --------------------------------------------------------------------------- GMM
@@ -314,10 +379,66 @@ def peer_finish(t: torch.Tensor, desc) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- torch.library registration
+# The launches as PyTorch custom ops (torch.ops.scc_b200.*; BASELINE.json north_star: "a thin C-ABI exposed as
+# PyTorch custom ops").  Operands are float32, contiguous, CUDA — the Python layer (networks.py) casts and pads.
+# `soft_assign` and `dec_kl_loss` carry autograd formulas (register_autograd), so ClusteringLayer / dec_kl_loss
+# are differentiable through torch.ops and traceable (fake kernels registered); the others are plain launches.
 def _register_custom_ops():
-    """Expose the launches as PyTorch custom ops (torch.ops.scc_b200.*)."""
     from torch.library import custom_op
 
+    # ---- ClusteringLayer.forward / backward (networks.py:279-288 + autograd)
+    @custom_op("scc_b200::soft_assign", mutates_args=(), device_types="cuda")
+    def _soft_assign(z: torch.Tensor, mu: torch.Tensor, alpha: float) -> torch.Tensor:
+        q, _, _ = dec_assign(z, mu, alpha, 0, want_labels=False)
+        return q
+
+    @_soft_assign.register_fake
+    def _(z, mu, alpha):
+        return z.new_empty(z.shape[0], mu.shape[0])
+
+    @custom_op("scc_b200::soft_assign_backward", mutates_args=(), device_types="cuda")
+    def _soft_assign_backward(z: torch.Tensor, mu: torch.Tensor, grad_q: torch.Tensor, alpha: float) -> tuple[
+            torch.Tensor, torch.Tensor]:
+        dz, dmu = dec_backward(z, mu, grad_q, alpha)
+        return dz, dmu.to(torch.float32)
+
+    @_soft_assign_backward.register_fake
+    def _(z, mu, grad_q, alpha):
+        return torch.empty_like(z), torch.empty_like(mu)
+
+    def _sa_setup(ctx, inputs, output):
+        z, mu, alpha = inputs
+        ctx.save_for_backward(z, mu)
+        ctx.alpha = alpha
+
+    def _sa_backward(ctx, grad_q):
+        z, mu = ctx.saved_tensors
+        dz, dmu = torch.ops.scc_b200.soft_assign_backward(z, mu, grad_q.contiguous(), ctx.alpha)
+        return dz, dmu, None
+
+    _soft_assign.register_autograd(_sa_backward, setup_context=_sa_setup)
+
+    # ---- fused clustering loss: scale * KL(p || softassign(z, mu)) + gradients from one launch (models.py:1124-1127)
+    @custom_op("scc_b200::dec_kl_loss", mutates_args=(), device_types="cuda")
+    def _dec_kl_loss(z: torch.Tensor, mu: torch.Tensor, p: torch.Tensor, alpha: float, scale: float) -> tuple[
+            torch.Tensor, torch.Tensor, torch.Tensor]:
+        stats, dz = dec_kl_grad(z, mu, alpha, p=p, scale=scale)
+        return stats[0].to(torch.float32), dz, stats[2:].view(mu.shape).to(torch.float32)
+
+    @_dec_kl_loss.register_fake
+    def _(z, mu, p, alpha, scale):
+        return z.new_empty(()), torch.empty_like(z), torch.empty_like(mu)
+
+    def _kl_setup(ctx, inputs, output):
+        ctx.save_for_backward(output[1], output[2])
+
+    def _kl_backward(ctx, g_loss, g_dz, g_dmu):
+        dz, dmu = ctx.saved_tensors
+        return g_loss * dz, g_loss * dmu, None, None, None
+
+    _dec_kl_loss.register_autograd(_kl_backward, setup_context=_kl_setup)
+
+    # ---- plain launches
     @custom_op("scc_b200::dec_assign", mutates_args=(), device_types="cuda")
     def _dec_assign(z: torch.Tensor, mu: torch.Tensor, alpha: float, round_decimals: int) -> tuple[
             torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -347,6 +468,29 @@ def _register_custom_ops():
     def _(z, mu, p, alpha, scale):
         return z.new_empty(mu.numel() + 2, dtype=torch.float64), torch.empty_like(z)
 
+    @custom_op("scc_b200::dec_target_kl_grad", mutates_args=(), device_types="cuda")
+    def _dec_target_kl_grad(z: torch.Tensor, mu: torch.Tensor, f: torch.Tensor, alpha: float, round_decimals: int,
+                            scale: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        stats, p, dz = dec_target_kl_grad(z, mu, f, alpha, round_decimals, scale)
+        return stats, p, dz
+
+    @_dec_target_kl_grad.register_fake
+    def _(z, mu, f, alpha, round_decimals, scale):
+        return (z.new_empty(mu.numel() + 2, dtype=torch.float64), z.new_empty(z.shape[0], mu.shape[0]),
+                torch.empty_like(z))
+
+    @custom_op("scc_b200::dec_step", mutates_args=(), device_types="cuda")
+    def _dec_step(z: torch.Tensor, mu: torch.Tensor, alpha: float, round_decimals: int, scale: float) -> tuple[
+            torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        r = dec_step(z, mu, alpha, round_decimals, scale)
+        return r["q"], r["labels"], r["f"], r["p"], r["dz"], r["stats"]
+
+    @_dec_step.register_fake
+    def _(z, mu, alpha, round_decimals, scale):
+        n, K = z.shape[0], mu.shape[0]
+        return (z.new_empty(n, K), z.new_empty(n, dtype=torch.int32), z.new_empty(K + 1, dtype=torch.float64),
+                z.new_empty(n, K), torch.empty_like(z), z.new_empty(mu.numel() + 2, dtype=torch.float64))
+
     @custom_op("scc_b200::dec_backward", mutates_args=(), device_types="cuda")
     def _dec_backward(z: torch.Tensor, mu: torch.Tensor, grad_q: torch.Tensor, alpha: float) -> tuple[
             torch.Tensor, torch.Tensor]:
@@ -365,9 +509,16 @@ def _register_custom_ops():
     def _(z, params, K):
         return z.new_empty(gmm_stat_doubles(K, z.shape[1]), dtype=torch.float64)
 
+    @custom_op("scc_b200::gmm_finalize", mutates_args=("means", "weights", "covariances", "prec_chol", "params", "ctrl"),
+               device_types="cuda")
+    def _gmm_finalize(stats: torch.Tensor, n_total: float, means: torch.Tensor, weights: torch.Tensor,
+                      covariances: torch.Tensor, prec_chol: torch.Tensor, params: torch.Tensor, ctrl: torch.Tensor,
+                      reg_covar: float, tol: float) -> None:
+        gmm_finalize(stats, n_total, means, weights, covariances, prec_chol, params, ctrl, reg_covar=reg_covar, tol=tol)
 
-try:
-    _register_custom_ops()
-except Exception as _exc:  # pragma: no cover - registration is best effort on exotic torch builds
-    import warnings
-    warnings.warn(f"scc_b200 custom-op registration skipped: {_exc}")
+    @_gmm_finalize.register_fake
+    def _(stats, n_total, means, weights, covariances, prec_chol, params, ctrl, reg_covar, tol):
+        return None
+
+
+_register_custom_ops()

@@ -246,3 +246,231 @@ def test_fused_kl_loss_matches_literal_line():
     loss.backward()
     assert abs(loss.item() / 3.0 - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
     assert rel_err(z.grad.cpu().numpy() / 3.0, g["dz"]) < 1e-5 and rel_err(w.grad.cpu().numpy() / 3.0, g["dmu"]) < 1e-5
+
+
+# ------------------------------------------------------------------------------ SURVEY §8(f) rows
+def test_batch_eval_matches_oracle_soft_assignment():
+    """f2: q / labels of the device batch_eval against the float64 oracle applied to the encoder's own latents
+    (networks.py:279-288, models.py:92-94) — not against this package's layer."""
+    from spectrogram_cube_clustering_b200.networks import DEC
+    from spectrogram_cube_clustering_b200.models import batch_eval
+    from spectrogram_cube_clustering_b200 import synth
+    from oracle import dec as odec
+    torch.manual_seed(4)
+    model = DEC(n_clusters=6).cuda()
+    with torch.no_grad():
+        model.clustering.weights.mul_(0.5).add_(0.2)
+    x = synth.spectrograms(3000)
+    loader = torch.utils.data.DataLoader(x, batch_size=256, shuffle=False)
+    q, labels, z = batch_eval(loader, model, "cuda")
+    assert q.dtype == np.float64 and labels.dtype == np.int64 and z.dtype == np.float64
+    mu = model.clustering.weights.detach().cpu().numpy().astype(np.float64)
+    q_ref = odec.soft_assign(z, mu, 1.0)                    # z: the latents batch_eval itself returned
+    dq = np.abs(q - np.round(q_ref, 5))
+    assert dq.max() <= 1.01e-5 and (dq > 1e-7).mean() < 0.01
+    lab_ref = odec.labels_from_q(q_ref)
+    mism = labels != lab_ref
+    if mism.any():
+        qs = np.sort(q_ref[mism], axis=1)
+        assert np.all(qs[:, -1] - qs[:, -2] < 1e-5)
+    # and the latents are the encoder's (same batch split)
+    model.eval()
+    with torch.no_grad():
+        zz = torch.cat([model.encoder(xb.cuda()) for xb in loader]).cpu().numpy()
+    assert rel_err(z, zz) < 1e-6
+    # device-resident form: buffer + fused label-change count
+    prev = torch.from_numpy(lab_ref.astype(np.int32)).cuda()
+    prev[:77] = (prev[:77] + 1) % 6
+    buf, q_dev, lab_dev = batch_eval(loader, model, "cuda", return_buffer=True, labels_prev=prev)
+    assert int(buf.assign_stats[-1].item()) == int((lab_dev != prev).sum().item())
+    assert abs(int(buf.assign_stats[-1].item()) - 77) <= int(mism.sum())
+
+
+def test_dec_training_refresh_and_stop_rule():
+    """f3: the loop crosses update_interval boundaries (p refreshed from a device batch_eval) and the
+    delta_label < tol stop fires from the fused label-change count (models.py:1093-1111)."""
+    import copy
+    from spectrogram_cube_clustering_b200.networks import DEC
+    from spectrogram_cube_clustering_b200.models import DEC_training, batch_eval
+    from spectrogram_cube_clustering_b200 import synth
+    torch.manual_seed(2)
+    model = DEC(n_clusters=4).cuda()
+    with torch.no_grad():
+        model.clustering.weights.mul_(0.4).add_(0.15)
+    x = synth.spectrograms(1024)
+    loader = torch.utils.data.DataLoader(x, batch_size=128, shuffle=False)
+    m0 = copy.deepcopy(model)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-3)
+    # tol = 0: never stops; 2 epochs x 8 batches, update_interval = ceil(1024 / 256) = 4 -> refreshes at
+    # (epoch 0, batch 4), (epoch 1, batch 0), (epoch 1, batch 4)
+    hist = DEC_training(model, loader, opt, n_epochs=2, gamma=1e-1, tol=0.0)
+    assert hist["update_interval"] == 4 and len(hist["deltas"]) == 3 and not hist["finished"]
+    assert hist["deltas_iter"] == [5, 9, 13] and len(hist["loss"]) == 2
+    assert all(0.0 <= dl <= 1.0 for dl in hist["deltas"])
+    # stop rule: the first refresh compares with the labels of the untouched model; tol = 2 fires at once
+    model2 = copy.deepcopy(m0)
+    opt2 = torch.optim.Adam(model2.parameters(), lr=5e-3)
+    _, lab0, _ = batch_eval(loader, m0, "cuda")
+    hist2 = DEC_training(model2, loader, opt2, n_epochs=3, gamma=1e-1, tol=2.0)
+    assert hist2["finished"] and len(hist2["deltas"]) == 1 and len(hist2["loss"]) == 1
+    _, lab1, _ = batch_eval(loader, model2, "cuda")        # the break leaves the model as the refresh saw it
+    delta_ref = float((lab1 != lab0).sum()) / len(lab0)    # models.py:1098-1099
+    assert abs(hist2["deltas"][0] - delta_ref) <= 2.0 / len(lab0)
+    # and with a tolerance that is NOT met the loop goes on
+    model3 = copy.deepcopy(m0)
+    hist3 = DEC_training(model3, loader, torch.optim.Adam(model3.parameters(), lr=5e-3), n_epochs=1, gamma=1e-1,
+                         tol=min(1e-9, hist2["deltas"][0] / 2))
+    assert len(hist3["deltas"]) == 1 and hist3["finished"] == (hist3["deltas"][0] < min(1e-9, hist2["deltas"][0] / 2))
+
+
+def test_initialize_clusters_and_dec_params_round_trip(tmp_path):
+    """f4: stage 2 -> stage 3 hand-off on disk (models.py:444-449 -> 523-530 -> 1006-1012, 1227-1228)."""
+    import types
+    from spectrogram_cube_clustering_b200.networks import DEC
+    from spectrogram_cube_clustering_b200 import models, synth
+    torch.manual_seed(3)
+    K = 4
+    model = DEC(n_clusters=K).cuda()
+    x = synth.spectrograms(1536)
+    loader = torch.utils.data.DataLoader(x, batch_size=256, shuffle=False)
+    weights = tmp_path / "AEC" / "AEC_Params_Final.pt"
+    weights.parent.mkdir()
+    torch.save(model.state_dict(), weights)
+    run = tmp_path / "run"
+    run.mkdir()
+    # stage 2: latent set -> gmm_fit -> labels.npy / centroids.npy where stage 3 looks for them
+    gmm_dir = weights.parent / "GMM" / f"n_clusters={K}"
+    gmm_dir.mkdir(parents=True)
+    z = models.batch_eval(loader, model, "cuda")[2]
+    lab_fit, cent_fit = models.gmm_fit(types.SimpleNamespace(savepath_run=str(gmm_dir)), z, K)
+    cfg = types.SimpleNamespace(init="load", saved_weights=str(weights), savepath_run=str(run), device="cuda",
+                                index_tra=np.arange(1536))
+    lab, cent = models.initialize_clusters(model, loader, cfg, n_clusters=K)
+    assert np.array_equal(lab, lab_fit) and np.array_equal(cent, cent_fit)
+    for init in ("kmeans", "gmm", "rand"):
+        cfg_i = types.SimpleNamespace(init=init, saved_weights=str(weights), savepath_run=str(run), device="cuda")
+        lab_i, cent_i = models.initialize_clusters(model, loader, cfg_i, n_clusters=K)
+        assert lab_i.shape == (1536,) and cent_i.shape == (K, 9) and np.isfinite(cent_i).all()
+        assert lab_i.min() >= 0 and lab_i.max() < K
+    with pytest.raises(ValueError):
+        models.initialize_clusters(model, loader, types.SimpleNamespace(init="nope"), n_clusters=K)
+    # stage 3 with the config: centroids copied into clustering.weights, both parameter files written
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    hist = models.DEC_training(model, loader, opt, n_epochs=1, gamma=1e-1, tol=0.0, config=cfg, n_clusters=K)
+    init_sd = torch.load(run / "DEC_Params_Initial.pt")
+    final_sd = torch.load(run / "DEC_Params_Final.pt")
+    assert set(init_sd) == set(model.state_dict()) and "clustering.weights" in init_sd
+    np.testing.assert_allclose(init_sd["clustering.weights"].numpy(), cent_fit.astype(np.float32), rtol=1e-6)
+    fresh = DEC(n_clusters=K)
+    fresh.load_state_dict(final_sd, strict=True)                       # the reference's keys, loadable as they are
+    assert torch.equal(fresh.clustering.weights.detach(), model.clustering.weights.detach().cpu())
+    assert (run / "DEC_history.csv").exists() and (run / "Delta_history.csv").exists()
+    assert hist["params_final"].endswith("DEC_Params_Final.pt")
+
+
+def test_kmeans_batched_restarts():
+    """f1: R restarts advance in one launch per Lloyd iteration; each equals the single-restart run from the
+    same centres, converged restarts freeze, and fit() keeps the lowest inertia."""
+    from spectrogram_cube_clustering_b200 import ops, synth
+    from spectrogram_cube_clustering_b200.models import KMeans
+    from spectrogram_cube_clustering_b200.latent_buffer import LatentBuffer
+    z, _ = synth.latent_points(20_000, 9, 6, device="cuda", rank=9)
+    buf = LatentBuffer(z)
+    km = KMeans(6, n_init=5, random_state=7, max_iter=300)
+    gen = torch.Generator(device="cpu"); gen.manual_seed(7)
+    c0 = km._plusplus(buf, 5, gen)
+    assert tuple(c0.shape) == (5, 6, 9)
+    # every seeded centre is a row of z
+    assert all((z == c0[r, k]).all(dim=1).any().item() for r in range(5) for k in range(6))
+    # one batched scan == five single scans
+    st_b = ops.kmeans_batch_step(z, c0)
+    for r in range(5):
+        st_1 = ops.kmeans_step(z, c0[r].contiguous())
+        assert torch.equal(st_b[r], st_1)
+    tol = km._shift_tol(buf, km.tol)
+    assert abs(tol - 1e-4 * z.double().var(dim=0, unbiased=False).mean().item()) < 1e-9 * tol + 1e-15
+    batch = c0.clone()
+    inertia, n_iter = km._lloyd_batch(buf, batch, tol)
+    for r in range(5):
+        c_r, in_r, _, it_r = km.lloyd(buf, c0[r])
+        assert torch.equal(c_r, batch[r]) and in_r == inertia[r].item() and it_r == int(n_iter[r].item())
+    km.fit(buf)
+    assert abs(km.inertia_ - inertia.min().item()) <= 1e-9 * km.inertia_
+    assert km.labels_.shape == (20_000,) and km.cluster_centers_.shape == (6, 9)
+    # skipped restarts keep their statistics
+    done = torch.tensor([0, 1, 0, 1, 0], dtype=torch.uint8, device="cuda")
+    st_keep = torch.full_like(st_b, -1.0)
+    ops.kmeans_batch_step(z, c0, done=done, out_stats=st_keep)
+    assert (st_keep[1] == -1).all() and (st_keep[3] == -1).all() and torch.equal(st_keep[0], st_b[0])
+
+
+@pytest.mark.parametrize("p", [2.0, 1.0, 0.5, 3.0])
+def test_distance_scans_match_reference_formulas(p):
+    """f4 (second half): utils.fractional_distance / distance_matrix / measure_class_inertia
+    (utils.py:866-869, 635-643, 1024-1029) on the device."""
+    from spectrogram_cube_clustering_b200 import models
+    rng = np.random.default_rng(5)
+    z = rng.normal(size=(3001, 9)) * 1.3 + 0.5
+    mu = rng.normal(size=(7, 9))
+    for j in (0, 6):
+        ref = np.sum(np.fabs(mu[j] - z) ** p, axis=1) ** (1 / p)            # utils.py:867-868
+        got = models.fractional_distance(mu[j], z, p)
+        assert got.dtype == np.float64 and rel_err(got, ref) < 2e-6
+    dm = models.distance_matrix(mu, mu, p)
+    ref_dm = np.array([[np.sum(np.fabs(mu[i] - mu[j]) ** p) ** (1 / p) for j in range(7)] for i in range(7)])
+    assert dm.shape == (7, 7) and np.abs(dm - ref_dm).max() < 2e-6 * ref_dm.max()
+    if p == 2.0:
+        ref_in = np.array([np.sum(np.sqrt(np.sum((z - mu[j]) ** 2, axis=1)) ** 2) for j in range(7)])
+        assert rel_err(models.measure_class_inertia(z, mu, 7), ref_in) < 1e-5
+    big = rng.normal(size=(40, 9))
+    assert models.distance_matrix(big, big, p).shape == (40, 40)            # more than 16 columns: scanned in blocks
+
+
+# ------------------------------------------------------------------------------ torch.ops.scc_b200.*
+def test_custom_ops_opcheck_and_layer_routes_through_them():
+    """The launches are registered PyTorch custom ops (fake kernels + autograd formulas): torch.library.opcheck
+    validates schema, fake tensors, autograd registration and AOT dispatch; ClusteringLayer / dec_kl_loss go
+    through torch.ops.scc_b200.soft_assign / dec_kl_loss."""
+    from torch.library import opcheck
+    from spectrogram_cube_clustering_b200 import ops, synth  # noqa: F401  (registers the ops)
+    from spectrogram_cube_clustering_b200.networks import ClusteringLayer, dec_kl_loss
+    g = load_golden("dec", "c1")
+    z = torch.from_numpy(g["z"]).float().cuda()
+    mu = torch.from_numpy(g["mu"]).float().cuda()
+    p = torch.from_numpy(g["p"]).float().cuda()
+    n, K = z.shape[0], mu.shape[0]
+    zg, mug = z.clone().requires_grad_(True), mu.clone().requires_grad_(True)
+    opcheck(torch.ops.scc_b200.soft_assign.default, (zg, mug, 1.0))
+    opcheck(torch.ops.scc_b200.dec_kl_loss.default, (zg, mug, p, 1.0, 1e-3 / n))
+    opcheck(torch.ops.scc_b200.soft_assign_backward.default, (z, mu, torch.randn(n, K, device="cuda"), 1.0))
+    opcheck(torch.ops.scc_b200.dec_assign.default, (z, mu, 1.0, 5))
+    q, _, f = torch.ops.scc_b200.dec_assign(z, mu, 1.0, 5)
+    opcheck(torch.ops.scc_b200.dec_target.default, (q, f, 5))
+    opcheck(torch.ops.scc_b200.dec_target_kl_grad.default, (z, mu, f, 1.0, 5, 1e-3 / n))
+    opcheck(torch.ops.scc_b200.dec_step.default, (z, mu, 1.0, 5, 1e-3 / n))
+    # registered ops == direct launches
+    r = torch.ops.scc_b200.dec_step(z, mu, 1.0, 5, 1e-3 / n)
+    d = ops.dec_step(z, mu, 1.0, 5, 1e-3 / n)
+    assert all(torch.equal(a, d[k]) for a, k in zip(r, ("q", "labels", "f", "p", "dz", "stats")))
+    # GMM: functional statistics op + mutating finalize op
+    gg = load_golden("gmm", "c1")
+    zz = torch.from_numpy(gg["z"]).float().cuda()
+    w0, m0, c0 = (torch.from_numpy(gg[k]).double().cuda() for k in ("w0", "mu0", "cov0"))
+    params, pchol, ctrl = ops.gmm_pack_params(w0, m0, c0)
+    Kg = m0.shape[0]
+    opcheck(torch.ops.scc_b200.gmm_em_step.default, (zz, params, Kg))
+    stats = torch.ops.scc_b200.gmm_em_step(zz, params, Kg)
+    means, weights, cov = m0.clone(), w0.clone(), c0.clone()
+    torch.ops.scc_b200.gmm_finalize(stats, float(zz.shape[0]), means, weights, cov, pchol, params, ctrl, 1e-6, 0.0)
+    assert rel_err(means.cpu().numpy(), gg["it_means"][0]) < TOL
+    # the layer: traced through the dispatcher, gradients in the caller's dtype
+    layer = ClusteringLayer(K, 9, 1.0, weights=mu.double()).double().cuda()
+    zd = z.double().requires_grad_(True)
+    with torch.profiler.profile() as prof:
+        qd = layer(zd)
+        loss = dec_kl_loss(zd, layer.weights, p, 1.0, 1e-3 / n) + 0.0 * qd.sum()
+        loss.backward()
+    names = {e.name for e in prof.events()}
+    assert "scc_b200::soft_assign" in names and "scc_b200::dec_kl_loss" in names
+    assert zd.grad.dtype == torch.float64 and layer.weights.grad.dtype == torch.float64
+    assert rel_err(zd.grad.cpu().numpy(), g["dz"]) < 1e-5 and rel_err(layer.weights.grad.cpu().numpy(), g["dmu"]) < 1e-5

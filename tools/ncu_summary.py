@@ -19,7 +19,10 @@ KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
 
 
 def main(rep, out_txt, out_json=None):
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if rep.endswith('.csv'):          # already exported on the GPU box (tools/ncu_capture.sh)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     traffic = {}
