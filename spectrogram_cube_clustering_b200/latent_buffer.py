@@ -73,6 +73,8 @@ class LatentBuffer:
         if z.dim() != 2:
             raise ValueError("z must be [n_local, d]")
         self.z = z.contiguous() if z.dtype == torch.float32 else z.float().contiguous()
+        if self.z.data_ptr() % 16:      # a row slice of a larger buffer: the kernels need a 16-byte aligned base
+            self.z = self.z.clone()
         self.n_local, self.d = self.z.shape
         self.group = group
         self.world = 1 if group is None else torch.distributed.get_world_size(group)

@@ -65,7 +65,7 @@ for n_total, tag in ((200_003, "ragged"), (world - 1, "empty shards")):
     z_all, mu = synth.latent_points(max(n_total, 1), d, K, rank=5, device=dev)
     z_all = z_all[:n_total]
     lo, hi = shard_bounds(n_total, rank, world)
-    z = z_all[lo:hi].contiguous()
+    z = z_all[lo:hi].clone()            # a row slice is a view at a 36-byte offset: the kernels need 16-byte alignment
     n = hi - lo
     scale = 1e-3 / max(n_total, 1)
     out = ops.dec_step(z, mu, 1.0, 5, scale, exchange=ex.desc)
@@ -95,7 +95,7 @@ say("[2] dec_step_ex (f and gradient statistics all-reduced inside the kernel) =
 d, K, n_total = 32, 16, 120_001
 z_all, mu = synth.latent_points(n_total, d, K, rank=6, device=dev)
 lo, hi = shard_bounds(n_total, rank, world)
-buf = LatentBuffer(z_all[lo:hi].contiguous(), n_total=n_total, group=group, exchange=ex)
+buf = LatentBuffer(z_all[lo:hi], n_total=n_total, group=group, exchange=ex)
 res = buf.dec_step(mu, 1.0, 1e-3, 0, want_dz=True)
 torch.cuda.synchronize()
 if rank == 0:
@@ -110,7 +110,7 @@ say("[3] sharded step at d=32, K=16 (514 statistics pushed by the tiled kernel's
 d, K, n_total = 9, 6, 40_000
 z_all, _ = synth.latent_points(n_total, d, K, rank=8, device=dev)
 lo, hi = shard_bounds(n_total, rank, world)
-buf = LatentBuffer(z_all[lo:hi].contiguous(), n_total=n_total, group=group, exchange=ex)
+buf = LatentBuffer(z_all[lo:hi], n_total=n_total, group=group, exchange=ex)
 km = KMeans(K, n_init=4, random_state=3, max_iter=200).fit(buf)
 km1 = KMeans(K, n_init=4, random_state=3, max_iter=200).fit(LatentBuffer(z_all))
 c_all = [torch.empty_like(km._centers) for _ in range(world)]
@@ -129,14 +129,14 @@ w0, mu0, cov0 = [t.numpy() for t in synth.gmm_initial_state(d, K, "cpu")]
 import warnings
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
-    buf = LatentBuffer(z_all[lo:hi].contiguous(), n_total=n_total, group=group, exchange=ex)
+    buf = LatentBuffer(z_all[lo:hi], n_total=n_total, group=group, exchange=ex)
     gm = GaussianMixture(K, max_iter=30, tol=1e-3, weights_init=w0, means_init=mu0, covariances_init=cov0,
                          poll_interval=5, group=group).fit(buf)
     gm1 = GaussianMixture(K, max_iter=30, tol=1e-3, weights_init=w0, means_init=mu0, covariances_init=cov0,
                           poll_interval=5).fit(LatentBuffer(z_all))
 assert gm.n_iter_ == gm1.n_iter_ and gm.converged_ == gm1.converged_, (gm.n_iter_, gm1.n_iter_)
 assert rel(gm.means_, gm1.means_) < 1e-6 and rel(gm.covariances_, gm1.covariances_) < 1e-6
-assert abs(gm.lower_bound_ - gm1.lower_bound_) < 1e-9 * abs(gm1.lower_bound_)
+assert abs(gm.lower_bound_ - gm1.lower_bound_) < 1e-6 * abs(gm1.lower_bound_)   # fp32 per-thread partial sums regroup with the shards
 m_all = [torch.empty_like(gm._means) for _ in range(world)]
 dist.all_gather(m_all, gm._means)
 assert all(torch.equal(m_all[0], m) for m in m_all), "GMM: ranks hold different means"
