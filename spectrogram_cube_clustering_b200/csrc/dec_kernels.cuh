@@ -20,14 +20,23 @@
 namespace scc {
 
 constexpr int kDecThreads = 256;
+#ifdef SCC_REG_THREADS
+constexpr int kRegThreads = SCC_REG_THREADS;   // A/B builds (make variant VFLAGS=-DSCC_REG_THREADS=192)
+#else
+// threads per CTA of the register-blocked gradient / step kernel.  192 (2 CTAs = 12 warps per SM, 168 registers per
+// thread): the K*(d+1) per-thread accumulators + the per-cluster chain fit without spilling.  Measured against 256
+// threads at the 128-register cap (16 warps per SM, ~40 local-memory accesses per point): one-kernel step 51.3 vs
+// 57.3 us at 1M points, 561 vs 672 us at 16M (profiles/r02_variants.txt).
+constexpr int kRegThreads = 192;
+#endif
 constexpr int kDecTile = 256;
 constexpr int kBatchGridX = 296;       // grid.x bound of a batched (grid.y = restarts) Lloyd launch
+constexpr int kFixOffset = 8;          // workspace header: u64[8 .. 8+K] = fixed-point f accumulators of the one-kernel step
 
 // doubles of reduction scratch for an NV-long statistics vector: cta_reduce needs
 // [num_warps][round_up(NV, 32)], grid_publish needs 2 * kDecThreads
-__host__ __device__ constexpr int reduce_scratch(int nv) {
-    return (kDecThreads / 32) * ((nv + 31) / 32 * 32) > 2 * kDecThreads ? (kDecThreads / 32) * ((nv + 31) / 32 * 32)
-                                                                      : 2 * kDecThreads;
+__host__ __device__ constexpr int reduce_scratch(int nv, int nt = kDecThreads) {
+    return (nt / 32) * ((nv + 31) / 32 * 32) > 2 * nt ? (nt / 32) * ((nv + 31) / 32 * 32) : 2 * nt;
 }
 
 template <int D>
@@ -37,80 +46,133 @@ __host__ __device__ constexpr int dec_stages() { return RowLayout<D>::kDense ? 4
 // Packed FP32 (sm_100 FFMA2 / FADD2 / FMUL2): two lanes of a float2 per instruction.  On B200 a
 // stream of 3-register scalar FFMAs issues at ~56 % of the FP32 peak (register-read bandwidth)
 // while FFMA2 reaches ~88 % (tools/ubench_fp32.cu), and the issue-slot count halves.
-// Rows are held as DP2 = ceil(D/2) float2 pairs; the pad lane of an odd D is kept at 0.
+//
+// The two lanes of a pair are two CLUSTERS (2jp, 2jp+1), not two dimensions: every per-cluster
+// quantity of a point (squared distance, w, u, t, q, p, gradient coefficient) then lives in
+// KP/2 float2 registers and the whole per-cluster chain — not only the distance loop — runs on
+// packed instructions, with the point's coordinate / the row-wide scalars riding in the .F32
+// broadcast operand of FFMA2/FADD2/FMUL2.  Per lane the operations and their order are exactly
+// those of a scalar evaluation: distance accumulated over c = 0..D-1 in ONE fma chain, so every
+// kernel that evaluates q this way produces bit-identical values.
 // ---------------------------------------------------------------------------
 template <int D>
 struct Pairs { static constexpr int N = (D + 1) / 2; };
 
-template <int D>
-__device__ __forceinline__ void pack_row(const float (&r)[D], float2 (&p)[Pairs<D>::N]) {
-#pragma unroll
-    for (int c = 0; c < Pairs<D>::N; ++c) p[c] = make_float2(r[2 * c], (2 * c + 1 < D) ? r[2 * c + 1] : 0.f);
+__device__ __forceinline__ float2 pair_sel(bool cx, bool cy, float2 v, float other) {
+    return make_float2(cx ? v.x : other, cy ? v.y : other);
+}
+
+__device__ __forceinline__ float2 round_dec5_2(float2 x) {
+    // np.round(x, 5) on both lanes, see round_dec5()
+    const float2 y = __ffma2_rn(x, make_float2(100000.0f, 100000.0f), make_float2(12582912.0f, 12582912.0f));
+    return __fmul2_rn(__fadd2_rn(y, make_float2(-12582912.0f, -12582912.0f)), make_float2(1.0e-5f, 1.0e-5f));
+}
+
+// negated centroids, transposed and paired over clusters: nmuT2[c][jp] = -(mu[2jp][c], mu[2jp+1][c]);
+// clusters j >= K are 0.  [D][KP/2] float2, 16-byte aligned.
+template <int D, int KP>
+__device__ __forceinline__ void load_neg_centroid_pairs(const float* __restrict__ mu, int K, float2* nmuT2) {
+    float* flat = reinterpret_cast<float*>(nmuT2);
+    for (int i = threadIdx.x; i < D * KP; i += blockDim.x) {
+        const int c = i / KP, j = i - c * KP;
+        flat[i] = (j < K) ? -mu[j * D + c] : 0.f;
+    }
 }
 
 // ---------------------------------------------------------------------------
-// Student's-t kernel of one point against every centroid.  networks.py:279-288, models.py:92.
-//   w_j = 1 + ||z - mu_j||^2 / alpha,  u_j = 1 / w_j,  t_j = u_j^((alpha+1)/2),  tsum = sum_j t_j
-// so q_j = t_j / tsum.  Distances use the exact difference form (z_c - mu_jc)^2: no cancellation.
-// nmu2_s holds the NEGATED centroids as float2 pairs [KP][DP2] (pad lane 0).
-// LABEL: also the hard label = argmin distance (== argmax q, first index wins) and that distance.
-// The arithmetic (operation order included) is the same as soft_assign_rows() of the assign kernel,
-// so the gradient kernels recompute bit-identical q.  Reciprocals are single MUFU.RCP instructions (w >= 1, so no range fix-up is needed).
+// Squared distances of P points (one thread) to every centroid, P points sharing each centroid load:
+// acc2[r][jp] = (||z_r - mu_2jp||^2, ||z_r - mu_2jp+1||^2).  networks.py:280-282.
 // ---------------------------------------------------------------------------
-template <int D, int KP, bool EXACT, bool ALPHA1, bool LABEL>
-__device__ __forceinline__ void student_t_row(const float2 (&z2)[Pairs<D>::N], const float2* __restrict__ nmu2_s,
-                                              int K, float inv_alpha, float expo, float (&w)[KP], float (&u)[KP],
-                                              float (&t)[KP], float& tsum, int& label, float& best) {
-    constexpr int DP2 = Pairs<D>::N;
-    float ts[2] = {0.f, 0.f};                 // two chains: short serial dependencies matter at 4 warps/scheduler
+template <int D, int KP, int P>
+__device__ __forceinline__ void sq_distances(const float (&z)[P][D], const float2* __restrict__ nmuT2,
+                                             float2 (&acc2)[P][KP / 2]) {
+    constexpr int JP = KP / 2;
+#pragma unroll
+    for (int r = 0; r < P; ++r)
+#pragma unroll
+        for (int jp = 0; jp < JP; ++jp) acc2[r][jp] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const float4* row = reinterpret_cast<const float4*>(nmuT2 + c * JP);
+#pragma unroll
+        for (int h = 0; h < JP / 2; ++h) {
+            const float4 m = row[h];
+#pragma unroll
+            for (int r = 0; r < P; ++r) {
+                const float2 zc = make_float2(z[r][c], z[r][c]);
+                const float2 d0 = __fadd2_rn(zc, make_float2(m.x, m.y));
+                const float2 d1 = __fadd2_rn(zc, make_float2(m.z, m.w));
+                acc2[r][2 * h] = __ffma2_rn(d0, d0, acc2[r][2 * h]);
+                acc2[r][2 * h + 1] = __ffma2_rn(d1, d1, acc2[r][2 * h + 1]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Student's-t kernel of one point from its squared distances.  networks.py:283-287, models.py:92.
+//   w_j = 1 + d_j / alpha,  u_j = 1 / w_j,  t_j = u_j^((alpha+1)/2),  tsum = sum_j t_j,  q_j = t_j / tsum.
+// LABEL: also the hard label = argmin distance (== argmax q, first index wins) and that distance.
+// Reciprocals are single MUFU.RCP instructions (w >= 1, so no range fix-up is needed).
+// ---------------------------------------------------------------------------
+template <int KP, bool EXACT, bool ALPHA1, bool LABEL>
+__device__ __forceinline__ void student_t_pairs(const float2 (&acc2)[KP / 2], int K, float inv_alpha, float expo,
+                                                float2 (&w2)[KP / 2], float2 (&u2)[KP / 2], float2 (&t2)[KP / 2],
+                                                float& tsum, int& label, float& best) {
+    constexpr int JP = KP / 2;
+    float2 ts2 = make_float2(0.f, 0.f);
     best = 3.4e38f;
     label = 0;
 #pragma unroll
-    for (int j = 0; j < KP; ++j) {
-        w[j] = 1.f; u[j] = 0.f; t[j] = 0.f;
-        if (EXACT || j < K) {
-            float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < DP2; ++c) {
-                const float2 df = __fadd2_rn(z2[c], nmu2_s[j * DP2 + c]);
-                acc2 = __ffma2_rn(df, df, acc2);
-            }
-            const float acc = acc2.x + acc2.y;
-            if (LABEL) {
-                if (acc < best) { best = acc; label = j; }
-            }
-            const float ww = ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f);
-            const float uu = rcp_approx(ww);
-            const float tt = ALPHA1 ? uu : ex2_approx(-expo * lg2_approx(ww));
-            w[j] = ww; u[j] = uu; t[j] = tt; ts[j & 1] += tt;
+    for (int jp = 0; jp < JP; ++jp) {
+        const bool vx = EXACT || 2 * jp < K, vy = EXACT || 2 * jp + 1 < K;
+        if (LABEL) {
+            if (vx && acc2[jp].x < best) { best = acc2[jp].x; label = 2 * jp; }
+            if (vy && acc2[jp].y < best) { best = acc2[jp].y; label = 2 * jp + 1; }
         }
+        float2 ww = ALPHA1 ? __fadd2_rn(acc2[jp], make_float2(1.f, 1.f))
+                           : __ffma2_rn(acc2[jp], make_float2(inv_alpha, inv_alpha), make_float2(1.f, 1.f));
+        float2 uu = make_float2(rcp_approx(ww.x), rcp_approx(ww.y));
+        float2 tt = ALPHA1 ? uu : make_float2(ex2_approx(-expo * lg2_approx(ww.x)), ex2_approx(-expo * lg2_approx(ww.y)));
+        if (!EXACT) {
+            ww = pair_sel(vx, vy, ww, 1.f); uu = pair_sel(vx, vy, uu, 0.f); tt = pair_sel(vx, vy, tt, 0.f);
+        }
+        w2[jp] = ww; u2[jp] = uu; t2[jp] = tt;
+        ts2 = __fadd2_rn(ts2, tt);
     }
-    tsum = ts[0] + ts[1];
-}
-
-// negated centroids as pairs: nmu2_s[j][c] = -(mu[j][2c], mu[j][2c+1]); rows j >= K and pad lanes are 0
-template <int D, int KP>
-__device__ __forceinline__ void load_neg_centroid_pairs(const float* __restrict__ mu, int K, float2* nmu2_s) {
-    constexpr int DP2 = Pairs<D>::N;
-    float* flat = reinterpret_cast<float*>(nmu2_s);
-    for (int i = threadIdx.x; i < KP * DP2 * 2; i += kDecThreads) {
-        const int j = i / (2 * DP2), c = i - j * (2 * DP2);
-        flat[i] = (j < K && c < D) ? -mu[j * D + c] : 0.f;
-    }
+    tsum = ts2.x + ts2.y;
 }
 
 template <int KP, bool EXACT>
-__device__ __forceinline__ void store_krow(float* __restrict__ dst, int K, const float (&v)[KP]) {
+__device__ __forceinline__ void store_krow2(float* __restrict__ dst, int K, const float2 (&v)[KP / 2]) {
     if (EXACT || (K & 3) == 0) {
 #pragma unroll
         for (int j = 0; j < KP; j += 4)
-            if (EXACT || j < K) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (EXACT || j < K)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j / 2].x, v[j / 2].y, v[j / 2 + 1].x, v[j / 2 + 1].y);
     } else {
 #pragma unroll
         for (int j = 0; j < KP; ++j)
-            if (j < K) dst[j] = v[j];
+            if (j < K) dst[j] = (j & 1) ? v[j / 2].y : v[j / 2].x;
     }
 }
+template <int KP, bool EXACT>
+__device__ __forceinline__ void load_krow2(const float* __restrict__ src, int K, float2 (&v)[KP / 2]) {
+    if (EXACT || (K & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < KP; j += 4) {
+            if (EXACT || j < K) {
+                const float4 x = ldg_stream4(reinterpret_cast<const float4*>(src + j));
+                v[j / 2] = make_float2(x.x, x.y); v[j / 2 + 1] = make_float2(x.z, x.w);
+            } else { v[j / 2] = make_float2(0.f, 0.f); v[j / 2 + 1] = make_float2(0.f, 0.f); }
+        }
+    } else {
+#pragma unroll
+        for (int jp = 0; jp < KP / 2; ++jp)
+            v[jp] = make_float2((2 * jp < K) ? ldg_stream(src + 2 * jp) : 0.f, (2 * jp + 1 < K) ? ldg_stream(src + 2 * jp + 1) : 0.f);
+    }
+}
+// scalar row load kept for colsum_kernel (dec_api.cu)
 template <int KP, bool EXACT>
 __device__ __forceinline__ void load_krow(const float* __restrict__ src, int K, float (&v)[KP]) {
     if (EXACT || (K & 3) == 0) {
@@ -154,50 +216,28 @@ __device__ __forceinline__ void cta_reduce(const float (&v)[NV], double* scratch
 }
 
 // ---------------------------------------------------------------------------
-// P rows per thread sharing every centroid load: the centroid broadcasts (one LDS.64/128 per pair)
-// are what saturates first at large K*d (LSU pipe: 1 wavefront/clk/SM against 4 FP32 warp-instr/clk),
-// so register-blocking P = 2 points halves the shared-memory traffic per point.
+// Soft assignment of P rows per thread (assign pass): q2[r][jp], label[r].  The centroid loads (one
+// LDS.128 per two cluster pairs and dimension) are shared by the P points: they are what saturates
+// first at large K*d (LSU pipe: 1 wavefront/clk/SM against 4 FP32 warp-instr/clk).
 // ---------------------------------------------------------------------------
 template <int D, int KP, bool EXACT, bool ALPHA1, int P>
-__device__ __forceinline__ void soft_assign_rows(const float2 (&z2)[P][Pairs<D>::N], const float2* __restrict__ nmu2_s,
-                                                 int K, float inv_alpha, float expo,
-                                                 float (&q)[P][KP], int (&label)[P]) {
-    constexpr int DP2 = Pairs<D>::N;
-    float tsum[P][2], best[P];
-#pragma unroll
-    for (int r = 0; r < P; ++r) { tsum[r][0] = 0.f; tsum[r][1] = 0.f; best[r] = 3.4e38f; label[r] = 0; }
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-#pragma unroll
-        for (int r = 0; r < P; ++r) q[r][j] = 0.f;
-        if (EXACT || j < K) {
-            float2 acc2[P];
-#pragma unroll
-            for (int r = 0; r < P; ++r) acc2[r] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < DP2; ++c) {
-                const float2 m = nmu2_s[j * DP2 + c];
-#pragma unroll
-                for (int r = 0; r < P; ++r) {
-                    const float2 df = __fadd2_rn(z2[r][c], m);
-                    acc2[r] = __ffma2_rn(df, df, acc2[r]);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < P; ++r) {
-                const float acc = acc2[r].x + acc2[r].y;
-                if (acc < best[r]) { best[r] = acc; label[r] = j; }
-                const float ww = ALPHA1 ? (1.f + acc) : fmaf(acc, inv_alpha, 1.f);
-                const float t = ALPHA1 ? rcp_approx(ww) : ex2_approx(-expo * lg2_approx(ww));
-                q[r][j] = t; tsum[r][j & 1] += t;
-            }
-        }
-    }
+__device__ __forceinline__ void soft_assign_rows(const float (&z)[P][D], const float2* __restrict__ nmuT2,
+                                                 int K, float inv_alpha, float expo, bool round5,
+                                                 float2 (&q2)[P][KP / 2], int (&label)[P]) {
+    constexpr int JP = KP / 2;
+    float2 acc2[P][JP];
+    sq_distances<D, KP, P>(z, nmuT2, acc2);
 #pragma unroll
     for (int r = 0; r < P; ++r) {
-        const float inv = rcp_approx(tsum[r][0] + tsum[r][1]);
+        float2 w2[JP], u2[JP];
+        float tsum, best;
+        student_t_pairs<KP, EXACT, ALPHA1, true>(acc2[r], K, inv_alpha, expo, w2, u2, q2[r], tsum, label[r], best);
+        const float inv = rcp_approx(tsum);
 #pragma unroll
-        for (int j = 0; j < KP; ++j) q[r][j] *= inv;
+        for (int jp = 0; jp < JP; ++jp) {
+            q2[r][jp] = __fmul2_rn(q2[r][jp], make_float2(inv, inv));
+            if (round5) q2[r][jp] = round_dec5_2(q2[r][jp]);
+        }
     }
 }
 
@@ -218,14 +258,14 @@ dec_assign_kernel(const DecArgs a) {
     constexpr int P = assign_ppt<D, KP>();
     constexpr int TILE = kDecTile * P;
     constexpr int S = assign_stages<D, KP>();
-    // CTA-level ring: a per-warp ring (WarpRing) was measured for this kernel too — its 6x more, 6x smaller
+    constexpr int JP = KP / 2;
+    // CTA-level ring: a per-warp ring was measured for this kernel too — its 6x more, 6x smaller
     // TMA copies lengthen the prologue by ~1.3 us and the short main loop gains nothing
     using Ring = ZRing<D, TILE, S, kDecThreads>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring_buf = reinterpret_cast<float*>(smem_raw);
-    constexpr int DP2 = Pairs<D>::N;
-    float2* nmu2_s = reinterpret_cast<float2*>(ring_buf + S * Ring::kTileFloats);      // [KP][DP2] (-mu pairs)
-    double* cta_stats = reinterpret_cast<double*>(nmu2_s + ((KP * DP2 + 1) & ~1));     // [KP+1]
+    float2* nmuT2 = reinterpret_cast<float2*>(ring_buf + ((S * Ring::kTileFloats + 3) & ~3));     // [D][JP] (-mu pairs)
+    double* cta_stats = reinterpret_cast<double*>(nmuT2 + ((D * JP + 1) & ~1));        // [KP+1]
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + (KP + 1));                // [S]
     // the reduction scratch [reduce_scratch(KP+1)] reuses the ring once the main loop is over: keeping it
     // separate pushes the d = 32 kernel (3 x 36 KB of stages) over half an SM's shared memory -> 1 CTA/SM
@@ -241,15 +281,16 @@ dec_assign_kernel(const DecArgs a) {
     const int G = gridDim.x;
 #pragma unroll
     for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
-    load_neg_centroid_pairs<D, KP>(a.mu, K, nmu2_s);
+    load_neg_centroid_pairs<D, KP>(a.mu, K, nmuT2);
     __syncthreads();
     SCC_TL(a.timeline, 1);
 
     const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
     const bool round5 = a.round5 != 0;
-    float facc[KP + 1];
+    float2 facc2[JP];
 #pragma unroll
-    for (int j = 0; j <= KP; ++j) facc[j] = 0.f;
+    for (int jp = 0; jp < JP; ++jp) facc2[jp] = make_float2(0.f, 0.f);
+    float changed = 0.f;
 
     int stage = 0;
     uint32_t use = 0;
@@ -257,37 +298,31 @@ dec_assign_kernel(const DecArgs a) {
         ring.wait(stage, tile, use);
         if (tile == (int)blockIdx.x) SCC_TL(a.timeline, 2);
         const int np = ring.points(tile);
-        float2 z2[P][DP2];
+        float zr[P][D];
         bool active[P];
 #pragma unroll
         for (int r = 0; r < P; ++r) {
             const int t = threadIdx.x + r * kDecThreads;
             active[r] = t < np;
-            float zr[D];
 #pragma unroll
-            for (int c = 0; c < D; ++c) zr[c] = 0.f;
-            if (active[r]) load_row<D>(ring.stage_ptr(stage), t, zr);
-            pack_row<D>(zr, z2[r]);
+            for (int c = 0; c < D; ++c) zr[r][c] = 0.f;
+            if (active[r]) load_row<D>(ring.stage_ptr(stage), t, zr[r]);
         }
         __syncthreads();                 // every row of the stage is in registers: refill it
         ring.issue(stage, tile + S * G);
         if (active[0]) {
-            float q[P][KP];
+            float2 q2[P][JP];
             int label[P];
-            soft_assign_rows<D, KP, EXACT, ALPHA1, P>(z2, nmu2_s, K, inv_alpha, expo, q, label);
+            soft_assign_rows<D, KP, EXACT, ALPHA1, P>(zr, nmuT2, K, inv_alpha, expo, round5, q2, label);
 #pragma unroll
             for (int r = 0; r < P; ++r) {
                 if (active[r]) {
                     const size_t i = (size_t)tile * TILE + threadIdx.x + r * kDecThreads;
-                    if (round5) {
 #pragma unroll
-                        for (int j = 0; j < KP; ++j) q[r][j] = round_dec5(q[r][j]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < KP; ++j) facc[j] += q[r][j];
-                    if (a.q) store_krow<KP, EXACT>(a.q + i * K, K, q[r]);
+                    for (int jp = 0; jp < JP; ++jp) facc2[jp] = __fadd2_rn(facc2[jp], q2[r][jp]);
+                    if (a.q) store_krow2<KP, EXACT>(a.q + i * K, K, q2[r]);
                     if (a.labels) a.labels[i] = label[r];
-                    if (a.labels_prev) facc[KP] += (a.labels_prev[i] != label[r]) ? 1.f : 0.f;
+                    if (a.labels_prev) changed += (a.labels_prev[i] != label[r]) ? 1.f : 0.f;
                 }
             }
         }
@@ -296,6 +331,10 @@ dec_assign_kernel(const DecArgs a) {
     pdl_trigger();                      // successor may start its prologue under our reduction tail
     SCC_TL(a.timeline, 3);
     __syncthreads();                    // every warp is done with the ring: it becomes the reduction scratch
+    float facc[KP + 1];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) facc[j] = (j & 1) ? facc2[j / 2].y : facc2[j / 2].x;
+    facc[KP] = changed;
     cta_reduce<KP + 1, kDecThreads>(facc, scratch, cta_stats);
     SCC_TL(a.timeline, 4);
     if (!EXACT) {                       // stats layout is [K+1]: compact the KP-padded vector
@@ -315,20 +354,14 @@ dec_assign_kernel(const DecArgs a) {
 //                  KL streams p from memory, KLF rebuilds it from the column sums (and may write it out)
 //   MODE_GENERIC : c_ij = q_ij (sum_j G_ij q_ij - G_ij) u_ij,  cs = (alpha+1)/alpha
 //   MODE_KMEANS  : c_ij = [j == argmin_j ||z_i - mu_j||^2],  cs = 1  (Lloyd step: counts, centre shifts, inertia)
-// Inputs are the Student's-t quantities of student_t_row(): q_j = t_j / tsum, 1/q_j = tsum w_j^expo.
+// Inputs are the Student's-t quantities of student_t_pairs(): q_j = t_j / tsum, 1/q_j = tsum w_j^expo.
+// Everything per cluster is a float2 over the cluster pair (2jp, 2jp+1).
 // ---------------------------------------------------------------------------
 // The [n, K] operand a gradient kernel streams besides z: the target p (MODE_KL, API mode) or the
-// upstream gradient dL/dq (MODE_GENERIC).  The row is requested at the top of the iteration, before
-// the wait on the z tile.  (Requesting it a whole iteration ahead was measured: the 8 extra live
-// registers spill at the 128-register cap and the kernel got 12 % slower.)
+// upstream gradient dL/dq (MODE_GENERIC).
 template <int MODE>
 __device__ __forceinline__ const float* krow_operand(const DecArgs& a) {
     return MODE == MODE_KL ? a.p : (MODE == MODE_GENERIC ? a.grad_q : nullptr);
-}
-template <int KP, bool EXACT>
-__device__ __forceinline__ void prefetch_krow(const float* __restrict__ src, int64_t base, int np, int K,
-                                              float (&row)[KP]) {
-    if (src && (int)threadIdx.x < np) load_krow<KP, EXACT>(src + ((size_t)base + threadIdx.x) * K, K, row);
 }
 
 template <int MODE>
@@ -340,30 +373,32 @@ __host__ __device__ __forceinline__ float grad_fold_scale(float scale, float alp
 }
 
 template <int KP, bool EXACT, bool ALPHA1, int MODE>
-__device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, int K, const float* __restrict__ inv_f,
-                                                  const float (&w)[KP], const float (&u)[KP], const float (&t)[KP],
-                                                  float tsum, float expo, int label, float best,
-                                                  const float (&pre)[KP],
-                                                  float (&coef)[KP], float& loss, float& ssum) {
+__device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, int K, const float2* __restrict__ inv_f2,
+                                                  const float2 (&w2)[KP / 2], const float2 (&u2)[KP / 2],
+                                                  const float2 (&t2)[KP / 2], float tsum, float expo, int label,
+                                                  float best, const float2 (&pre2)[KP / 2],
+                                                  float2 (&coef2)[KP / 2], float& loss, float& ssum) {
+    constexpr int JP = KP / 2;
     if constexpr (MODE == MODE_KMEANS) {
         // Lloyd statistics: one-hot coefficient on the nearest centre, "loss" = inertia
 #pragma unroll
-        for (int j = 0; j < KP; ++j) coef[j] = (j == label) ? 1.f : 0.f;
+        for (int jp = 0; jp < JP; ++jp) coef2[jp] = make_float2(2 * jp == label ? 1.f : 0.f, 2 * jp + 1 == label ? 1.f : 0.f);
         loss += best;
         if (a.labels) a.labels[i] = label;
         if (a.mindist) a.mindist[i] = best;
     } else if constexpr (mode_is_kl<MODE>()) {
         const float inv = rcp_approx(tsum);
-        float p[KP];
-        if constexpr (MODE == MODE_KL) {           // target row requested before the z tile wait (prefetch_krow)
+        float2 p2[JP];
+        if constexpr (MODE == MODE_KL) {           // target row streamed from memory
 #pragma unroll
-            for (int j = 0; j < KP; ++j) p[j] = pre[j];
+            for (int jp = 0; jp < JP; ++jp) p2[jp] = pre2[jp];
         } else {                                   // MODE_KLF / MODE_STEP: rebuild p from the column sums
+            const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
-            for (int j = 0; j < KP; ++j) {
-                const float q = t[j] * inv;
-                const float qq = a.round5 ? round_dec5(q) : q;
-                p[j] = (EXACT || j < K) ? qq * qq * inv_f[j] : 0.f;
+            for (int jp = 0; jp < JP; ++jp) {
+                float2 q = __fmul2_rn(t2[jp], inv2);
+                if (a.round5) q = round_dec5_2(q);
+                p2[jp] = __fmul2_rn(__fmul2_rn(q, q), inv_f2[jp]);         // inv_f is 0 for clusters >= K
             }
             // row sum in the order dec_target_kernel uses (groups of 4, then a pairwise tree over the
             // groups; sequential when K is not 4, 8 or 16), so the rebuilt p is bit-identical to its output
@@ -371,62 +406,69 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
             if ((K & 3) == 0 && K != 12) {
                 float g4[KP / 4];
 #pragma unroll
-                for (int b = 0; b < KP / 4; ++b) g4[b] = (p[4 * b] + p[4 * b + 1]) + (p[4 * b + 2] + p[4 * b + 3]);
+                for (int b = 0; b < KP / 4; ++b) g4[b] = (p2[2 * b].x + p2[2 * b].y) + (p2[2 * b + 1].x + p2[2 * b + 1].y);
                 if constexpr (KP == 4) wsum = g4[0];
                 else if constexpr (KP == 8) wsum = (K == 4) ? g4[0] : g4[0] + g4[1];
                 else wsum = (K == 4) ? g4[0] : ((K == 8) ? g4[0] + g4[1] : (g4[0] + g4[1]) + (g4[2] + g4[3]));
             } else {
                 wsum = 0.f;
 #pragma unroll
-                for (int j = 0; j < KP; ++j) wsum += (EXACT || j < K) ? p[j] : 0.f;
+                for (int j = 0; j < KP; ++j) wsum += (EXACT || j < K) ? ((j & 1) ? p2[j / 2].y : p2[j / 2].x) : 0.f;
             }
             const float winv = 1.f / wsum;
+            const float2 winv2 = make_float2(winv, winv);
 #pragma unroll
-            for (int j = 0; j < KP; ++j) {
-                p[j] *= winv;
-                if (a.round5) p[j] = round_dec5(p[j]);
+            for (int jp = 0; jp < JP; ++jp) {
+                p2[jp] = __fmul2_rn(p2[jp], winv2);
+                if (a.round5) p2[jp] = round_dec5_2(p2[jp]);
             }
-            if (a.p_out) store_krow<KP, EXACT>(a.p_out + i * K, K, p);      // materialise target_distribution(q)
+            if (a.p_out) store_krow2<KP, EXACT>(a.p_out + i * K, K, p2);      // materialise target_distribution(q)
         }
         // p_j / q_j = p_j w_j tsum for alpha == 1 (w_j = 1 + d_j is already in registers: no division); the log is
         // taken of the RATIO (near 1), not of its large factors separately — lg2.approx has a relative error, so
         // log2(p w) + log2(tsum) would lose the digits that cancel.  The 1e-37 keeps a zero target at
         // 0 * finite = 0 (torch KLDivLoss: xlogy); negative / NaN targets still give NaN.
-        float s2[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f};
+        float2 s2 = make_float2(0.f, 0.f), l2 = make_float2(0.f, 0.f);
+        const float2 tiny2 = make_float2(1e-37f, 1e-37f);
 #pragma unroll
-        for (int j = 0; j < KP; ++j) {
-            if (EXACT || j < K) {
-                s2[j & 1] += p[j];
-                const float ratio = ALPHA1 ? fmaf(p[j] * w[j], tsum, 1e-37f)
-                                           : fmaf(p[j], rcp_approx(fmaxf(t[j] * inv, 1e-37f)), 1e-37f);
-                l2[j & 1] = fmaf(p[j], lg2_approx(ratio), l2[j & 1]);
+        for (int jp = 0; jp < JP; ++jp) {
+            s2 = __fadd2_rn(s2, p2[jp]);
+            float2 ratio;
+            if (ALPHA1) {
+                ratio = __ffma2_rn(__fmul2_rn(p2[jp], w2[jp]), make_float2(tsum, tsum), tiny2);
+            } else {
+                ratio = make_float2(fmaf(p2[jp].x, rcp_approx(fmaxf(t2[jp].x * inv, 1e-37f)), 1e-37f),
+                                    fmaf(p2[jp].y, rcp_approx(fmaxf(t2[jp].y * inv, 1e-37f)), 1e-37f));
             }
+            l2 = __ffma2_rn(p2[jp], make_float2(lg2_approx(ratio.x), lg2_approx(ratio.y)), l2);
         }
-        const float s = s2[0] + s2[1];
+        const float s = s2.x + s2.y;
         const float nis = -(inv * s);
+        const float2 nis2 = make_float2(nis, nis);
 #pragma unroll
-        for (int j = 0; j < KP; ++j) coef[j] = (EXACT || j < K) ? fmaf(t[j], nis, p[j]) * u[j] : 0.f;
-        loss += l2[0] + l2[1];
+        for (int jp = 0; jp < JP; ++jp) coef2[jp] = __fmul2_rn(__ffma2_rn(t2[jp], nis2, p2[jp]), u2[jp]);
+        loss += l2.x + l2.y;
         ssum += s;
     } else {
         const float inv = rcp_approx(tsum);
-        float g[KP];
+        float2 d2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < KP; ++j) g[j] = pre[j];
-        float dot = 0.f;
+        for (int jp = 0; jp < JP; ++jp) d2 = __ffma2_rn(pre2[jp], t2[jp], d2);
+        const float dot = (d2.x + d2.y) * inv;
+        const float2 inv2 = make_float2(inv, inv), dot2 = make_float2(dot, dot);
 #pragma unroll
-        for (int j = 0; j < KP; ++j) dot = fmaf(g[j], t[j], dot);
-        dot *= inv;
-#pragma unroll
-        for (int j = 0; j < KP; ++j) coef[j] = (EXACT || j < K) ? (t[j] * inv) * (dot - g[j]) * u[j] : 0.f;
+        for (int jp = 0; jp < JP; ++jp) {
+            const float2 ng = make_float2(-pre2[jp].x, -pre2[jp].y);
+            coef2[jp] = __fmul2_rn(__fmul2_rn(__fmul2_rn(t2[jp], inv2), __fadd2_rn(dot2, ng)), u2[jp]);
+        }
     }
 }
 
 // dz_c = cs ((sum_j c_j) zc_c - sum_j c_j mc_jc)  with zc = z - c0, mc = mu - c0 (algebraic form of
-// sum_j c_j (z_c - mu_jc): K*D/2 FFMA2 instead of K*D (FADD + FMA)).  nmc2_s = -cs (mu - c0) pairs,
-// csum = cs sum_j c_j.  The pad lane of an odd D holds garbage and is never stored.
+// sum_j c_j (z_c - mu_jc): K*D/2 FFMA2 instead of K*D (FADD + FMA)).  nmc2_s = -cs (mu - c0) as pairs over
+// the DIMENSION [KP][ceil(D/2)], csum = cs sum_j c_j.  The pad lane of an odd D holds garbage and is never stored.
 template <int D, int KP, bool EXACT>
-__device__ __forceinline__ void dz_from_coefficients(const float2 (&zc2)[Pairs<D>::N], const float (&coef)[KP],
+__device__ __forceinline__ void dz_from_coefficients(const float2 (&zc2)[Pairs<D>::N], const float2 (&coef2)[KP / 2],
                                                      float csum, const float2* __restrict__ nmc2_s, int K,
                                                      float (&dzr)[D]) {
     constexpr int DP2 = Pairs<D>::N;
@@ -437,7 +479,7 @@ __device__ __forceinline__ void dz_from_coefficients(const float2 (&zc2)[Pairs<D
 #pragma unroll
     for (int j = 0; j < KP; ++j) {
         if (EXACT || j < K) {
-            const float2 cj = splat2(coef[j]);
+            const float2 cj = splat2((j & 1) ? coef2[j / 2].y : coef2[j / 2].x);
 #pragma unroll
             for (int c = 0; c < DP2; ++c) dz2[c] = __ffma2_rn(cj, nmc2_s[j * DP2 + c], dz2[c]);
         }
@@ -471,9 +513,10 @@ __device__ __forceinline__ void copy_tile_out(const float* __restrict__ tile, fl
     }
 }
 
-// Shared prologue of the gradient kernels: -mu pairs, -cs (mu - c0) pairs, c0, (mu - c0), 1/f.
+// Shared prologue of the gradient kernels: -mu cluster pairs (transposed), -cs (mu - c0) dimension pairs,
+// c0, (mu - c0), 1/f.
 template <int D, int KP>
-__device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, float cs, float2* nmu2_s,
+__device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, float cs, float2* nmuT2,
                                                     float2* nmc2_s, float* mc_s, float* c0_s, float* inv_f) {
     constexpr int DP2 = Pairs<D>::N;
     if (threadIdx.x < D) {
@@ -490,16 +533,147 @@ __device__ __forceinline__ void load_grad_constants(const DecArgs& a, int K, flo
         inv_f[threadIdx.x] = (a.f_cols && (int)threadIdx.x < K) ? (float)(1.0 / a.f_cols[threadIdx.x]) : 0.f;
     }
     __syncthreads();
-    float* nmu = reinterpret_cast<float*>(nmu2_s);
+    load_neg_centroid_pairs<D, KP>(a.mu, K, nmuT2);
     float* nmc = reinterpret_cast<float*>(nmc2_s);
-    for (int i = threadIdx.x; i < KP * DP2 * 2; i += kDecThreads) {
+    for (int i = threadIdx.x; i < KP * DP2 * 2; i += blockDim.x) {
         const int j = i / (2 * DP2), c = i - j * (2 * DP2);
         const bool ok = (j < K && c < D);
-        const float m = ok ? a.mu[j * D + c] : 0.f;
-        nmu[i] = -m;
-        nmc[i] = ok ? -cs * (m - c0_s[c]) : 0.f;
+        nmc[i] = ok ? -cs * (a.mu[j * D + c] - c0_s[c]) : 0.f;
     }
-    for (int i = threadIdx.x; i < KP * D; i += kDecThreads) mc_s[i] = (i < K * D) ? a.mu[i] - c0_s[i % D] : 0.f;
+    for (int i = threadIdx.x; i < KP * D; i += blockDim.x) mc_s[i] = (i < K * D) ? a.mu[i] - c0_s[i % D] : 0.f;
+}
+
+// ---------------------------------------------------------------------------
+// Per-warp stream of latent rows (register-blocked gradient kernel / one-kernel step).
+//   The rows are split into contiguous blocks, one per WARP of the grid (blocks differ by at most one
+//   32-row slice: a static, deterministic, balanced partition whatever the stage size); a warp walks its
+//   block in stages of up to 32*P rows — ONE TMA bulk copy onto the warp's own mbarrier (padded layouts:
+//   the warp's lanes issue cp.async / plain loads) — and the only synchronisation in the main loop is
+//   __syncwarp().  Lane l owns rows l, l+32, ... of a stage and processes them one after the other, so the
+//   ring / barrier / copy-out bookkeeping is paid once per P rows of every thread.
+//   dL/dz rows are written IN PLACE over the consumed z rows and leave with one bulk store per stage; the
+//   stage is refilled after the first slice of the NEXT stage has been processed (by then the store has
+//   long finished reading shared memory, and the refill still has P-1 slices of compute to land behind).
+// ---------------------------------------------------------------------------
+template <int D, int P, int STAGES>
+struct WarpStream {
+    using L = RowLayout<D>;
+    static constexpr int kRows = 32 * P;
+    static constexpr int kStageFloats = kRows * L::LD;
+    static constexpr bool kCpAsync = L::kVec4 && !L::kDense;
+    static_assert(STAGES >= 2, "stream needs two stages");
+
+    float* buf;            // this warp's STAGES stages
+    uint64_t* bar;         // this warp's STAGES mbarriers
+    const float* zw;       // first row of this warp's block
+    int64_t row_begin;     // its global row index
+    int total, req;        // rows in the block / rows requested so far (a warp's block is far below 2^31 rows)
+    int lane;
+    uint32_t phase;        // bit s = parity the next wait on stage s expects (flips per completed TMA fill)
+
+    __device__ __forceinline__ void init(float* warp_buf, uint64_t* warp_bars, const float* z_, int64_t n,
+                                         int warp_global, int warps_total) {
+        buf = warp_buf; bar = warp_bars; phase = 0u; lane = threadIdx.x & 31;
+        const int64_t slices = (n + 31) >> 5;
+        const int64_t base = slices / warps_total, rem = slices - base * warps_total;
+        const int64_t s0 = warp_global * base + (warp_global < rem ? warp_global : rem);
+        const int64_t cnt = base + (warp_global < rem ? 1 : 0);
+        row_begin = 32 * s0 < n ? 32 * s0 : n;
+        const int64_t row_end = 32 * (s0 + cnt) < n ? 32 * (s0 + cnt) : n;
+        total = (int)(row_end - row_begin);
+        req = 0;
+        zw = z_ + (size_t)row_begin * D;
+        if (L::kDense && lane == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void rewind() { req = 0; }
+    __device__ __forceinline__ float* stage_ptr(int stage) const { return buf + stage * kStageFloats; }
+    static __device__ __forceinline__ bool tma_ok(int rows) { return L::kDense && rows > 0 && ((rows * D) & 3) == 0; }
+    // rows of the stage that starts at local row `from`
+    __device__ __forceinline__ int stage_rows(int from) const {
+        const int left = total - from;
+        return left < kRows ? left : kRows;
+    }
+
+    // Called by all lanes of the warp (converged): request the next stage of this warp's block.
+    __device__ __forceinline__ void issue(int stage) {
+        const int rows = stage_rows(req);
+        if (rows > 0) {
+            float* dst = stage_ptr(stage);
+            const float* src = zw + (size_t)req * D;
+            if (tma_ok(rows)) {
+                if (lane == 0) {
+                    mbar_expect_tx(&bar[stage], (uint32_t)rows * D * sizeof(float));
+                    bulk_g2s(dst, src, (uint32_t)rows * D * sizeof(float), &bar[stage]);
+                }
+            } else if constexpr (L::kVec4) {
+                const int nvec = rows * (D / 4);
+                const float4* src4 = reinterpret_cast<const float4*>(src);
+                for (int v = lane; v < nvec; v += 32) {
+                    const int row = v / (D / 4), c4 = v - row * (D / 4);
+                    if constexpr (kCpAsync) cp_async16(dst + row * L::LD + 4 * c4, src4 + v);
+                    else *reinterpret_cast<float4*>(dst + row * L::LD + 4 * c4) = ldg_stream4(src4 + v);
+                }
+            } else {
+                const int nf = rows * D;
+                for (int f = lane; f < nf; f += 32) {
+                    const int row = f / D, c = f - row * D;
+                    dst[row * L::LD + c] = ldg_stream(src + f);
+                }
+            }
+            req += rows;
+        }
+        if constexpr (kCpAsync) cp_async_commit();        // empty groups keep the per-thread count aligned
+    }
+    // After wait() returns every lane may read any row of the stage.  The awaited fill is the youngest
+    // group but STAGES-2 (a stage is refilled one stage late, see above).  Stages filled with plain stores
+    // were written at least one __syncwarp() ago.
+    __device__ __forceinline__ void wait(int stage, int rows) {
+        if constexpr (kCpAsync) {
+            cp_async_wait<STAGES - 2>();
+            __syncwarp();
+        } else if constexpr (L::kDense) {
+            if (tma_ok(rows)) {
+                mbar_wait(&bar[stage], (phase >> stage) & 1u);
+                phase ^= 1u << stage;
+            }
+        }
+    }
+};
+
+// rows per thread and stage of the register-blocked kernels: 2 stages x 8 warps x 32P rows x LD floats <= ~80 KB
+template <int D>
+__host__ __device__ constexpr int reg_ppt() {
+#ifdef SCC_REG_PPT
+    return SCC_REG_PPT;                 // A/B builds (make variant VFLAGS=-DSCC_REG_PPT=2)
+#else
+    return 40 / RowLayout<D>::LD > 4 ? 4 : (40 / RowLayout<D>::LD < 1 ? 1 : 40 / RowLayout<D>::LD);
+#endif
+}
+constexpr int kRegStages = 2;
+
+// Copy `rows` staged rows (row stride LD) of this warp to rows * D contiguous floats at dst, all lanes.
+template <int D>
+__device__ __forceinline__ void warp_copy_rows_out(const float* __restrict__ src, float* __restrict__ dst, int rows) {
+    using L = RowLayout<D>;
+    const int lane = threadIdx.x & 31;
+    if constexpr (L::kVec4) {
+        const int nvec = rows * (D / 4);
+        for (int v = lane; v < nvec; v += 32) {
+            const int row = v / (D / 4), c4 = v - row * (D / 4);
+            reinterpret_cast<float4*>(dst)[v] = *reinterpret_cast<const float4*>(src + row * L::LD + 4 * c4);
+        }
+    } else {
+        const int nf = rows * D;
+        for (int f = lane; f < nf; f += 32) {
+            const int row = f / D, c = f - row * D;
+            dst[f] = src[row * L::LD + c];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -528,202 +702,219 @@ __device__ __forceinline__ bool batch_view(DecArgs& a, int K) {
 }
 
 // ---------------------------------------------------------------------------
-// dec_grad, REG variant.  Per-thread accumulators: loss, sum s, W_j = sum_i c_ij,
-// B_jc = sum_i c_ij (z_ic - c0_c);  dmu_jc = -cs (B_jc - W_j (mu_jc - c0_c)).
-// For odd D the pad lane of the last float2 pair of the centred point is the constant 1, so W_j
-// accumulates in the pad lane of B_j for free (no separate registers / adds).
+// dec_grad, REG variant.  Per-thread accumulators (float2 over cluster pairs):
+//   B_jc = sum_i c_ij (z_ic - c0_c),  W_j = sum_i c_ij;   dmu_jc = -cs (B_jc - W_j (mu_jc - c0_c)).
 // stats out: [loss, sum_i s_i, dmu[K*D]]
+// MODE_STEP: the same persistent warps first run the assign pass over their rows, meet at a grid-wide barrier
+// that all-reduces f (over the CTAs and, multi-GPU, over NVLink), then run the target + gradient pass.
 // ---------------------------------------------------------------------------
+template <int D, int KP>
+__host__ __device__ constexpr int grad_reg_accumulators() { return 2 + KP * (D + 1); }
+
 template <int D, int KP, bool EXACT, bool ALPHA1, int MODE>
-__global__ void __launch_bounds__(kDecThreads, (2 + KP + 2 * KP * Pairs<D>::N) <= 100 ? 2 : 1)
+__global__ void __launch_bounds__(kRegThreads, grad_reg_accumulators<D, KP>() <= 100 ? 2 : 1)
 dec_grad_reg_kernel(const DecArgs a_in) {
-    constexpr int S = dec_stages<D>();
+    constexpr int S = kRegStages;
+    constexpr int P = reg_ppt<D>();
     constexpr int DP2 = Pairs<D>::N;
-    constexpr bool kPadW = (D & 1) != 0;
-    using Ring = WarpRing<D, kDecTile, S, kDecThreads>;
+    constexpr int JP = KP / 2;
+    constexpr int DW = D + 1;                                                // accumulator row: B_c (c < D), W
+    constexpr int NW = kRegThreads / 32;
+    using Stream = WarpStream<D, P, S>;
     using L = RowLayout<D>;
     constexpr int NV = 2 + KP + KP * D;                                      // [loss, sum s, W[KP], B[KP*D]]
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* ring_buf = reinterpret_cast<float*>(smem_raw);
-    // dz staging, per warp: dense row layouts ship the warp's 32 rows with a TMA bulk store from two
-    // alternating buffers; padded layouts keep one buffer and a coalesced copy by the warp's lanes
-    constexpr bool kBulkOut = L::kDense;
-    constexpr int NOUT = kBulkOut ? 2 : 1;
-    float* out_tile = ring_buf + S * Ring::kTileFloats;                      // [NOUT][TILE*LD]
-    float2* nmu2_s = reinterpret_cast<float2*>(out_tile + NOUT * Ring::kTileFloats);  // [KP][DP2]
-    float2* nmc2_s = nmu2_s + ((KP * DP2 + 1) & ~1);                         // [KP][DP2]
+    float* ring_buf = reinterpret_cast<float*>(smem_raw);                    // [NW][S][32P*LD]
+    float2* nmuT2 = reinterpret_cast<float2*>(ring_buf + ((NW * S * Stream::kStageFloats + 3) & ~3));   // [D][JP]
+    float2* nmc2_s = nmuT2 + ((D * JP + 1) & ~1);                            // [KP][DP2]
     float* mc_s = reinterpret_cast<float*>(nmc2_s + ((KP * DP2 + 1) & ~1));  // [KP*D]
     float* c0_s = mc_s + ((KP * D + 3) & ~3);                                // [D]
-    float* inv_f = c0_s + ((D + 3) & ~3);                                    // [KP]
-    float2* nc0_s = reinterpret_cast<float2*>(inv_f + ((KP + 3) & ~3));      // [DP2] -c0 pairs (pad lane: +1)
-    double* scratch = reinterpret_cast<double*>(nc0_s + ((DP2 + 1) & ~1));   // [reduce_scratch(NV)]
-    double* cta_stats = scratch + reduce_scratch(NV);                        // [NV]  (>= K*D + 2 + K)
+    float* inv_f = c0_s + ((D + 3) & ~3);                                    // [KP] (read as cluster pairs)
+    float2* nc0_s = reinterpret_cast<float2*>(inv_f + ((KP + 3) & ~3));      // [DP2] -c0 as dimension pairs
+    double* scratch = reinterpret_cast<double*>(nc0_s + ((DP2 + 1) & ~1));   // [reduce_scratch(NV, kRegThreads)]
+    double* cta_stats = scratch + reduce_scratch(NV, kRegThreads);                        // [NV]  (>= K*D + 2 + K)
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NV);            // [NW][S]
+    constexpr bool kBulkOut = L::kDense;
 
     const int K = EXACT ? KP : a_in.K;
-    Ring ring;
-    ring.init(ring_buf, bars, a_in.z, a_in.n);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Stream st;
+    st.init(ring_buf + warp * S * Stream::kStageFloats, bars + warp * S, a_in.z, a_in.n,
+            blockIdx.x * NW + warp, gridDim.x * NW);
     pdl_wait();                         // no global access before this point (see scc_common.cuh)
     DecArgs a_view = a_in;
     if (!batch_view<MODE, D>(a_view, K)) return;
     const DecArgs& a = (MODE == MODE_KMEANS) ? a_view : a_in;
     const float cs = grad_fold_scale<MODE>(a.scale, a.alpha);
     SCC_TL(a.timeline, 0);
-    const int G = gridDim.x;
 #pragma unroll
-    for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
-    load_grad_constants<D, KP>(a, K, cs, nmu2_s, nmc2_s, mc_s, c0_s, inv_f);
+    for (int s = 0; s < S; ++s) st.issue(s);
+    load_grad_constants<D, KP>(a, K, cs, nmuT2, nmc2_s, mc_s, c0_s, inv_f);
+    if (threadIdx.x < DP2)
+        nc0_s[threadIdx.x] = make_float2(-c0_s[2 * threadIdx.x], (2 * threadIdx.x + 1 < D) ? -c0_s[2 * threadIdx.x + 1] : 0.f);
     __syncthreads();
     SCC_TL(a.timeline, 1);
 
     const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
     const bool want_dz = a.dz != nullptr;
-    float sm[2 + (kPadW ? 0 : KP)];       // loss, sum s, (W_j when there is no pad lane)
-#pragma unroll
-    for (int s = 0; s < 2 + (kPadW ? 0 : KP); ++s) sm[s] = 0.f;
-    float2 B2[KP * DP2];                  // B_jc = sum_i c_ij (z_ic - c0_c), as pairs
-#pragma unroll
-    for (int s = 0; s < KP * DP2; ++s) B2[s] = make_float2(0.f, 0.f);
-    // -c0 as pairs, read back from shared memory once per tile (keeping them in registers costs
-    // 2*DP2 live registers the accumulators need)
-    if (threadIdx.x < DP2)
-        nc0_s[threadIdx.x] = make_float2(-c0_s[2 * threadIdx.x],
-                                         (2 * threadIdx.x + 1 < D) ? -c0_s[2 * threadIdx.x + 1] : 1.f);
-    __syncthreads();
-
-    const float* krows = krow_operand<MODE>(a);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int stage = 0, ob = 0;
+    const float2* inv_f2 = reinterpret_cast<const float2*>(inv_f);
 
     if constexpr (MODE == MODE_STEP) {
         // ---- pass 1 of the one-kernel DEC step: the assign pass (same arithmetic as dec_assign_kernel) over
-        // this CTA's tiles, then a grid-wide barrier + all-reduce of f, all CTAs co-resident (cooperative launch)
-        float facc[KP + 1];
+        // this warp's rows, then a grid-wide barrier + all-reduce of f, all CTAs co-resident (cooperative launch)
+        float2 facc2[JP];
 #pragma unroll
-        for (int j = 0; j <= KP; ++j) facc[j] = 0.f;
-        for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
-            const int np = ring.points(tile);
-            const bool active = (int)threadIdx.x < np;
-            ring.wait(stage, tile);
-            float zr[D];
-            if (active) load_row<D>(ring.stage_ptr(stage), threadIdx.x, zr);
-            __syncwarp();
-            ring.issue(stage, tile + S * G);
-            if (active) {
-                const size_t i = (size_t)tile * kDecTile + threadIdx.x;
-                float w[KP], u[KP], t[KP];
-                float2 z2[DP2];
-                pack_row<D>(zr, z2);
-                int label;
-                float best, tsum;
-                student_t_row<D, KP, EXACT, ALPHA1, true>(z2, nmu2_s, K, inv_alpha, expo, w, u, t, tsum, label, best);
-                const float inv = rcp_approx(tsum);
+        for (int jp = 0; jp < JP; ++jp) facc2[jp] = make_float2(0.f, 0.f);
+        float changed = 0.f;
+        int cons = 0, stage = 0, pending = -1;
+        while (cons < st.total) {
+            const int rows = st.stage_rows(cons);
+            st.wait(stage, rows);
+            const float* sp = st.stage_ptr(stage);
+            const int nsl = (rows + 31) >> 5;
+            for (int r = 0; r < nsl; ++r) {
+                const int row_in = 32 * r + lane;
+                if (row_in < rows) {
+                    const size_t i = (size_t)st.row_begin + (cons + row_in);
+                    float zr[1][D];
+                    load_row<D>(sp, row_in, zr[0]);
+                    float2 q2[1][JP];
+                    int label[1];
+                    soft_assign_rows<D, KP, EXACT, ALPHA1, 1>(zr, nmuT2, K, inv_alpha, expo, a.round5 != 0, q2, label);
 #pragma unroll
-                for (int j = 0; j < KP; ++j) {
-                    float q = t[j] * inv;
-                    if (a.round5) q = round_dec5(q);
-                    t[j] = q;
-                    facc[j] += q;
+                    for (int jp = 0; jp < JP; ++jp) facc2[jp] = __fadd2_rn(facc2[jp], q2[0][jp]);
+                    if (a.q) store_krow2<KP, EXACT>(a.q + i * K, K, q2[0]);
+                    if (a.labels) a.labels[i] = label[0];
+                    if (a.labels_prev) changed += (a.labels_prev[i] != label[0]) ? 1.f : 0.f;
                 }
-                if (a.q) store_krow<KP, EXACT>(a.q + i * K, K, t);
-                if (a.labels) a.labels[i] = label;
-                if (a.labels_prev) facc[KP] += (a.labels_prev[i] != label) ? 1.f : 0.f;
+                if (r == 0 && pending >= 0) {           // refill the stage consumed before this one
+                    __syncwarp();
+                    st.issue(pending);
+                    pending = -1;
+                }
             }
+            __syncwarp();                               // every lane has its rows of this stage in registers
+            cons += rows;
+            pending = stage;
             if (++stage == S) stage = 0;
         }
         SCC_TL(a.timeline, 6);                                     // pass 1 main loop done
-        // pass 2's first tiles are requested before the grid barrier: they land while the CTAs wait
+        // pass 2's first stages are requested before the grid barrier: they land while the CTAs wait
+        st.rewind();
 #pragma unroll
-        for (int s = 0; s < S; ++s) ring.issue((stage + s) % S, blockIdx.x + s * G);
+        for (int s = 0; s < S; ++s) st.issue(s);
         __syncthreads();
+        float facc[KP + 1];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) facc[j] = (j & 1) ? facc2[j / 2].y : facc2[j / 2].x;
+        facc[KP] = changed;
         double* f_s = cta_stats;                                   // [K+1] (cta_stats is free until the tail)
         double* mine_s = cta_stats + ((KP + 2) & ~1);              // [KP+1] this CTA's sums
-        cta_reduce<KP + 1, kDecThreads>(facc, scratch, mine_s);
+        cta_reduce<KP + 1, kRegThreads>(facc, scratch, mine_s);
         if (!EXACT) {
             if (threadIdx.x == 0 && K < KP) mine_s[K] = mine_s[KP];
             __syncthreads();
         }
-        const int sp_tail = (K * D + 2 + 1) & ~1;                  // pass-1 slots live behind the tail's slots
+        const int sp_tail = (K * D + 2 + 1) & ~1;                  // the world's f lives behind the tail's slots
         const PeerCtx ex1{a.ex_windows, a.ex_rank, a.ex_world, a.ex_max_len};
-        grid_barrier_sum<kDecThreads>(mine_s, K + 1, a.partials + (size_t)gridDim.x * sp_tail, a.counter + 1, f_s,
-                                      scratch, &ex1);
+        // f_j and the label-change count are sums of values in [0, 1] over at most n points: fixed point with
+        // 2^shift * n < 2^62, accumulated with integer atomics in the workspace header (bit-reproducible)
+        const int shift = 61 - (64 - __clzll((long long)(a.n > 0 ? a.n : 1)));
+        unsigned long long* fix = reinterpret_cast<unsigned long long*>(a.counter) + kFixOffset;
+        grid_barrier_sum_fixed<kRegThreads>(mine_s, K + 1, fix, a.counter + 1, f_s, ldexp(1.0, shift), ldexp(1.0, -shift),
+                                            a.partials + (size_t)gridDim.x * sp_tail, &ex1);
         if (threadIdx.x < KP) inv_f[threadIdx.x] = ((int)threadIdx.x < K) ? (float)(1.0 / f_s[threadIdx.x]) : 0.f;
         if (blockIdx.x == 0 && (int)threadIdx.x <= K && a.f_out) a.f_out[threadIdx.x] = f_s[threadIdx.x];
         __syncthreads();
         SCC_TL(a.timeline, 7);                                     // grid barrier + f all-reduce done
     }
 
-    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {       // no CTA-wide barrier in this loop
-        const int np = ring.points(tile);
-        const bool active = (int)threadIdx.x < np;
-        // the [n, K] operand row (target p / upstream dL/dq) is requested before the wait on the z tile
-        float kcur[KP];
+    const float* krows = krow_operand<MODE>(a);
+    float sm[2] = {0.f, 0.f};             // loss, sum s
+    float2 B2[JP * DW];                   // (B_2jp,c , B_2jp+1,c) for c < D, then (W_2jp, W_2jp+1)
 #pragma unroll
-        for (int j = 0; j < KP; ++j) kcur[j] = 0.f;
-        prefetch_krow<KP, EXACT>(krows, (int64_t)tile * kDecTile, np, K, kcur);
-        ring.wait(stage, tile);
-        if (tile == (int)blockIdx.x) SCC_TL(a.timeline, 2);
-        float zr[D];
-        if (active) load_row<D>(ring.stage_ptr(stage), threadIdx.x, zr);
-        __syncwarp();                    // the warp's rows are in registers (and its previous dz rows copied out)
-        ring.issue(stage, tile + S * G);
-        float* out_cur = out_tile + ob * Ring::kTileFloats;
-        if (active) {
-            const size_t i = (size_t)tile * kDecTile + threadIdx.x;
-            float w[KP], u[KP], t[KP], coef[KP];
-            float2 z2[DP2];
-            pack_row<D>(zr, z2);
-            int label;
-            float best, tsum;
-            student_t_row<D, KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(z2, nmu2_s, K, inv_alpha, expo, w, u, t, tsum,
-                                                                     label, best);
-            grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f, w, u, t, tsum, expo, label, best, kcur, coef,
-                                                       sm[0], sm[1]);
-            if constexpr (!kPadW) {
+    for (int s = 0; s < JP * DW; ++s) B2[s] = make_float2(0.f, 0.f);
+    {   // ---- gradient pass: no CTA-wide barrier in this loop
+        int cons = 0, stage = 0, pending = -1;
+        bool first = true;
+        while (cons < st.total) {
+            const int rows = st.stage_rows(cons);
+            st.wait(stage, rows);
+            if (first) { SCC_TL(a.timeline, 2); first = false; }
+            float* sp = st.stage_ptr(stage);
+            const int nsl = (rows + 31) >> 5;
+            for (int r = 0; r < nsl; ++r) {
+                const int row_in = 32 * r + lane;
+                if (row_in < rows) {
+                    const size_t i = (size_t)st.row_begin + (cons + row_in);
+                    // the [n, K] operand row (target p / upstream dL/dq) is requested before the z row is read
+                    float2 pre2[JP];
 #pragma unroll
-                for (int j = 0; j < KP; ++j) sm[2 + j] += coef[j];
-            }
+                    for (int jp = 0; jp < JP; ++jp) pre2[jp] = make_float2(0.f, 0.f);
+                    if (krows) load_krow2<KP, EXACT>(krows + i * K, K, pre2);
+                    float zr[1][D];
+                    load_row<D>(sp, row_in, zr[0]);
+                    float2 acc2[1][JP], w2[JP], u2[JP], t2[JP], coef2[JP];
+                    sq_distances<D, KP, 1>(zr, nmuT2, acc2);
+                    int label;
+                    float best, tsum;
+                    student_t_pairs<KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(acc2[0], K, inv_alpha, expo, w2, u2, t2, tsum,
+                                                                            label, best);
+                    grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f2, w2, u2, t2, tsum, expo, label, best, pre2,
+                                                               coef2, sm[0], sm[1]);
+                    // the row is read a second time for the accumulation phase: keeping it in registers across the
+                    // coefficient phase costs D registers the 128-register budget does not have (spills)
+                    asm volatile("" ::: "memory");
+                    float zb[D];
+                    load_row<D>(sp, row_in, zb);
+                    float2 zc2[DP2];                               // centred point as dimension pairs
 #pragma unroll
-            for (int c = 0; c < DP2; ++c) z2[c] = __fadd2_rn(z2[c], nc0_s[c]);     // centred point (pad lane: 1)
+                    for (int c = 0; c < DP2; ++c)
+                        zc2[c] = __fadd2_rn(make_float2(zb[2 * c], (2 * c + 1 < D) ? zb[2 * c + 1] : 0.f), nc0_s[c]);
 #pragma unroll
-            for (int j = 0; j < KP; ++j) {
-                if (EXACT || j < K) {
-                    const float2 cj = splat2(coef[j]);
+                    for (int c = 0; c < D; ++c) {
+                        const float zc = (c & 1) ? zc2[c >> 1].y : zc2[c >> 1].x;
 #pragma unroll
-                    for (int c = 0; c < DP2; ++c) B2[j * DP2 + c] = __ffma2_rn(cj, z2[c], B2[j * DP2 + c]);
+                        for (int jp = 0; jp < JP; ++jp)
+                            B2[jp * DW + c] = __ffma2_rn(coef2[jp], make_float2(zc, zc), B2[jp * DW + c]);
+                    }
+#pragma unroll
+                    for (int jp = 0; jp < JP; ++jp) B2[jp * DW + D] = __fadd2_rn(B2[jp * DW + D], coef2[jp]);
+                    if (want_dz) {
+                        float2 c2 = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int jp = 0; jp < JP; ++jp) c2 = __fadd2_rn(c2, coef2[jp]);
+                        float dzr[D];
+                        dz_from_coefficients<D, KP, EXACT>(zc2, coef2, cs * (c2.x + c2.y), nmc2_s, K, dzr);
+                        store_row<D>(sp, row_in, dzr);             // in place: the z row is in registers
+                    }
+                }
+                if (r == 0 && pending >= 0) {           // refill the stage consumed before this one: its dz store
+                    if (kBulkOut && want_dz && lane == 0) bulk_wait_read0();     // has read shared memory by now
+                    __syncwarp();
+                    st.issue(pending);
+                    pending = -1;
                 }
             }
             if (want_dz) {
-                float cs2[2] = {0.f, 0.f};
-#pragma unroll
-                for (int j = 0; j < KP; ++j) cs2[j & 1] += coef[j];
-                float dzr[D];
-                dz_from_coefficients<D, KP, EXACT>(z2, coef, cs * (cs2[0] + cs2[1]), nmc2_s, K, dzr);
-                store_row<D>(out_cur, threadIdx.x, dzr);
-            }
-        }
-        if (want_dz) {
-            const int nv = (np == kDecTile) ? 32 : ring.slice_rows(np, 0);
-            const float* src_w = out_cur + 32 * warp * L::LD;
-            float* dst_w = a.dz + ((size_t)tile * kDecTile + 32 * warp) * D;
-            if (kBulkOut && (np == kDecTile || Ring::tma_ok(nv))) {
-                // the warp's rows -> async proxy -> one bulk store by lane 0.  wait_group.read 1 leaves this
-                // store in flight but guarantees the previous one has finished reading the OTHER buffer,
-                // which the warp overwrites after the next iteration's __syncwarp().
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    bulk_s2g(dst_w, src_w, (uint32_t)nv * D * sizeof(float));
-                    bulk_commit();
-                    bulk_wait_read<1>();
+                float* dst = a.dz + ((size_t)st.row_begin + cons) * D;
+                if (kBulkOut && Stream::tma_ok(rows)) {
+                    fence_proxy_async();                // the warp's dz rows -> async proxy -> one bulk store by lane 0
+                    __syncwarp();
+                    if (lane == 0) {
+                        bulk_s2g(dst, sp, (uint32_t)rows * D * sizeof(float));
+                        bulk_commit();
+                    }
+                } else {
+                    __syncwarp();
+                    warp_copy_rows_out<D>(sp, dst, rows);
                 }
-                ob ^= 1;
-            } else if (nv > 0) {
-                __syncwarp();
-                warp_copy_rows_out<D>(src_w, dst_w, nv);
             }
+            __syncwarp();
+            cons += rows;
+            pending = stage;
+            if (++stage == S) stage = 0;
         }
-        if (++stage == S) stage = 0;
     }
     if (kBulkOut && lane == 0) bulk_wait0();             // this warp's dz stores are complete
     pdl_trigger();                      // successor may start its prologue under our reduction tail
@@ -732,20 +923,18 @@ dec_grad_reg_kernel(const DecArgs a_in) {
     float acc[NV];
     acc[0] = sm[0]; acc[1] = sm[1];
 #pragma unroll
-    for (int j = 0; j < KP; ++j) {
-        if constexpr (kPadW) acc[2 + j] = B2[j * DP2 + DP2 - 1].y;
-        else acc[2 + j] = sm[2 + (kPadW ? 0 : j)];
-    }
+    for (int j = 0; j < KP; ++j) acc[2 + j] = (j & 1) ? B2[(j / 2) * DW + D].y : B2[(j / 2) * DW + D].x;
 #pragma unroll
     for (int j = 0; j < KP; ++j)
 #pragma unroll
         for (int c = 0; c < D; ++c)
-            acc[2 + KP + j * D + c] = (c & 1) ? B2[j * DP2 + (c >> 1)].y : B2[j * DP2 + (c >> 1)].x;
+            acc[2 + KP + j * D + c] = (j & 1) ? B2[(j / 2) * DW + c].y : B2[(j / 2) * DW + c].x;
     __syncthreads();
-    cta_reduce<NV, kDecThreads>(acc, scratch, cta_stats);
+    cta_reduce<NV, kRegThreads>(acc, scratch, cta_stats);
     SCC_TL(a.timeline, 4);
     // dmu_jc = -cs (B_jc - W_j (mu_jc - c0_c)), compacted to [loss, sum s, dmu[K*D]]
     // (MODE_KMEANS: [inertia, 0, sum_{i in j} (z_i - mu_j) [K*D], counts[K]])
+    static_assert(KP * D <= kRegThreads, "one thread per statistic in the tail");
     double dmu = 0.0, wj = 0.0;
     const int o = threadIdx.x;
     if (o < K * D) dmu = -(double)cs * (cta_stats[2 + KP + o] - cta_stats[2 + o / D] * (double)mc_s[o]);
@@ -755,9 +944,12 @@ dec_grad_reg_kernel(const DecArgs a_in) {
     if (MODE == MODE_KMEANS && o < K) cta_stats[2 + K * D + o] = wj;
     __syncthreads();
     const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
-    const bool last = grid_publish<kDecThreads, 25>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials,
+    const bool last = grid_publish<kRegThreads, 25>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials,
                                                     a.counter, a.stats, scratch, &push, a.ex_push);
-    if (MODE == MODE_STEP && last && threadIdx.x == 0) a.counter[1] = 0u;    // every CTA is past the pass-1 barrier
+    if (MODE == MODE_STEP && last) {                                          // every CTA is past the pass-1 barrier
+        if (threadIdx.x == 0) a.counter[1] = 0u;
+        if ((int)threadIdx.x <= K) reinterpret_cast<unsigned long long*>(a.counter)[kFixOffset + threadIdx.x] = 0ull;
+    }
     SCC_TL(a.timeline, 5);
 }
 
@@ -786,8 +978,9 @@ dec_grad_tiled_kernel(const DecArgs a_in) {
     float* out_tile = ring_buf + S * Ring::kTileFloats;      // [TILE*LD] dz staging
     float* w_tile = out_tile + Ring::kTileFloats;            // [TILE*KP] coefficients
     constexpr int DP2 = Pairs<D>::N;
-    float2* nmu2_s = reinterpret_cast<float2*>(w_tile + kDecTile * KP);      // [KP][DP2]
-    float2* nmc2_s = nmu2_s + KP * DP2;                      // [KP][DP2]
+    constexpr int JP = KP / 2;
+    float2* nmuT2 = reinterpret_cast<float2*>(w_tile + kDecTile * KP);       // [D][JP] (D even: same size as [KP][DP2])
+    float2* nmc2_s = nmuT2 + D * JP;                         // [KP][DP2]
     float* mc_s = reinterpret_cast<float*>(nmc2_s + KP * DP2);               // [KP*D]
     float* c0_s = mc_s + KP * D;                             // [D]
     float* inv_f = c0_s + D;                                 // [KP]
@@ -808,11 +1001,12 @@ dec_grad_tiled_kernel(const DecArgs a_in) {
     const int G = gridDim.x;
 #pragma unroll
     for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
-    load_grad_constants<D, KP>(a, K, cs, nmu2_s, nmc2_s, mc_s, c0_s, inv_f);
+    load_grad_constants<D, KP>(a, K, cs, nmuT2, nmc2_s, mc_s, c0_s, inv_f);
     __syncthreads();
 
     const float inv_alpha = 1.f / a.alpha, expo = 0.5f * (a.alpha + 1.f);
     const bool want_dz = a.dz != nullptr;
+    const float2* inv_f2 = reinterpret_cast<const float2*>(inv_f);
     float2 nc0[DP2];
 #pragma unroll
     for (int c = 0; c < DP2; ++c) nc0[c] = make_float2(-c0_s[2 * c], -c0_s[2 * c + 1]);
@@ -834,47 +1028,51 @@ dec_grad_tiled_kernel(const DecArgs a_in) {
     for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
         const int np = ring.points(tile);
         const int64_t base = (int64_t)tile * kDecTile;
-        float kcur[KP];
-#pragma unroll
-        for (int j = 0; j < KP; ++j) kcur[j] = 0.f;
-        prefetch_krow<KP, EXACT>(krows, base, np, K, kcur);
-        ring.wait(stage, tile, use);
         const bool active = (int)threadIdx.x < np;
-        float* ztile = ring.stage_ptr(stage);
-        float coef[KP];
+        float2 pre2[JP];
 #pragma unroll
-        for (int j = 0; j < KP; ++j) coef[j] = 0.f;
+        for (int jp = 0; jp < JP; ++jp) pre2[jp] = make_float2(0.f, 0.f);
+        // the [n, K] operand row (target p / upstream dL/dq) is requested before the wait on the z tile
+        if (krows && active) load_krow2<KP, EXACT>(krows + ((size_t)base + threadIdx.x) * K, K, pre2);
+        ring.wait(stage, tile, use);
+        float* ztile = ring.stage_ptr(stage);
+        float2 coef2[JP];
+#pragma unroll
+        for (int jp = 0; jp < JP; ++jp) coef2[jp] = make_float2(0.f, 0.f);
         if (active) {
-            float zr[D];
-            load_row<D>(ztile, threadIdx.x, zr);
+            float zr[1][D];
+            load_row<D>(ztile, threadIdx.x, zr[0]);
             const size_t i = (size_t)base + threadIdx.x;
-            float w[KP], u[KP], t[KP];
-            float2 z2[DP2];
-            pack_row<D>(zr, z2);
+            float2 acc2[1][JP], w2[JP], u2[JP], t2[JP];
+            sq_distances<D, KP, 1>(zr, nmuT2, acc2);
             int label;
             float best, tsum;
-            student_t_row<D, KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(z2, nmu2_s, K, inv_alpha, expo, w, u, t, tsum,
-                                                                     label, best);
-            grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f, w, u, t, tsum, expo, label, best, kcur, coef,
+            student_t_pairs<KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(acc2[0], K, inv_alpha, expo, w2, u2, t2, tsum,
+                                                                    label, best);
+            grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f2, w2, u2, t2, tsum, expo, label, best, pre2, coef2,
                                                        small[0], small[1]);
-            float csum = 0.f;
+            float2 c2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < KP; ++j) { small[2 + j] += coef[j]; csum += coef[j]; }
+            for (int jp = 0; jp < JP; ++jp) {
+                small[2 + 2 * jp] += coef2[jp].x; small[3 + 2 * jp] += coef2[jp].y;
+                c2 = __fadd2_rn(c2, coef2[jp]);
+            }
+            float2 z2[DP2];
 #pragma unroll
-            for (int c = 0; c < DP2; ++c) z2[c] = __fadd2_rn(z2[c], nc0[c]);
+            for (int c = 0; c < DP2; ++c) z2[c] = __fadd2_rn(make_float2(zr[0][2 * c], zr[0][2 * c + 1]), nc0[c]);
 #pragma unroll
-            for (int c = 0; c < D; ++c) zr[c] = (c & 1) ? z2[c >> 1].y : z2[c >> 1].x;
-            store_row<D>(ztile, threadIdx.x, zr);     // own row, centred, for phase 2
+            for (int c = 0; c < D; ++c) zr[0][c] = (c & 1) ? z2[c >> 1].y : z2[c >> 1].x;
+            store_row<D>(ztile, threadIdx.x, zr[0]);  // own row, centred, for phase 2
             if (want_dz) {
                 float dzr[D];
-                dz_from_coefficients<D, KP, EXACT>(z2, coef, cs * csum, nmc2_s, K, dzr);
+                dz_from_coefficients<D, KP, EXACT>(z2, coef2, cs * (c2.x + c2.y), nmc2_s, K, dzr);
                 store_row<D>(out_tile, threadIdx.x, dzr);
             }
         }
 #pragma unroll
         for (int j = 0; j < KP; j += 4)
             *reinterpret_cast<float4*>(w_tile + threadIdx.x * KP + j) =
-                make_float4(coef[j], coef[j + 1], coef[j + 2], coef[j + 3]);
+                make_float4(coef2[j / 2].x, coef2[j / 2].y, coef2[j / 2 + 1].x, coef2[j / 2 + 1].y);
         __syncthreads();
         if (want_dz) copy_tile_out<D, kDecThreads>(out_tile, a.dz + (size_t)base * D, np);
         if (p2_active) {
@@ -932,18 +1130,18 @@ dec_grad_tiled_kernel(const DecArgs a_in) {
 template <int D, int KP>
 constexpr size_t assign_smem() {
     constexpr int S = assign_stages<D, KP>();
-    return sizeof(float) * (S * kDecTile * assign_ppt<D, KP>() * RowLayout<D>::LD + 2 * ((KP * Pairs<D>::N + 1) & ~1)) +
+    return sizeof(float) * (((S * kDecTile * assign_ppt<D, KP>() * RowLayout<D>::LD + 3) & ~3) + 2 * ((D * (KP / 2) + 1) & ~1)) +
            sizeof(double) * (KP + 1) + sizeof(uint64_t) * S;
 }
 template <int D, int KP>
 constexpr size_t grad_reg_smem() {
-    constexpr int S = dec_stages<D>();
+    constexpr int S = kRegStages, P = reg_ppt<D>(), NW = kRegThreads / 32;
     constexpr int NV = 2 + KP + KP * D;
-    constexpr int SCR = reduce_scratch(NV);
-    return sizeof(float) * ((S + (RowLayout<D>::kDense ? 2 : 1)) * kDecTile * RowLayout<D>::LD +
-                            4 * ((KP * Pairs<D>::N + 1) & ~1) +
+    constexpr int SCR = reduce_scratch(NV, kRegThreads);
+    return sizeof(float) * (((NW * S * 32 * P * RowLayout<D>::LD + 3) & ~3) + 2 * ((D * (KP / 2) + 1) & ~1) +
+                            2 * ((KP * Pairs<D>::N + 1) & ~1) +
                             ((KP * D + 3) & ~3) + ((D + 3) & ~3) + ((KP + 3) & ~3) + 2 * ((Pairs<D>::N + 1) & ~1)) +
-           sizeof(double) * (SCR + NV) + sizeof(uint64_t) * S * (kDecThreads / 32);
+           sizeof(double) * (SCR + NV) + sizeof(uint64_t) * S * NW;
 }
 template <int D, int KP>
 constexpr size_t grad_tiled_smem() {
@@ -965,9 +1163,9 @@ constexpr size_t grad_tiled_smem() {
 
 template <typename Kern>
 static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t stream, int tile_points = kDecTile,
-                      bool cooperative = false) {
+                      bool cooperative = false, int threads = kDecThreads) {
     const int64_t num_tiles = (args.n + tile_points - 1) / tile_points;
-    int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), kDecThreads, smem, kMaxCtasPerSm);
+    int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), threads, smem, kMaxCtasPerSm);
     if (grid < 0) return (int)grid;
     if (grid > kMaxDecGrid) grid = kMaxDecGrid;
     if (grid > num_tiles) grid = num_tiles;
@@ -975,7 +1173,7 @@ static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t 
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid, args.batch > 0 ? (unsigned)args.batch : 1u);
-    cfg.blockDim = dim3(kDecThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1014,8 +1212,8 @@ struct DecOps {
             else
                 return SCC_ERR_UNSUPPORTED;
         } else {
-            return launch_dec(dec_grad_reg_kernel<D, KP, EXACT, A1, MODE>, a, grad_reg_smem<D, KP>(), st, kDecTile,
-                              MODE == MODE_STEP);
+            return launch_dec(dec_grad_reg_kernel<D, KP, EXACT, A1, MODE>, a, grad_reg_smem<D, KP>(), st, kRegThreads,
+                              MODE == MODE_STEP, kRegThreads);
         }
     }
     template <int MODE>

@@ -151,7 +151,7 @@ int gmm_em_step(const float* z, int64_t n, int d, int K, const float* params, do
                 void* ws, size_t ws_bytes, cudaStream_t st) {
     if ((!z && n > 0) || !params || !stats || n < 0) return SCC_ERR_INVALID;
     if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return SCC_ERR_INVALID;
-    if (mode < 0 || mode > 2) return SCC_ERR_INVALID;
+    if (mode < 0 || (mode & 3) > 2 || (mode & ~(3 | SCC_GMM_NOSKIP))) return SCC_ERR_INVALID;
     if (!gmm_supported(d, K)) return SCC_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(z) & 15u) != 0) return SCC_ERR_MISALIGNED;
     if (!ws || ws_bytes < workspace_bytes(d, K)) return SCC_ERR_WORKSPACE;

@@ -146,7 +146,7 @@ gmm_em_full_kernel(const GmmArgs a) {
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
                 float r = (active && k < K) ? expf(lp[k] - lse) : 0.f;
-                if (a.accumulate == SCC_GMM_HARD) r = (active && k == label) ? 1.f : 0.f;
+                if ((a.accumulate & 3) == SCC_GMM_HARD) r = (active && k == label) ? 1.f : 0.f;
                 r_s[k * TILE + threadIdx.x] = r;
                 lp[k] = r;
             }
@@ -162,7 +162,7 @@ gmm_em_full_kernel(const GmmArgs a) {
         }
         __syncthreads();
         // ---------------- phase 2: moments of component kc over the tile ----------------
-        if (a.accumulate && kc < K) {
+        if ((a.accumulate & 3) && kc < K) {
             for (int t = lane; t < np; t += 32) {
                 const float r = r_s[kc * TILE + t];
                 float df[D];
@@ -184,7 +184,7 @@ gmm_em_full_kernel(const GmmArgs a) {
         __syncthreads();
         ring.issue(stage, tile + S * G);
     }
-    if (a.accumulate) flush();
+    if (a.accumulate & 3) flush();
     {
         const float w = warp_sum(loglik);
         if (lane == 0) ll_s[warp] = (double)w;
@@ -399,7 +399,7 @@ gmm_em_packed_kernel(const GmmArgs a) {
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
                 float r = (active && k < K) ? expf(lp[k] - lse) : 0.f;
-                if (a.accumulate == SCC_GMM_HARD) r = (active && k == label) ? 1.f : 0.f;
+                if ((a.accumulate & 3) == SCC_GMM_HARD) r = (active && k == label) ? 1.f : 0.f;
                 r_s[k * TILE + threadIdx.x] = r;
                 lp[k] = r;
             }
@@ -415,7 +415,7 @@ gmm_em_packed_kernel(const GmmArgs a) {
         }
         __syncthreads();
         // ---------------- phase 2 ----------------
-        if (a.accumulate && kc < K) {
+        if ((a.accumulate & 3) && kc < K) {
             for (int t = lane; t < np; t += 32) {
                 const float r = r_s[kc * TILE + t];
                 float xr[D];
@@ -444,7 +444,7 @@ gmm_em_packed_kernel(const GmmArgs a) {
         __syncthreads();
         ring.issue(stage, tile + S * G);
     }
-    if (a.accumulate) flush();
+    if (a.accumulate & 3) flush();
     {
         const float w = warp_sum(loglik);
         if (lane == 0) ll_s[warp] = (double)w;
@@ -480,6 +480,268 @@ constexpr size_t gmm_packed_smem() {
            sizeof(double) * (KP * NM + KP + 1 + KP * NM) + sizeof(uint64_t) * S;
 }
 
+// ---------------------------------------------------------------------------
+// SPARSE variant of the d <= 12 kernel (default).  Same two phases as gmm_em_full_kernel, with the two
+// changes that matter for the instruction count (profiles/: the full kernel issues ~3600 thread-instructions
+// per point for 1872 algorithmic FMAs at d = 9, K = 16, LSU 37 %):
+//   E-step:  packed FP32 over COMPONENT PAIRS (2kp, 2kp+1): df2_c = (x_c - mu_kc, x_c - mu_k'c) with the point's
+//            coordinate in the .F32 broadcast operand, y2_b = sum_c df2_c * (U_k[c][b], U_k'[c][b]) — every
+//            FADD2/FFMA2 does two components' work and every 128-bit shared-memory load feeds four FMAs; no pad
+//            lane for odd d (the pair is over k, not over the dimension).  Responsibilities come from ONE
+//            exponential per component (e_k = 2^((lp_k - max) log2 e), r_k = e_k / sum e) instead of two.
+//   M-step:  responsibility-sparsity skip (lever c).  After the first few EM iterations only ~1.4 of
+//            16 components per point have r_ik >= 2^-30; pairs below that contribute < 1e-9 relative to any
+//            moment.  Phase 1 ballots (r_ik >= 2^-30) per component; the warp masks are turned into per-component
+//            COMPACT point lists (positions from a prefix over the source warps: point order, deterministic) and
+//            the component's warp sweeps only its list, all 32 lanes busy.  SCC_GMM_NOSKIP keeps every pair.
+// ---------------------------------------------------------------------------
+constexpr float kGmmSkipThreshold = 9.313225746154785e-10f;       // 2^-30
+
+template <int D, int KP>
+__global__ void __launch_bounds__(32 * KP, 1)
+gmm_em_sparse_kernel(const GmmArgs a) {
+    constexpr int NT = 32 * KP;
+    constexpr int TILE = NT;
+    constexpr int S = 3;
+    constexpr int NW = KP;                                 // warps per CTA == components
+    constexpr int JP = KP / 2;                             // component pairs
+    constexpr int TRI = tri(D);
+    constexpr int TRIP = (TRI + 1) & ~1;                   // U pairs per component pair, padded to 16 bytes
+    constexpr int DP = (D + 1) & ~1;
+    constexpr int NM = 1 + D + TRI;
+    constexpr int FLUSH = 16;
+    using Ring = ZRing<D, TILE, S, NT>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring_buf = reinterpret_cast<float*>(smem_raw);
+    float* r_s = ring_buf + ((S * Ring::kTileFloats + 3) & ~3);            // [KP][TILE]
+    float2* nmu2_s = reinterpret_cast<float2*>(r_s + KP * TILE);           // [JP][DP]    -mu pairs over components
+    float2* u2_s = nmu2_s + JP * DP;                                       // [JP][TRIP]  U pairs
+    float2* cst2_s = u2_s + JP * TRIP;                                     // [JP]
+    float* muk_s = reinterpret_cast<float*>(cst2_s + ((JP + 1) & ~1));     // [KP][D] means (phase 2)
+    double* mom_s = reinterpret_cast<double*>(muk_s + ((KP * D + 3) & ~3));   // [KP][NM]
+    double* ll_s = mom_s + KP * NM;                                        // [KP]
+    double* cta_stats = ll_s + KP;                                         // [1 + KP*NM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + 1 + KP * NM); // [S]
+    unsigned int* mask_s = reinterpret_cast<unsigned int*>(bars + S);      // [KP][NW] ballot of (r >= thr) per source warp
+    int* pref_s = reinterpret_cast<int*>(mask_s + KP * NW);                // [KP][NW + 1] exclusive prefix, total
+    unsigned short* list_s = reinterpret_cast<unsigned short*>(pref_s + KP * (NW + 1));   // [KP][TILE]
+
+    if (a.ctrl && a.ctrl[5] != 0.0) return;              // frozen fit: converged or failed earlier
+
+    const int K = a.K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {   // parameters -> component-pair layouts
+        float* nmu = reinterpret_cast<float*>(nmu2_s);
+        for (int i = threadIdx.x; i < JP * DP * 2; i += NT) {
+            const int kp = i / (2 * DP), e = i - kp * (2 * DP), c = e >> 1, k = 2 * kp + (e & 1);
+            nmu[i] = (k < K && c < D) ? -a.params[k * D + c] : 0.f;
+        }
+        float* u2 = reinterpret_cast<float*>(u2_s);
+        for (int i = threadIdx.x; i < JP * TRIP * 2; i += NT) {
+            const int kp = i / (2 * TRIP), e = i - kp * (2 * TRIP), t = e >> 1, k = 2 * kp + (e & 1);
+            u2[i] = (k < K && t < TRI) ? a.params[K * D + k * TRI + t] : 0.f;
+        }
+        float* cst = reinterpret_cast<float*>(cst2_s);
+        if (threadIdx.x < KP) cst[threadIdx.x] = ((int)threadIdx.x < K) ? a.params[K * D + K * TRI + threadIdx.x] : 0.f;
+        for (int i = threadIdx.x; i < KP * D; i += NT) muk_s[i] = (i < K * D) ? a.params[i] : 0.f;
+        for (int i = threadIdx.x; i < KP * NM; i += NT) mom_s[i] = 0.0;
+    }
+    const float thr = (a.accumulate & SCC_GMM_NOSKIP) ? 0.f : kGmmSkipThreshold;
+    const int acc_mode = a.accumulate & 3;
+
+    Ring ring;
+    ring.init(ring_buf, bars, a.z, a.n);
+    __syncthreads();
+    const int G = gridDim.x;
+#pragma unroll
+    for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
+    __syncthreads();
+
+    // phase-2 state of this warp's component
+    const int kc = warp;
+    float muk[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) muk[c] = muk_s[kc * D + c];
+    float mom[NM];
+#pragma unroll
+    for (int s = 0; s < NM; ++s) mom[s] = 0.f;
+    float loglik = 0.f;
+
+    auto flush = [&]() {
+        if (kc < K) {
+#pragma unroll
+            for (int s = 0; s < NM; ++s) {
+                const float w = warp_sum(mom[s]);
+                if (lane == 0) mom_s[kc * NM + s] += (double)w;
+                mom[s] = 0.f;
+            }
+        }
+    };
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G, ++it) {
+        const int stage = it % S;
+        ring.wait(stage, tile, (uint32_t)(it / S));
+        const int np = ring.points(tile);
+        const float* ztile = ring.stage_ptr(stage);
+        // ---------------- phase 1: E-step for point threadIdx.x ----------------
+        const bool active = (int)threadIdx.x < np;
+        float2 r2[JP];
+#pragma unroll
+        for (int kp = 0; kp < JP; ++kp) r2[kp] = make_float2(0.f, 0.f);
+        int label = 0;
+        if (active) {
+            float x[D];
+            load_row<D>(ztile, threadIdx.x, x);
+            float2 lp2[JP];
+#pragma unroll
+            for (int kp = 0; kp < JP; ++kp) {
+                lp2[kp] = make_float2(-3.4e38f, -3.4e38f);
+                if (2 * kp < K) {
+                    float2 df2[D];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) df2[c] = __fadd2_rn(make_float2(x[c], x[c]), nmu2_s[kp * DP + c]);
+                    float2 m2 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int b = 0; b < D; ++b) {
+                        float2 y2 = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int c = 0; c <= b; ++c) y2 = __ffma2_rn(df2[c], u2_s[kp * TRIP + tri(b) + c], y2);
+                        m2 = __ffma2_rn(y2, y2, m2);
+                    }
+                    float2 v = __ffma2_rn(make_float2(-0.5f, -0.5f), m2, cst2_s[kp]);
+                    if (2 * kp + 1 >= K) v.y = -3.4e38f;
+                    lp2[kp] = v;
+                }
+            }
+            float best = -3.4e38f;
+#pragma unroll
+            for (int kp = 0; kp < JP; ++kp) {
+                if (lp2[kp].x > best) { best = lp2[kp].x; label = 2 * kp; }
+                if (lp2[kp].y > best) { best = lp2[kp].y; label = 2 * kp + 1; }
+            }
+            // e_k = exp(lp_k - best) once per component; r_k = e_k / sum_k e_k; log p(x) = best + log sum_k e_k
+            const float2 nb2 = make_float2(-best, -best);
+            const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+            float2 se2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int kp = 0; kp < JP; ++kp) {
+                const float2 arg = __fmul2_rn(__fadd2_rn(lp2[kp], nb2), l2e);
+                r2[kp] = make_float2(ex2_approx(fmaxf(arg.x, -126.f)), ex2_approx(fmaxf(arg.y, -126.f)));
+                if (2 * kp >= K) r2[kp].x = 0.f;
+                if (2 * kp + 1 >= K) r2[kp].y = 0.f;
+                se2 = __fadd2_rn(se2, r2[kp]);
+            }
+            const float se = se2.x + se2.y;
+            loglik += best + 0.6931471805599453f * lg2_approx(se);
+            const float inv = 1.f / se;
+#pragma unroll
+            for (int kp = 0; kp < JP; ++kp) r2[kp] = __fmul2_rn(r2[kp], make_float2(inv, inv));
+            if (acc_mode == SCC_GMM_HARD) {
+#pragma unroll
+                for (int kp = 0; kp < JP; ++kp)
+                    r2[kp] = make_float2(label == 2 * kp ? 1.f : 0.f, label == 2 * kp + 1 ? 1.f : 0.f);
+            }
+            const size_t i = (size_t)tile * TILE + threadIdx.x;
+            if (a.labels) a.labels[i] = label;
+            if (a.resp) {
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (k < K) a.resp[i * K + k] = (k & 1) ? r2[k / 2].y : r2[k / 2].x;
+            }
+        }
+        if (acc_mode) {
+            // ---- per-component ballots of the significant pairs, responsibilities parked for phase 2
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const float r = (k & 1) ? r2[k / 2].y : r2[k / 2].x;
+                r_s[k * TILE + threadIdx.x] = r;
+                const unsigned int m = __ballot_sync(0xffffffffu, active && k < K && r >= thr && r > 0.f);
+                if (lane == 0) mask_s[k * NW + warp] = m;
+            }
+            __syncthreads();
+            // exclusive prefix of the per-warp counts: thread (k, w)
+            if (threadIdx.x < KP * NW) {
+                const int k = threadIdx.x / NW, w = threadIdx.x - k * NW;
+                int p = 0;
+                for (int ww = 0; ww < w; ++ww) p += __popc(mask_s[k * NW + ww]);
+                pref_s[k * (NW + 1) + w] = p;
+                if (w == NW - 1) pref_s[k * (NW + 1) + NW] = p + __popc(mask_s[k * NW + w]);
+            }
+            __syncthreads();
+            // compact point lists, point order (deterministic)
+            const unsigned int lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const unsigned int m = mask_s[k * NW + warp];
+                if ((m >> lane) & 1u)
+                    list_s[k * TILE + pref_s[k * (NW + 1) + warp] + __popc(m & lt)] = (unsigned short)threadIdx.x;
+            }
+            __syncthreads();
+            // ---------------- phase 2: moments of component kc over its list ----------------
+            if (kc < K) {
+                const int cnt = pref_s[kc * (NW + 1) + NW];
+                for (int e = lane; e < cnt; e += 32) {
+                    const int t = list_s[kc * TILE + e];
+                    const float r = r_s[kc * TILE + t];
+                    float df[D];
+                    load_row<D>(ztile, t, df);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) df[c] -= muk[c];
+                    mom[0] += r;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        const float w = r * df[c];
+                        mom[1 + c] += w;
+#pragma unroll
+                        for (int b = c; b < D; ++b)                      // S2[c][b], c <= b, column-packed
+                            mom[1 + D + tri(b) + c] = fmaf(w, df[b], mom[1 + D + tri(b) + c]);
+                    }
+                }
+                if ((it + 1) % FLUSH == 0) flush();
+            }
+        }
+        __syncthreads();
+        ring.issue(stage, tile + S * G);
+    }
+    if (acc_mode) flush();
+    {
+        const float w = warp_sum(loglik);
+        if (lane == 0) ll_s[warp] = (double)w;
+    }
+    __syncthreads();
+    // pack CTA statistics with the true K: [ll, N_k[K], S1[K*D], S2[K*TRI]]
+    const int NS = 1 + K * NM;
+    for (int s = threadIdx.x; s < NS; s += NT) {
+        double v;
+        if (s == 0) {
+            v = 0.0;
+            for (int w = 0; w < KP; ++w) v += ll_s[w];
+        } else if (s < 1 + K) {
+            v = mom_s[(s - 1) * NM];
+        } else if (s < 1 + K + K * D) {
+            const int o = s - 1 - K, k = o / D, c = o - k * D;
+            v = mom_s[k * NM + 1 + c];
+        } else {
+            const int o = s - 1 - K - K * D, k = o / TRI, e = o - k * TRI;
+            v = mom_s[k * NM + 1 + D + e];
+        }
+        cta_stats[s] = v;
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < NS; s += NT) a.partials[(size_t)blockIdx.x * NS + s] = cta_stats[s];
+}
+
+template <int D, int KP>
+constexpr size_t gmm_sparse_smem() {
+    constexpr int NT = 32 * KP, TILE = NT, S = 3, TRI = tri(D), NM = 1 + D + TRI, JP = KP / 2, NW = KP;
+    constexpr int TRIP = (TRI + 1) & ~1, DP = (D + 1) & ~1;
+    return sizeof(float) * (((S * TILE * RowLayout<D>::LD + 3) & ~3) + KP * TILE + 2 * (JP * DP + JP * TRIP + ((JP + 1) & ~1)) +
+                            ((KP * D + 3) & ~3)) +
+           sizeof(double) * (KP * NM + KP + 1 + KP * NM) + sizeof(uint64_t) * S +
+           sizeof(unsigned int) * KP * NW + sizeof(int) * KP * (NW + 1) + sizeof(unsigned short) * KP * TILE;
+}
+
 // which d <= 12 kernel to run (set from measurements; SCC_GMM_FORCE_SCALAR / _PACKED override for A/B runs)
 template <int D, int KP>
 static int launch_gmm_small(const GmmArgs& a, cudaStream_t st) {
@@ -490,7 +752,27 @@ static int launch_gmm_small(const GmmArgs& a, cudaStream_t st) {
     }();
     // measured (tools/gmm_ab.py, N=4M): packed wins only for even d (d=12: 477 vs 522 us, d=4: 153 vs 160 us);
     // at the reference's d=9 the pad lane and half-pair splats make it 30 % slower (534 vs 403 us, K=8)
-    const bool packed = force ? (force == 1) : (KP <= 8 && D % 2 == 0);
+    static const int sparse_off = []() {
+        const char* e = getenv("SCC_GMM_VARIANT");
+        return e ? (e[0] == 'f' || e[0] == 'p' || e[0] == 's') : 0;          // f(ull) / p(acked) / s(calar): the round-1 kernels
+    }();
+    if (!sparse_off) {
+        auto kern = gmm_em_sparse_kernel<D, KP>;
+        constexpr size_t smem = gmm_sparse_smem<D, KP>();
+        const int64_t tiles = (a.n + NT - 1) / NT;
+        int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), NT, smem, 2);
+        if (grid < 0) return (int)grid;
+        if (grid > kMaxGmmGrid) grid = kMaxGmmGrid;
+        if (grid > tiles) grid = tiles;
+        if (grid < 1) grid = 1;
+        kern<<<(unsigned)grid, NT, smem, st>>>(a);
+        SCC_CUDA(cudaGetLastError());
+        const int NS = SCC_GMM_STAT_DOUBLES(a.K, D);
+        reduce_partials_kernel<<<(NS + 255) / 256, 256, 0, st>>>(a.partials, NS, (int)grid, a.stats, a.ctrl);
+        SCC_CUDA(cudaGetLastError());
+        return SCC_OK;
+    }
+    const bool packed = force ? (force == 1) : false;
     if (!packed) return launch_gmm_full<D, KP>(a, st);
     auto kern = gmm_em_packed_kernel<D, KP>;
     constexpr size_t smem = gmm_packed_smem<D, KP>();
@@ -662,7 +944,7 @@ gmm_em_block_kernel(const GmmArgs a) {
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
                 float r = (active && k < K) ? expf(lp[k] - lse) : 0.f;
-                if (a.accumulate == SCC_GMM_HARD) r = (active && k == label) ? 1.f : 0.f;
+                if ((a.accumulate & 3) == SCC_GMM_HARD) r = (active && k == label) ? 1.f : 0.f;
                 lp[k] = r;
             }
 #pragma unroll
@@ -680,7 +962,7 @@ gmm_em_block_kernel(const GmmArgs a) {
         }
         __syncthreads();
         // ---------------- phase 2: 4x4 moment blocks over all points of the tile ----------------
-        if (a.accumulate) {
+        if (a.accumulate & 3) {
             for (int t = 0; t < np; ++t) {
                 const float* row = ztile + t * L::LD;
 #pragma unroll
@@ -707,7 +989,7 @@ gmm_em_block_kernel(const GmmArgs a) {
         __syncthreads();
         ring.issue(stage, tile + S * G);
     }
-    if (a.accumulate) flush();
+    if (a.accumulate & 3) flush();
     {
         const float w = warp_sum(loglik);
         if (lane == 0) ll_s[warp] = (double)w;

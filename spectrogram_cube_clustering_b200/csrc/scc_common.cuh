@@ -244,154 +244,6 @@ struct ZRing {
 };
 
 // ----------------------------------------------------------------------------
-// Per-warp streaming ring (DEC assign / gradient kernels).
-//   Same tile order and shared-memory layout as ZRing (CTA tile i = blockIdx.x + i * gridDim.x, TILE =
-//   NT * P rows, thread t owns rows t, t + NT, ...), but every WARP moves and synchronises only its own
-//   32-row slices: lane 0 issues the TMA bulk copies of the warp's slices onto the warp's own mbarrier
-//   (padded layouts: the warp's lanes issue cp.async / plain loads), and the only synchronisation in the
-//   main loop is __syncwarp().  Warps of a CTA drift apart, so their latency stalls (MUFU, LDS, the
-//   dependent FMA chains) no longer line up the way they do behind a CTA-wide barrier per tile.
-//   Protocol per warp:  prologue issue(s, tile_s) for s < STAGES;  iteration: wait(stage) ; read own rows
-//   into registers ; __syncwarp() ; issue(stage, tile_{i+STAGES}) ; compute.
-// ----------------------------------------------------------------------------
-template <int D, int TILE, int STAGES, int NT, int P = 1>
-struct WarpRing {
-    using L = RowLayout<D>;
-    static constexpr int NW = NT / 32;
-    static constexpr int kTileFloats = TILE * L::LD;
-    static constexpr bool kCpAsync = L::kVec4 && !L::kDense;
-    static_assert(TILE == NT * P, "one row per thread and sub-tile");
-    static_assert(STAGES >= 2, "ring needs two stages");
-
-    float* buf;
-    uint64_t* bar;      // this warp's STAGES barriers
-    const float* z;
-    int num_tiles, last_points, warp, lane;
-    uint32_t phase;     // bit s = parity the next wait on stage s expects (flips per completed TMA fill)
-
-    // bars: [NW][STAGES] uint64.  Ends with __syncwarp(); no CTA-wide barrier needed (each warp only ever
-    // touches its own barriers and its own rows).
-    __device__ __forceinline__ void init(float* b, uint64_t* bars, const float* z_, int64_t n_) {
-        buf = b; z = z_; phase = 0u;
-        warp = threadIdx.x >> 5; lane = threadIdx.x & 31;
-        bar = bars + warp * STAGES;
-        num_tiles = (int)((n_ + TILE - 1) / TILE);
-        last_points = (int)(n_ - (int64_t)(num_tiles - 1) * TILE);
-        if (L::kDense && lane == 0) {
-#pragma unroll
-            for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
-            fence_mbar_init();
-        }
-        __syncwarp();
-    }
-    __device__ __forceinline__ int points(int tile) const { return tile == num_tiles - 1 ? last_points : TILE; }
-    __device__ __forceinline__ float* stage_ptr(int stage) const { return buf + stage * kTileFloats; }
-    // valid rows of this warp's slice r (rows r*NT + 32*warp ... + 31) in a tile of np points
-    __device__ __forceinline__ int slice_rows(int np, int r) const {
-        const int v = np - (r * NT + 32 * warp);
-        return v <= 0 ? 0 : (v > 32 ? 32 : v);
-    }
-    static __device__ __forceinline__ bool tma_ok(int rows) { return L::kDense && rows > 0 && ((rows * D) & 3) == 0; }
-
-    // Called by all lanes of the warp (converged).
-    __device__ __forceinline__ void issue(int stage, int tile) {
-        if (L::kDense && tile < num_tiles && (tile != num_tiles - 1 || last_points == TILE)) {
-            // fast path, whole tile: fixed-size slices, no per-slice bookkeeping
-            if (lane == 0) {
-                mbar_expect_tx(&bar[stage], P * 32u * D * (uint32_t)sizeof(float));
-                float* dst = stage_ptr(stage) + 32 * warp * L::LD;
-                const float* src = z + ((size_t)tile * TILE + 32 * warp) * D;
-#pragma unroll
-                for (int r = 0; r < P; ++r)
-                    bulk_g2s(dst + r * NT * L::LD, src + (size_t)r * NT * D, 32u * D * (uint32_t)sizeof(float), &bar[stage]);
-            }
-        } else if (tile < num_tiles) {
-            const int np = points(tile);
-            if (L::kDense && lane == 0) {                       // one expect_tx for all of the warp's TMA slices
-                uint32_t bytes = 0;
-#pragma unroll
-                for (int r = 0; r < P; ++r) {
-                    const int nv = slice_rows(np, r);
-                    if (tma_ok(nv)) bytes += (uint32_t)nv * D * sizeof(float);
-                }
-                if (bytes) mbar_expect_tx(&bar[stage], bytes);
-            }
-#pragma unroll
-            for (int r = 0; r < P; ++r) {
-                const int nv = slice_rows(np, r);
-                if (nv == 0) continue;
-                const int row0 = r * NT + 32 * warp;
-                float* dst = stage_ptr(stage) + row0 * L::LD;
-                const float* src = z + ((size_t)tile * TILE + row0) * D;
-                if (tma_ok(nv)) {
-                    if (lane == 0) bulk_g2s(dst, src, (uint32_t)nv * D * sizeof(float), &bar[stage]);
-                } else if constexpr (L::kVec4) {
-                    const int nvec = nv * (D / 4);
-                    const float4* src4 = reinterpret_cast<const float4*>(src);
-                    for (int v = lane; v < nvec; v += 32) {
-                        const int row = v / (D / 4), c4 = v - row * (D / 4);
-                        if constexpr (kCpAsync) cp_async16(dst + row * L::LD + 4 * c4, src4 + v);
-                        else *reinterpret_cast<float4*>(dst + row * L::LD + 4 * c4) = ldg_stream4(src4 + v);
-                    }
-                } else {
-                    const int nf = nv * D;
-                    for (int f = lane; f < nf; f += 32) {
-                        const int row = f / D, c = f - row * D;
-                        dst[row * L::LD + c] = ldg_stream(src + f);
-                    }
-                }
-            }
-        }
-        if constexpr (kCpAsync) cp_async_commit();        // empty groups keep the per-thread count aligned
-    }
-    // After wait() returns every lane may read any row of the warp's slices.  (Slices filled with plain
-    // stores were written STAGES iterations ago and are ordered by the __syncwarp() of the iterations in
-    // between.)  The mbarrier parity is tracked per stage, so a kernel may run several passes over z.
-    __device__ __forceinline__ void wait(int stage, int tile) {
-        if constexpr (kCpAsync) {
-            cp_async_wait<STAGES - 1>();
-            __syncwarp();
-        } else if constexpr (L::kDense) {
-            bool any = true;
-            if (tile == num_tiles - 1 && last_points != TILE) {
-                any = false;
-#pragma unroll
-                for (int r = 0; r < P; ++r) any = any || tma_ok(slice_rows(last_points, r));
-            }
-            if (any) {
-                mbar_wait(&bar[stage], (phase >> stage) & 1u);
-                phase ^= 1u << stage;
-            }
-        }
-    }
-};
-
-// Copy this warp's `rows` staged rows (row stride LD, first row at `src`) to `rows * D` contiguous
-// floats at dst (16-byte aligned), all lanes.
-template <int D>
-__device__ __forceinline__ void warp_copy_rows_out(const float* __restrict__ src, float* __restrict__ dst, int rows) {
-    using L = RowLayout<D>;
-    const int lane = threadIdx.x & 31;
-    if constexpr (L::kVec4) {
-        const int nvec = rows * (D / 4);
-        for (int v = lane; v < nvec; v += 32) {
-            const int row = v / (D / 4), c4 = v - row * (D / 4);
-            reinterpret_cast<float4*>(dst)[v] = *reinterpret_cast<const float4*>(src + row * L::LD + 4 * c4);
-        }
-    } else if constexpr (L::kDense) {
-        const int nf = rows * D, nvec = nf / 4;
-        for (int v = lane; v < nvec; v += 32) reinterpret_cast<float4*>(dst)[v] = reinterpret_cast<const float4*>(src)[v];
-        for (int f = nvec * 4 + lane; f < nf; f += 32) dst[f] = src[f];
-    } else {
-        const int nf = rows * D;
-        for (int f = lane; f < nf; f += 32) {
-            const int row = f / D, c = f - row * D;
-            dst[f] = src[row * L::LD + c];
-        }
-    }
-}
-
-// ----------------------------------------------------------------------------
 // Peer-memory exchange window (see peer_exchange.cu).  Layout, identical on every rank:
 //   [0, 512)            header {seq, flags[2][16]}
 //   fence/flag slots    double [2 parity][16 src rank][max_len]          (vectors longer than kPeerLLMax)
@@ -747,6 +599,62 @@ __device__ __forceinline__ void grid_barrier_sum(const double* cta_stats, int S,
     double* global_vec = slots + (size_t)G * SP;                    // [S] the world's sum, behind the slots
     if (s_ticket == (unsigned int)G - 1) {                          // last CTA of this GPU: local sum, then the exchange
         grid_sum_slots<NT>(slots, S, out_s, scratch);
+        const unsigned int seq = peer_push(*ex, out_s, S);
+        peer_pull(*ex, out_s, S, seq);                              // rank-ordered sum of every GPU's vector
+        if (tid < S) __stcg(global_vec + tid, out_s[tid]);
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + 1), "r"(epoch + 1u) : "memory");
+    } else {
+        if (tid == 0) {
+            unsigned int now;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(counter + 1) : "memory");
+            } while (now != epoch + 1u);
+        }
+        __syncthreads();
+        if (tid < S) out_s[tid] = __ldcg(global_vec + tid);
+        __syncthreads();
+    }
+}
+
+// Variant for NON-NEGATIVE statistics bounded by a known value (the column sums f_j <= n and the label-change
+// count of the DEC assign pass): every CTA adds its S values as 64-bit FIXED-POINT integers to S global
+// accumulators with integer atomics before taking its ticket — integer addition is associative, so the totals
+// are bit-reproducible whatever the arrival order — and after the barrier every CTA just reads S values
+// instead of summing gridDim.x slots (~1.5 us at 296 CTAs).  `inv_scale` = 2^-shift with 2^shift * bound < 2^62.
+// fix[0..S) must be 0 on entry; the caller resets them once no CTA can still be reading.
+template <int NT>
+__device__ __forceinline__ void grid_barrier_sum_fixed(const double* cta_stats, int S, unsigned long long* fix,
+                                                       unsigned int* counter, double* out_s, double scale,
+                                                       double inv_scale, double* global_vec, const PeerCtx* ex = nullptr) {
+    __shared__ unsigned int s_ticket;
+    const int tid = threadIdx.x;
+    const int G = gridDim.x;
+    const bool multi = ex && ex->windows;
+    unsigned int epoch = 0;
+    if (multi && tid == 0)
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(epoch) : "l"(counter + 1) : "memory");
+    if (tid < S) atomicAdd(fix + tid, (unsigned long long)__double2ll_rn(cta_stats[tid] * scale));
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int seen;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
+        s_ticket = seen;
+        if (!multi) {
+            ++seen;
+            while (seen < (unsigned int)G)
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        }
+    }
+    __syncthreads();
+    if (!multi) {
+        if (tid < S) out_s[tid] = (double)__ldcg(fix + tid) * inv_scale;
+        __syncthreads();
+        return;
+    }
+    if (s_ticket == (unsigned int)G - 1) {                          // last CTA of this GPU: the exchange
+        if (tid < S) out_s[tid] = (double)__ldcg(fix + tid) * inv_scale;
+        __syncthreads();
         const unsigned int seq = peer_push(*ex, out_s, S);
         peer_pull(*ex, out_s, S, seq);                              // rank-ordered sum of every GPU's vector
         if (tid < S) __stcg(global_vec + tid, out_s[tid]);

@@ -329,6 +329,7 @@ def gmm_pack_params(weights, means, covariances, params=None, prec_chol=None, ct
 
 
 GMM_ESTEP_ONLY, GMM_SOFT, GMM_HARD = 0, 1, 2
+GMM_NOSKIP = 16      # OR-able: keep (point, component) pairs with responsibility < 2^-30 in the M-step sums
 
 
 def gmm_em_step(z, K, params, stats=None, labels=None, resp=None, ctrl=None, mode=GMM_SOFT):
