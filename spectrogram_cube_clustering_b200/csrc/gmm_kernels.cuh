@@ -497,19 +497,30 @@ constexpr size_t gmm_packed_smem() {
 // ---------------------------------------------------------------------------
 constexpr float kGmmSkipThreshold = 9.313225746154785e-10f;       // 2^-30
 
+// points per thread of the E-step: every parameter load (one 128-bit shared-memory load per two U pairs) then
+// feeds PP points.  With one point per thread the kernel is bound by the shared-memory RETURN bandwidth
+// (128 B/clk/SM: a warp-wide LDS.128 occupies the pipe for 4 cycles whatever the broadcast) — K (d + TRI) floats per
+// point, 3.4 KB at d = 9, K = 16 = 27 cycles/point against ~8 for the arithmetic.
+template <int KP>
+__host__ __device__ constexpr int gmm_ppt() { return 2; }
+template <int KP>
+__host__ __device__ constexpr int gmm_stages() { return KP >= 16 ? 2 : 3; }
+
 template <int D, int KP>
 __global__ void __launch_bounds__(32 * KP, 1)
 gmm_em_sparse_kernel(const GmmArgs a) {
     constexpr int NT = 32 * KP;
-    constexpr int TILE = NT;
-    constexpr int S = 3;
+    constexpr int PP = gmm_ppt<KP>();
+    constexpr int TILE = NT * PP;
+    constexpr int S = gmm_stages<KP>();
     constexpr int NW = KP;                                 // warps per CTA == components
+    constexpr int NSRC = NW * PP;                          // 32-point groups of a tile (ballot sources)
     constexpr int JP = KP / 2;                             // component pairs
     constexpr int TRI = tri(D);
     constexpr int TRIP = (TRI + 1) & ~1;                   // U pairs per component pair, padded to 16 bytes
     constexpr int DP = (D + 1) & ~1;
     constexpr int NM = 1 + D + TRI;
-    constexpr int FLUSH = 16;
+    constexpr int FLUSH = 32;                              // tiles between float -> double flushes (<= ~100 terms per lane)
     using Ring = ZRing<D, TILE, S, NT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring_buf = reinterpret_cast<float*>(smem_raw);
@@ -522,9 +533,9 @@ gmm_em_sparse_kernel(const GmmArgs a) {
     double* ll_s = mom_s + KP * NM;                                        // [KP]
     double* cta_stats = ll_s + KP;                                         // [1 + KP*NM]
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + 1 + KP * NM); // [S]
-    unsigned int* mask_s = reinterpret_cast<unsigned int*>(bars + S);      // [KP][NW] ballot of (r >= thr) per source warp
-    int* pref_s = reinterpret_cast<int*>(mask_s + KP * NW);                // [KP][NW + 1] exclusive prefix, total
-    unsigned short* list_s = reinterpret_cast<unsigned short*>(pref_s + KP * (NW + 1));   // [KP][TILE]
+    unsigned int* mask_s = reinterpret_cast<unsigned int*>(bars + S);      // [KP][NSRC] ballot of (r >= thr) per 32-point group
+    int* pref_s = reinterpret_cast<int*>(mask_s + KP * NSRC);              // [KP][NSRC + 1] exclusive prefix, total
+    unsigned short* list_s = reinterpret_cast<unsigned short*>(pref_s + KP * (NSRC + 1));   // [KP][TILE]
 
     if (a.ctrl && a.ctrl[5] != 0.0) return;              // frozen fit: converged or failed earlier
 
@@ -584,103 +595,137 @@ gmm_em_sparse_kernel(const GmmArgs a) {
         ring.wait(stage, tile, (uint32_t)(it / S));
         const int np = ring.points(tile);
         const float* ztile = ring.stage_ptr(stage);
-        // ---------------- phase 1: E-step for point threadIdx.x ----------------
-        const bool active = (int)threadIdx.x < np;
-        float2 r2[JP];
+        // ---------------- phase 1: E-step for points threadIdx.x + p * NT ----------------
+        bool active[PP];
+        float2 r2[PP][JP];
+        {
+            float x[PP][D];
 #pragma unroll
-        for (int kp = 0; kp < JP; ++kp) r2[kp] = make_float2(0.f, 0.f);
-        int label = 0;
-        if (active) {
-            float x[D];
-            load_row<D>(ztile, threadIdx.x, x);
-            float2 lp2[JP];
+            for (int p = 0; p < PP; ++p) {
+                active[p] = (int)threadIdx.x + p * NT < np;
+#pragma unroll
+                for (int c = 0; c < D; ++c) x[p][c] = 0.f;
+                if (active[p]) load_row<D>(ztile, threadIdx.x + p * NT, x[p]);
+            }
+            float2 lp2[PP][JP];
 #pragma unroll
             for (int kp = 0; kp < JP; ++kp) {
-                lp2[kp] = make_float2(-3.4e38f, -3.4e38f);
-                if (2 * kp < K) {
-                    float2 df2[D];
 #pragma unroll
-                    for (int c = 0; c < D; ++c) df2[c] = __fadd2_rn(make_float2(x[c], x[c]), nmu2_s[kp * DP + c]);
-                    float2 m2 = make_float2(0.f, 0.f);
+                for (int p = 0; p < PP; ++p) lp2[p][kp] = make_float2(-3.4e38f, -3.4e38f);
+                if (2 * kp < K) {
+                    float2 df2[PP][D];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        const float2 nm = nmu2_s[kp * DP + c];
+#pragma unroll
+                        for (int p = 0; p < PP; ++p) df2[p][c] = __fadd2_rn(make_float2(x[p][c], x[p][c]), nm);
+                    }
+                    float2 m2[PP];
+#pragma unroll
+                    for (int p = 0; p < PP; ++p) m2[p] = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int b = 0; b < D; ++b) {
-                        float2 y2 = make_float2(0.f, 0.f);
+                        float2 y2[PP];
 #pragma unroll
-                        for (int c = 0; c <= b; ++c) y2 = __ffma2_rn(df2[c], u2_s[kp * TRIP + tri(b) + c], y2);
-                        m2 = __ffma2_rn(y2, y2, m2);
+                        for (int p = 0; p < PP; ++p) y2[p] = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int c = 0; c <= b; ++c) {
+                            const float2 u = u2_s[kp * TRIP + tri(b) + c];
+#pragma unroll
+                            for (int p = 0; p < PP; ++p) y2[p] = __ffma2_rn(df2[p][c], u, y2[p]);
+                        }
+#pragma unroll
+                        for (int p = 0; p < PP; ++p) m2[p] = __ffma2_rn(y2[p], y2[p], m2[p]);
                     }
-                    float2 v = __ffma2_rn(make_float2(-0.5f, -0.5f), m2, cst2_s[kp]);
-                    if (2 * kp + 1 >= K) v.y = -3.4e38f;
-                    lp2[kp] = v;
+                    const float2 cst = cst2_s[kp];
+#pragma unroll
+                    for (int p = 0; p < PP; ++p) {
+                        float2 v = __ffma2_rn(make_float2(-0.5f, -0.5f), m2[p], cst);
+                        if (2 * kp + 1 >= K) v.y = -3.4e38f;
+                        lp2[p][kp] = v;
+                    }
                 }
             }
-            float best = -3.4e38f;
 #pragma unroll
-            for (int kp = 0; kp < JP; ++kp) {
-                if (lp2[kp].x > best) { best = lp2[kp].x; label = 2 * kp; }
-                if (lp2[kp].y > best) { best = lp2[kp].y; label = 2 * kp + 1; }
-            }
-            // e_k = exp(lp_k - best) once per component; r_k = e_k / sum_k e_k; log p(x) = best + log sum_k e_k
-            const float2 nb2 = make_float2(-best, -best);
-            const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
-            float2 se2 = make_float2(0.f, 0.f);
+            for (int p = 0; p < PP; ++p) {
+                float best = -3.4e38f;
+                int label = 0;
 #pragma unroll
-            for (int kp = 0; kp < JP; ++kp) {
-                const float2 arg = __fmul2_rn(__fadd2_rn(lp2[kp], nb2), l2e);
-                r2[kp] = make_float2(ex2_approx(fmaxf(arg.x, -126.f)), ex2_approx(fmaxf(arg.y, -126.f)));
-                if (2 * kp >= K) r2[kp].x = 0.f;
-                if (2 * kp + 1 >= K) r2[kp].y = 0.f;
-                se2 = __fadd2_rn(se2, r2[kp]);
-            }
-            const float se = se2.x + se2.y;
-            loglik += best + 0.6931471805599453f * lg2_approx(se);
-            const float inv = 1.f / se;
+                for (int kp = 0; kp < JP; ++kp) {
+                    if (lp2[p][kp].x > best) { best = lp2[p][kp].x; label = 2 * kp; }
+                    if (lp2[p][kp].y > best) { best = lp2[p][kp].y; label = 2 * kp + 1; }
+                }
+                // e_k = exp(lp_k - best) once per component; r_k = e_k / sum_k e_k; log p(x) = best + log sum_k e_k
+                const float2 nb2 = make_float2(-best, -best);
+                const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+                float2 se2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int kp = 0; kp < JP; ++kp) r2[kp] = __fmul2_rn(r2[kp], make_float2(inv, inv));
-            if (acc_mode == SCC_GMM_HARD) {
+                for (int kp = 0; kp < JP; ++kp) {
+                    const float2 arg = __fmul2_rn(__fadd2_rn(lp2[p][kp], nb2), l2e);
+                    r2[p][kp] = make_float2(ex2_approx(fmaxf(arg.x, -126.f)), ex2_approx(fmaxf(arg.y, -126.f)));
+                    if (2 * kp >= K) r2[p][kp].x = 0.f;
+                    if (2 * kp + 1 >= K) r2[p][kp].y = 0.f;
+                    se2 = __fadd2_rn(se2, r2[p][kp]);
+                }
+                const float se = se2.x + se2.y;
+                if (active[p]) loglik += best + 0.6931471805599453f * lg2_approx(se);
+                const float inv = 1.f / se;
 #pragma unroll
-                for (int kp = 0; kp < JP; ++kp)
-                    r2[kp] = make_float2(label == 2 * kp ? 1.f : 0.f, label == 2 * kp + 1 ? 1.f : 0.f);
-            }
-            const size_t i = (size_t)tile * TILE + threadIdx.x;
-            if (a.labels) a.labels[i] = label;
-            if (a.resp) {
+                for (int kp = 0; kp < JP; ++kp) r2[p][kp] = __fmul2_rn(r2[p][kp], make_float2(inv, inv));
+                if (acc_mode == SCC_GMM_HARD) {
 #pragma unroll
-                for (int k = 0; k < KP; ++k)
-                    if (k < K) a.resp[i * K + k] = (k & 1) ? r2[k / 2].y : r2[k / 2].x;
+                    for (int kp = 0; kp < JP; ++kp)
+                        r2[p][kp] = make_float2(label == 2 * kp ? 1.f : 0.f, label == 2 * kp + 1 ? 1.f : 0.f);
+                }
+                if (active[p]) {
+                    const size_t i = (size_t)tile * TILE + threadIdx.x + p * NT;
+                    if (a.labels) a.labels[i] = label;
+                    if (a.resp) {
+#pragma unroll
+                        for (int k = 0; k < KP; ++k)
+                            if (k < K) a.resp[i * K + k] = (k & 1) ? r2[p][k / 2].y : r2[p][k / 2].x;
+                    }
+                }
             }
         }
         if (acc_mode) {
             // ---- per-component ballots of the significant pairs, responsibilities parked for phase 2
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                const float r = (k & 1) ? r2[k / 2].y : r2[k / 2].x;
-                r_s[k * TILE + threadIdx.x] = r;
-                const unsigned int m = __ballot_sync(0xffffffffu, active && k < K && r >= thr && r > 0.f);
-                if (lane == 0) mask_s[k * NW + warp] = m;
+            for (int p = 0; p < PP; ++p) {
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    const float r = (k & 1) ? r2[p][k / 2].y : r2[p][k / 2].x;
+                    r_s[k * TILE + threadIdx.x + p * NT] = r;
+                    const unsigned int m = __ballot_sync(0xffffffffu, active[p] && k < K && r >= thr && r > 0.f);
+                    if (lane == 0) mask_s[k * NSRC + p * NW + warp] = m;
+                }
             }
             __syncthreads();
-            // exclusive prefix of the per-warp counts: thread (k, w)
-            if (threadIdx.x < KP * NW) {
-                const int k = threadIdx.x / NW, w = threadIdx.x - k * NW;
-                int p = 0;
-                for (int ww = 0; ww < w; ++ww) p += __popc(mask_s[k * NW + ww]);
-                pref_s[k * (NW + 1) + w] = p;
-                if (w == NW - 1) pref_s[k * (NW + 1) + NW] = p + __popc(mask_s[k * NW + w]);
+            // exclusive prefix of the per-group counts: thread (k, group)
+            for (int o = threadIdx.x; o < KP * NSRC; o += NT) {
+                const int k = o / NSRC, w = o - k * NSRC;
+                int pfx = 0;
+                for (int ww = 0; ww < w; ++ww) pfx += __popc(mask_s[k * NSRC + ww]);
+                pref_s[k * (NSRC + 1) + w] = pfx;
+                if (w == NSRC - 1) pref_s[k * (NSRC + 1) + NSRC] = pfx + __popc(mask_s[k * NSRC + w]);
             }
             __syncthreads();
             // compact point lists, point order (deterministic)
             const unsigned int lt = (1u << lane) - 1u;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                const unsigned int m = mask_s[k * NW + warp];
-                if ((m >> lane) & 1u)
-                    list_s[k * TILE + pref_s[k * (NW + 1) + warp] + __popc(m & lt)] = (unsigned short)threadIdx.x;
+            for (int p = 0; p < PP; ++p) {
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    const unsigned int m = mask_s[k * NSRC + p * NW + warp];
+                    if ((m >> lane) & 1u)
+                        list_s[k * TILE + pref_s[k * (NSRC + 1) + p * NW + warp] + __popc(m & lt)] =
+                            (unsigned short)(threadIdx.x + p * NT);
+                }
             }
             __syncthreads();
             // ---------------- phase 2: moments of component kc over its list ----------------
             if (kc < K) {
-                const int cnt = pref_s[kc * (NW + 1) + NW];
+                const int cnt = pref_s[kc * (NSRC + 1) + NSRC];
                 for (int e = lane; e < cnt; e += 32) {
                     const int t = list_s[kc * TILE + e];
                     const float r = r_s[kc * TILE + t];
@@ -734,12 +779,13 @@ gmm_em_sparse_kernel(const GmmArgs a) {
 
 template <int D, int KP>
 constexpr size_t gmm_sparse_smem() {
-    constexpr int NT = 32 * KP, TILE = NT, S = 3, TRI = tri(D), NM = 1 + D + TRI, JP = KP / 2, NW = KP;
+    constexpr int NT = 32 * KP, PP = gmm_ppt<KP>(), TILE = NT * PP, S = gmm_stages<KP>(), TRI = tri(D), NM = 1 + D + TRI;
+    constexpr int JP = KP / 2, NSRC = KP * PP;
     constexpr int TRIP = (TRI + 1) & ~1, DP = (D + 1) & ~1;
     return sizeof(float) * (((S * TILE * RowLayout<D>::LD + 3) & ~3) + KP * TILE + 2 * (JP * DP + JP * TRIP + ((JP + 1) & ~1)) +
                             ((KP * D + 3) & ~3)) +
            sizeof(double) * (KP * NM + KP + 1 + KP * NM) + sizeof(uint64_t) * S +
-           sizeof(unsigned int) * KP * NW + sizeof(int) * KP * (NW + 1) + sizeof(unsigned short) * KP * TILE;
+           sizeof(unsigned int) * KP * NSRC + sizeof(int) * KP * (NSRC + 1) + sizeof(unsigned short) * KP * TILE;
 }
 
 // which d <= 12 kernel to run (set from measurements; SCC_GMM_FORCE_SCALAR / _PACKED override for A/B runs)
@@ -759,7 +805,8 @@ static int launch_gmm_small(const GmmArgs& a, cudaStream_t st) {
     if (!sparse_off) {
         auto kern = gmm_em_sparse_kernel<D, KP>;
         constexpr size_t smem = gmm_sparse_smem<D, KP>();
-        const int64_t tiles = (a.n + NT - 1) / NT;
+        constexpr int tile_points = NT * gmm_ppt<KP>();
+        const int64_t tiles = (a.n + tile_points - 1) / tile_points;
         int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), NT, smem, 2);
         if (grid < 0) return (int)grid;
         if (grid > kMaxGmmGrid) grid = kMaxGmmGrid;
