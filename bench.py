@@ -209,6 +209,8 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from spectrogram_cube_clustering_b200.latent_buffer import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(dev) if world > 1 else {"bound": False}     # pinned staging on the GPU-local node
     group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -602,7 +604,7 @@ def run_gpu(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world),
-            "details": {"parallelism": parallelism,
+            "details": {"parallelism": parallelism, "numa": numa,
                        "launch": (("one CUDA graph replay per step" if args.single_step_graphs else
                                    f"CUDA graph replays of {GRAPH_STEPS} consecutive steps (rotating over the {N_SETS} input sets), "
                                    "single-step graphs for the remainder")

@@ -20,6 +20,42 @@ import torch
 from . import ops
 
 
+def bind_to_gpu_numa_node(device) -> dict:
+    """Pin this process (and so the pinned staging buffers it allocates next: first-touch placement) to the CPU
+    cores of the NUMA node the GPU hangs off.  With one process per GPU every rank otherwise inherits the same
+    affinity mask and all ranks stage their uploads through one memory controller (round 1: 45 GB/s H2D on one
+    GPU, 23.5 GB/s per GPU on eight).  Best effort: returns what it found and did; never raises."""
+    import os
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        dev = torch.device(device)
+        bus = torch.cuda.get_device_properties(dev).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(dev), "pci_bus_id") else None
+        domain = getattr(torch.cuda.get_device_properties(dev), "pci_domain_id", 0)
+        devid = getattr(torch.cuda.get_device_properties(dev), "pci_device_id", 0)
+        if bus is None:
+            return info
+        path = f"/sys/bus/pci/devices/{domain:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+        with open(path) as fh:
+            node = int(fh.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        info["cpus"] = len(allowed)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+    except Exception as exc:  # pragma: no cover - depends on the box
+        info["error"] = repr(exc)
+    return info
+
+
 def shard_bounds(n_total: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous row block of ``rank``: sizes differ by at most one row."""
     base, rem = divmod(int(n_total), int(world))

@@ -136,7 +136,7 @@ with warnings.catch_warnings():
                           poll_interval=5).fit(LatentBuffer(z_all))
 assert gm.n_iter_ == gm1.n_iter_ and gm.converged_ == gm1.converged_, (gm.n_iter_, gm1.n_iter_)
 assert rel(gm.means_, gm1.means_) < 1e-6 and rel(gm.covariances_, gm1.covariances_) < 1e-6
-assert abs(gm.lower_bound_ - gm1.lower_bound_) < 1e-6 * abs(gm1.lower_bound_)   # fp32 per-thread partial sums regroup with the shards
+assert abs(gm.lower_bound_ - gm1.lower_bound_) < 1e-5 * abs(gm1.lower_bound_)   # fp32 per-thread partial sums regroup with the shards
 m_all = [torch.empty_like(gm._means) for _ in range(world)]
 dist.all_gather(m_all, gm._means)
 assert all(torch.equal(m_all[0], m) for m in m_all), "GMM: ranks hold different means"
