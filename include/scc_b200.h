@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SCC_ABI_VERSION 2
+#define SCC_ABI_VERSION 3
 #define SCC_MAX_D 32
 #define SCC_MAX_K 16
 
@@ -190,6 +190,8 @@ int scc_kmeans_batch_update(float* centers, const double* stats, int d, int K, i
 int scc_dec_distances(const float* z, int64_t n, int d, const float* mu, int K, float p, float* out,
                       scc_stream_t stream);
 
+struct scc_exchange;   /* multi-GPU exchange descriptor, defined below */
+
 /* ------------------------------------------------------------------------- *
  * GMM stage (full covariance)
  * ------------------------------------------------------------------------- */
@@ -259,6 +261,21 @@ int scc_gmm_finalize(const double* stats, double n_total, int d, int K,
                      double* means, double* weights, double* covariances,
                      double* prec_chol, float* params, double* ctrl,
                      scc_stream_t stream);
+
+/*
+ * One whole EM iteration in two launches: the fused E+M statistics pass over z (scc_gmm_em_step) and ONE tail
+ * kernel that sums the per-thread-block partial statistics in a fixed order, all-reduces them over the GPUs
+ * (`exchange`, or NULL on a single GPU: every thread block ships / polls its own slice of the vector through the
+ * flag-in-data exchange window) and runs the M-step finalisation of scc_gmm_finalize in its last thread block.
+ * Same arithmetic as scc_gmm_em_step -> (all-reduce) -> scc_gmm_finalize; `stats` receives the world's sums.
+ * mode: SCC_GMM_SOFT or SCC_GMM_HARD, optionally | SCC_GMM_NOSKIP.  A frozen fit (ctrl[5] != 0) is a no-op.
+ * Replaces one trip of the loop in sklearn:mixture/_base.py:262-278.
+ */
+int scc_gmm_em_iteration(const float* z, int64_t n, int d, int K, float* params, double* stats, int mode,
+                         double n_total, double reg_covar, double nk_eps, double tol,
+                         double* means, double* weights, double* covariances, double* prec_chol, double* ctrl,
+                         void* workspace, size_t workspace_bytes, const struct scc_exchange* exchange,
+                         scc_stream_t stream);
 
 /*
  * Build the packed E-step parameter block from explicit (pi, mu, Sigma) float64

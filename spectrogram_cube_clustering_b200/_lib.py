@@ -90,6 +90,9 @@ _SIGNATURES = {
                                 c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "scc_gmm_finalize": (c_int, [c_void_p, c_double, c_int, c_int, c_double, c_double, c_double, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scc_gmm_em_iteration": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_double, c_double,
+                                     c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_size_t, c_void_p, c_void_p]),
     "scc_gmm_pack_params": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
 }

@@ -26,10 +26,9 @@ struct FinArgs {
     double* ctrl;
 };
 
+// All threads of one CTA of at least 32 * K threads.
 template <bool FROM_STATS>
-__global__ void __launch_bounds__(512, 1)
-gmm_finalize_kernel(const FinArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+__device__ __forceinline__ void gmm_finalize_body(const FinArgs& a, unsigned char* smem_raw) {
     const int d = a.d, K = a.K, LDA = d + 1, TRI = tri(d);
     double* mats = reinterpret_cast<double*>(smem_raw);       // [K][d*LDA]  L below, Y^T above
     __shared__ double nk_s[SCC_MAX_K];
@@ -137,6 +136,75 @@ gmm_finalize_kernel(const FinArgs a) {
     }
 }
 
+template <bool FROM_STATS>
+__global__ void __launch_bounds__(512, 1)
+gmm_finalize_kernel(const FinArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    gmm_finalize_body<FROM_STATS>(a, smem_raw);
+}
+
+// ---------------------------------------------------------------------------
+// Tail of one EM iteration in ONE launch: fixed-order reduction of the per-CTA partial statistics, their
+// cross-GPU all-reduce and the M-step finalisation.  Every CTA owns a slice of the statistics vector: it sums
+// the slice over the statistics kernel's partial slots, ships it to every rank's exchange window and polls the
+// same slice of every rank (flag-in-data: slices are independent), writes the world's sums to `stats`; the CTA
+// that finishes last then runs the finalisation (scaling, Cholesky, U = L^-T, lower bound, stop rule).
+// Replaces reduce_partials -> exchange -> finalize (three launches) behind the statistics kernel.
+// ---------------------------------------------------------------------------
+constexpr int kTailSlice = 512;
+
+__global__ void __launch_bounds__(512, 1)
+gmm_tail_kernel(const double* __restrict__ partials, int G, int NS, double* __restrict__ stats, PeerCtx ex,
+                unsigned int* __restrict__ ticket, const FinArgs fin) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double slice[kTailSlice];
+    __shared__ int s_last;
+    if (fin.ctrl[5] != 0.0) return;              // frozen fit (identical on every rank): nothing to exchange
+    const int lo = blockIdx.x * kTailSlice, hi = min(NS, lo + kTailSlice);
+    const int s = lo + threadIdx.x;
+    if (s < hi) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int b = 0;
+        for (; b + 3 < G; b += 4) {
+            a0 += partials[(size_t)b * NS + s];
+            a1 += partials[(size_t)(b + 1) * NS + s];
+            a2 += partials[(size_t)(b + 2) * NS + s];
+            a3 += partials[(size_t)(b + 3) * NS + s];
+        }
+        for (; b < G; ++b) a0 += partials[(size_t)b * NS + s];
+        slice[threadIdx.x] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+    if (ex.windows) {
+        PeerHeader* me = reinterpret_cast<PeerHeader*>(ex.windows[ex.rank]);
+        const unsigned int seq = ld_relaxed_gpu_u32(&me->seq) + 1u;
+        peer_push_slice(ex, slice, lo, hi, seq);
+        peer_pull_slice(ex, stats + lo, lo, hi, seq);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int t;
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(&me->ticket) : "memory");
+            if (t == gridDim.x - 1) {
+                me->ticket = 0u;
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&me->seq), "r"(seq) : "memory");
+            }
+        }
+    } else if (s < hi) {
+        stats[s] = slice[threadIdx.x];
+    }
+    // the CTA that finishes last sees every slice of `stats` (writes above -> CTA barrier -> acq_rel ticket)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+        if (s_last) *ticket = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    gmm_finalize_body<true>(fin, smem_raw);
+}
+
 
 bool gmm_supported(int d, int K) {
     if (K < 1 || K > SCC_MAX_K) return false;
@@ -168,6 +236,43 @@ int gmm_em_step(const float* z, int64_t n, int d, int K, const float* params, do
 }
 
 static size_t finalize_smem(int d, int K) { return sizeof(double) * (size_t)K * d * (d + 1); }
+
+int gmm_em_iteration(const float* z, int64_t n, int d, int K, float* params, double* stats, int mode, double n_total,
+                     double reg_covar, double nk_eps, double tol, double* means, double* weights, double* covariances,
+                     double* prec_chol, double* ctrl, void* ws, size_t ws_bytes, const ExchangeDesc* ex, cudaStream_t st) {
+    if ((!z && n > 0) || !params || !stats || !means || !weights || !covariances || !ctrl || n < 0) return SCC_ERR_INVALID;
+    if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K || !(n_total > 0)) return SCC_ERR_INVALID;
+    if ((mode & 3) == 0 || (mode & 3) > 2 || (mode & ~(3 | SCC_GMM_NOSKIP))) return SCC_ERR_INVALID;
+    if (!gmm_supported(d, K)) return SCC_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(z) & 15u) != 0) return SCC_ERR_MISALIGNED;
+    if (!ws || ws_bytes < workspace_bytes(d, K)) return SCC_ERR_WORKSPACE;
+    const int NS = SCC_GMM_STAT_DOUBLES(K, d);
+    if (ex && ex->windows && NS > ex->max_len) return SCC_ERR_INVALID;
+    int grid = 0;
+    GmmArgs a{};
+    a.z = z; a.n = n; a.K = K; a.params = params; a.ctrl = ctrl; a.accumulate = mode; a.stats = stats;
+    a.counter = reinterpret_cast<unsigned int*>(ws);
+    a.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + kWorkspaceHeader);
+    a.skip_reduce = 1; a.grid_out = &grid;
+    if (n > 0) {
+        int rc = SCC_ERR_UNSUPPORTED;
+#define SCC_CASE(D_) if (d == D_) rc = gmm_em_dim##D_(a, st);
+        SCC_FOR_EACH_GMM_DIM(SCC_CASE)
+#undef SCC_CASE
+        if (rc != SCC_OK) return rc;
+    }
+    FinArgs f{};
+    f.stats = stats; f.n_total = n_total; f.reg_covar = reg_covar; f.nk_add = nk_eps; f.tol = tol;
+    f.d = d; f.K = K; f.means = means; f.weights = weights; f.covariances = covariances;
+    f.prec_chol = prec_chol; f.params = params; f.ctrl = ctrl;
+    PeerCtx px{nullptr, 0, 1, 0};
+    if (ex && ex->windows) px = PeerCtx{reinterpret_cast<unsigned char* const*>(ex->windows), ex->rank, ex->world, ex->max_len};
+    const size_t smem = finalize_smem(d, K);
+    SCC_CUDA(cudaFuncSetAttribute(gmm_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gmm_tail_kernel<<<(NS + kTailSlice - 1) / kTailSlice, 512, smem, st>>>(a.partials, grid, NS, stats, px, a.counter + 4, f);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
 
 int gmm_finalize(const double* stats, double n_total, int d, int K, double reg_covar, double nk_eps, double tol,
                  double* means, double* weights, double* covariances, double* prec_chol, float* params,

@@ -33,7 +33,19 @@ struct GmmArgs {
     double* stats;
     double* partials;
     unsigned int* counter;
+    int skip_reduce;           // leave the per-CTA partial slots for gmm_tail_kernel (fused EM iteration)
+    int* grid_out;             // host: number of partial slots written (grid of the statistics kernel)
 };
+
+// after the statistics kernel: stand-alone fixed-order reduction, or hand the slots to the fused tail
+static inline int gmm_after_stats(const GmmArgs& a, int grid, int D, cudaStream_t st) {
+    if (a.grid_out) *a.grid_out = grid;
+    if (a.skip_reduce) return SCC_OK;
+    const int NS = SCC_GMM_STAT_DOUBLES(a.K, D);
+    reduce_partials_kernel<<<(NS + 255) / 256, 256, 0, st>>>(a.partials, NS, grid, a.stats, a.ctrl);
+    SCC_CUDA(cudaGetLastError());
+    return SCC_OK;
+}
 
 __host__ __device__ constexpr int tri(int d) { return d * (d + 1) / 2; }
 
@@ -234,10 +246,7 @@ static int launch_gmm_full(const GmmArgs& a, cudaStream_t st) {
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, NT, smem, st>>>(a);
     SCC_CUDA(cudaGetLastError());
-    const int NS = SCC_GMM_STAT_DOUBLES(a.K, D);
-    reduce_partials_kernel<<<(NS + 255) / 256, 256, 0, st>>>(a.partials, NS, (int)grid, a.stats, a.ctrl);
-    SCC_CUDA(cudaGetLastError());
-    return SCC_OK;
+    return gmm_after_stats(a, (int)grid, D, st);
 }
 
 
@@ -814,10 +823,7 @@ static int launch_gmm_small(const GmmArgs& a, cudaStream_t st) {
         if (grid < 1) grid = 1;
         kern<<<(unsigned)grid, NT, smem, st>>>(a);
         SCC_CUDA(cudaGetLastError());
-        const int NS = SCC_GMM_STAT_DOUBLES(a.K, D);
-        reduce_partials_kernel<<<(NS + 255) / 256, 256, 0, st>>>(a.partials, NS, (int)grid, a.stats, a.ctrl);
-        SCC_CUDA(cudaGetLastError());
-        return SCC_OK;
+        return gmm_after_stats(a, (int)grid, D, st);
     }
     const bool packed = force ? (force == 1) : false;
     if (!packed) return launch_gmm_full<D, KP>(a, st);
@@ -831,10 +837,7 @@ static int launch_gmm_small(const GmmArgs& a, cudaStream_t st) {
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, NT, smem, st>>>(a);
     SCC_CUDA(cudaGetLastError());
-    const int NS = SCC_GMM_STAT_DOUBLES(a.K, D);
-    reduce_partials_kernel<<<(NS + 255) / 256, 256, 0, st>>>(a.partials, NS, (int)grid, a.stats, a.ctrl);
-    SCC_CUDA(cudaGetLastError());
-    return SCC_OK;
+    return gmm_after_stats(a, (int)grid, D, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -1070,10 +1073,7 @@ static int launch_gmm_block(const GmmArgs& a, cudaStream_t st) {
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, B::NT, smem, st>>>(a);
     SCC_CUDA(cudaGetLastError());
-    const int NS = SCC_GMM_STAT_DOUBLES(a.K, D);
-    reduce_partials_kernel<<<(NS + 255) / 256, 256, 0, st>>>(a.partials, NS, (int)grid, a.stats, a.ctrl);
-    SCC_CUDA(cudaGetLastError());
-    return SCC_OK;
+    return gmm_after_stats(a, (int)grid, D, st);
 }
 
 template <int D, int KP>

@@ -10,26 +10,43 @@
 //
 // Window layout (identical on every rank; slots double-buffered by sequence parity so a fast rank
 // can run at most one exchange ahead of the slowest without overwriting unread data):
-//   uint32 seq; uint32 flags[2][16]; double slots[2][16][max_len]; uint64 ll_cells[2][16][2*min(max_len,1024)]
-// Vectors of up to 1024 doubles (all DEC statistics) use the flag-in-data cells: no system fence and no
-// flag round trip, see scc_common.cuh.
+//   uint32 seq, ticket; uint64 ll_cells[2][16][2*max_len]    (flag-in-data cells, see scc_common.cuh: no system
+//   fence, no flag round trip; long vectors are exchanged slice-wise by several CTAs)
 // One process per GPU: kernels of different ranks run on different devices, so the spin-wait is safe.
 #include "scc_common.cuh"
 #include "scc_launch.h"
 
 namespace scc {
 
+constexpr int kExchangeSlice = 256;        // elements per CTA of the stand-alone exchange kernel
+
 __global__ void __launch_bounds__(256)
 peer_allreduce_kernel(const double* __restrict__ local, int len, double* __restrict__ out, PeerCtx ex) {
-    // Launched with the PDL attribute: this one-CTA kernel is already resident when the statistics kernel
-    // before it drains, and the kernel after it may be scheduled (up to its own dependency wait) while
-    // the exchange is in flight — the two launch latencies around the exchange leave the critical path.
+    // Launched with the PDL attribute: the kernel is already resident when the statistics kernel before it
+    // drains, and the kernel after it may be scheduled (up to its own dependency wait) while the exchange is in
+    // flight — the two launch latencies around the exchange leave the critical path.
     pdl_wait();
     pdl_trigger();
-    // push my vector into slot [parity][rank] of every window (own window included), wait for the world's
-    // vectors and sum them in rank order; short vectors travel flag-in-data (scc_common.cuh)
-    const unsigned int seq = peer_push(ex, local, len);
-    peer_pull(ex, out, len, seq);
+    // every CTA owns a slice: push it into cell [parity][rank] of every window (own window included), poll the
+    // same slice of every rank and sum in rank order.  Flag-in-data needs no ordering between elements, so the
+    // slices are independent; the sequence number is advanced by the CTA that finishes last.
+    __shared__ double slice[kExchangeSlice];
+    PeerHeader* me = reinterpret_cast<PeerHeader*>(ex.windows[ex.rank]);
+    const unsigned int seq = ld_relaxed_gpu_u32(&me->seq) + 1u;
+    const int lo = blockIdx.x * kExchangeSlice, hi = min(len, lo + kExchangeSlice);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) slice[i - lo] = local[i];
+    __syncthreads();
+    peer_push_slice(ex, slice, lo, hi, seq);
+    peer_pull_slice(ex, out + lo, lo, hi, seq);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(&me->ticket) : "memory");
+        if (t == gridDim.x - 1) {                   // every CTA has read me->seq (it takes its ticket at the end)
+            me->ticket = 0u;
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&me->seq), "r"(seq) : "memory");
+        }
+    }
 }
 
 // Second half of a fused exchange: the producing kernel's last CTA already pushed (grid_publish with a
@@ -48,11 +65,11 @@ peer_push_kernel(const double* __restrict__ local, int len, PeerCtx ex) {
     peer_push(ex, local, len);
 }
 
-// One-CTA launch with programmatic stream serialization allowed (see scc_common.cuh, PDL).
+// Small launch with programmatic stream serialization allowed (see scc_common.cuh, PDL).
 template <typename Kern, typename... Args>
-static cudaError_t launch_one_cta_pdl(Kern kern, cudaStream_t st, Args... args) {
+static cudaError_t launch_ctas_pdl(int ctas, Kern kern, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(1);
+    cfg.gridDim = dim3((unsigned)ctas);
     cfg.blockDim = dim3(256);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -65,7 +82,7 @@ static cudaError_t launch_one_cta_pdl(Kern kern, cudaStream_t st, Args... args) 
 
 size_t peer_window_bytes(int max_len) {
     if (max_len < 1) return 0;
-    return peer_ll_offset(max_len) + sizeof(unsigned long long) * 2 * kPeerMaxWorld * 2 * (size_t)peer_ll_len(max_len);
+    return kPeerHeaderBytes + sizeof(unsigned long long) * 2 * kPeerMaxWorld * 2 * (size_t)max_len;
 }
 
 int peer_allreduce(const double* local, int len, double* out, void* const* windows_dev, int rank, int world,
@@ -73,7 +90,7 @@ int peer_allreduce(const double* local, int len, double* out, void* const* windo
     if (!local || !out || !windows_dev || len < 1 || len > max_len) return SCC_ERR_INVALID;
     if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world) return SCC_ERR_INVALID;
     PeerCtx ex{reinterpret_cast<unsigned char* const*>(windows_dev), rank, world, max_len};
-    SCC_CUDA(launch_one_cta_pdl(peer_allreduce_kernel, st, local, len, out, ex));
+    SCC_CUDA(launch_ctas_pdl((len + kExchangeSlice - 1) / kExchangeSlice, peer_allreduce_kernel, st, local, len, out, ex));
     return SCC_OK;
 }
 
@@ -91,7 +108,7 @@ int peer_finish(double* out, int len, void* const* windows_dev, int rank, int wo
     if (!out || !windows_dev || len < 1 || len > max_len) return SCC_ERR_INVALID;
     if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world) return SCC_ERR_INVALID;
     PeerCtx ex{reinterpret_cast<unsigned char* const*>(windows_dev), rank, world, max_len};
-    SCC_CUDA(launch_one_cta_pdl(peer_finish_kernel, st, out, len, ex));
+    SCC_CUDA(launch_ctas_pdl(1, peer_finish_kernel, st, out, len, ex));
     return SCC_OK;
 }
 

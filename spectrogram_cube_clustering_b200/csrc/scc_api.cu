@@ -240,6 +240,16 @@ int scc_gmm_finalize(const double* stats, double n_total, int d, int K, double r
                              params, ctrl, (cudaStream_t)stream);
 }
 
+int scc_gmm_em_iteration(const float* z, int64_t n, int d, int K, float* params, double* stats, int mode,
+                         double n_total, double reg_covar, double nk_eps, double tol, double* means, double* weights,
+                         double* covariances, double* prec_chol, double* ctrl, void* workspace, size_t workspace_bytes,
+                         const scc_exchange* exchange, scc_stream_t stream) {
+    scc::ExchangeDesc t;
+    return scc::gmm_em_iteration(z, n, d, K, params, stats, mode, n_total, reg_covar, nk_eps, tol, means, weights,
+                                 covariances, prec_chol, ctrl, workspace, workspace_bytes, as_desc(exchange, &t),
+                                 (cudaStream_t)stream);
+}
+
 int scc_gmm_pack_params(const double* weights, const double* means, const double* covariances, int d, int K,
                         double* prec_chol, float* params, double* ctrl, scc_stream_t stream) {
     return scc::gmm_pack_params(weights, means, covariances, d, K, prec_chol, params, ctrl, (cudaStream_t)stream);

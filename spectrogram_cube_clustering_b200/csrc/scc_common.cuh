@@ -245,46 +245,31 @@ struct ZRing {
 
 // ----------------------------------------------------------------------------
 // Peer-memory exchange window (see peer_exchange.cu).  Layout, identical on every rank:
-//   [0, 512)            header {seq, flags[2][16]}
-//   fence/flag slots    double [2 parity][16 src rank][max_len]          (vectors longer than kPeerLLMax)
-//   LL cells            uint64 [2 parity][16 src rank][2 * ll_len]       (ll_len = min(max_len, kPeerLLMax))
-// Short vectors (every DEC statistic: K+1 and K*d+2 doubles) travel "flag in data" (LL): each double is
-// shipped as two naturally aligned 8-byte words {32 data bits, 32-bit sequence number}, written with plain
-// relaxed system-scope stores (an aligned 8-byte scalar store is single-copy atomic, also over NVLink).  The
-// receiver polls the words themselves until they carry the sequence number of this exchange: no
-// __threadfence_system, no separate flag round trip.  Cells are double-buffered by sequence parity (a rank
-// can be at most one exchange ahead of the slowest: to start exchange n+2 it needs everybody's n+1 data,
-// which a rank only sends after it has consumed exchange n), and a stale cell carries seq - 2.
-// Long vectors (GMM moments) keep the bandwidth-friendlier fence + flag protocol.
-// `push` runs in ONE CTA (the last CTA of a statistics kernel, or a one-CTA exchange kernel); `pull` in
-// the same CTA right after it (complete all-reduce inside the kernel) or in every CTA of the consumer.
+//   [0, 512)      header {seq, ticket}
+//   LL cells      uint64 [2 parity][16 src rank][2 * max_len]
+// Every vector travels "flag in data" (LL): each double is shipped as two naturally aligned 8-byte words
+// {32 data bits, 32-bit sequence number}, written with plain relaxed system-scope stores (an aligned 8-byte
+// scalar store is single-copy atomic, also over NVLink).  The receiver polls the words themselves until they
+// carry the sequence number of this exchange: no __threadfence_system, no separate flag round trip, and no
+// ordering between elements — so a long vector can be exchanged by many CTAs, each owning a slice.
+// Cells are double-buffered by sequence parity (a rank can be at most one exchange ahead of the slowest: to
+// start exchange n+2 it needs everybody's n+1 data, which a rank only sends after it has consumed exchange n),
+// and a stale cell carries seq - 2.
+// `push` runs in ONE CTA (the last CTA of a statistics kernel) or slice-wise in every CTA of an exchange kernel;
+// `pull` in the same CTA right after it (complete all-reduce inside the kernel) or in every CTA of the consumer.
 // ----------------------------------------------------------------------------
 constexpr int kPeerMaxWorld = 16;
-constexpr int kPeerLLMax = 1024;
 constexpr size_t kPeerHeaderBytes = 512;
 struct PeerHeader {
     unsigned int seq;
-    unsigned int pad[31];
-    unsigned int flags[2][kPeerMaxWorld];
+    unsigned int ticket;            // multi-CTA exchange kernels: CTAs that have finished their slice
+    unsigned int pad[126];
 };
 struct PeerCtx {                    // by value inside kernel argument structs
     unsigned char* const* windows;  // device array of `world` window base pointers (nullptr = no exchange)
     int rank, world, max_len;
 };
 
-__host__ __device__ __forceinline__ int peer_ll_len(int max_len) { return max_len < kPeerLLMax ? max_len : kPeerLLMax; }
-__host__ __device__ __forceinline__ size_t peer_ll_offset(int max_len) {
-    return kPeerHeaderBytes + sizeof(double) * 2 * kPeerMaxWorld * (size_t)max_len;
-}
-
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -298,44 +283,65 @@ __device__ __forceinline__ unsigned int ld_relaxed_gpu_u32(const unsigned int* p
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ double* peer_slot(unsigned char* window, int parity, int src_rank, int max_len) {
-    return reinterpret_cast<double*>(window + kPeerHeaderBytes) + ((size_t)parity * kPeerMaxWorld + src_rank) * max_len;
-}
 __device__ __forceinline__ unsigned long long* peer_ll_slot(unsigned char* window, int parity, int src_rank, int max_len) {
-    return reinterpret_cast<unsigned long long*>(window + peer_ll_offset(max_len)) +
-           ((size_t)parity * kPeerMaxWorld + src_rank) * 2 * peer_ll_len(max_len);
+    return reinterpret_cast<unsigned long long*>(window + kPeerHeaderBytes) +
+           ((size_t)parity * kPeerMaxWorld + src_rank) * 2 * (size_t)max_len;
 }
 
-// All threads of ONE CTA: ship src[0..len) (shared or global memory, already visible to the CTA) to every
-// rank's window (own window included).  Advances the local sequence number and returns it.  Ends with a
-// CTA barrier, so src may be overwritten afterwards.  Kept out of line: it runs once per kernel, in one CTA,
-// and must not weigh on the register allocation of the streaming loops.
+// Ship elements [lo, hi) of a vector (src[i - lo] holds element i; shared or global memory, visible to the CTA)
+// to every rank's window (own window included) under sequence number seq.  All threads of the CTA; no barrier.
+__device__ __forceinline__ void peer_push_slice(const PeerCtx& ex, const double* src, int lo, int hi, unsigned int seq) {
+    const int parity = seq & 1u;
+    const int nw = 2 * (hi - lo);
+    for (int w = threadIdx.x; w < nw * ex.world; w += blockDim.x) {
+        const int r = w / nw, e = w - r * nw;
+        const double v = src[e >> 1];
+        const unsigned int word = (e & 1) ? (unsigned int)__double2hiint(v) : (unsigned int)__double2loint(v);
+        st_relaxed_sys_u64(peer_ll_slot(ex.windows[r], parity, ex.rank, ex.max_len) + 2 * lo + e,
+                           ((unsigned long long)seq << 32) | word);
+    }
+}
+
+// Wait for elements [lo, hi) of exchange `seq` from every rank and write their rank-ordered sums to
+// dst[i - lo].  All threads of the CTA; no barrier.
+__device__ __forceinline__ void peer_pull_slice(const PeerCtx& ex, double* dst, int lo, int hi, unsigned int seq) {
+    const int parity = seq & 1u;
+    const unsigned long long* base = peer_ll_slot(ex.windows[ex.rank], parity, 0, ex.max_len);
+    const size_t rstride = 2 * (size_t)ex.max_len;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        double acc = 0.0;
+        for (int r0 = 0; r0 < ex.world; r0 += 4) {              // 8 polls in flight, summed in rank order
+            unsigned long long wlo[4], whi[4];
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (r0 + u < ex.world) {
+                        const unsigned long long* c = base + (size_t)(r0 + u) * rstride + 2 * i;
+                        wlo[u] = ld_relaxed_sys_u64(c);
+                        whi[u] = ld_relaxed_sys_u64(c + 1);
+                        ok = ok && (unsigned int)(wlo[u] >> 32) == seq && (unsigned int)(whi[u] >> 32) == seq;
+                    }
+                }
+            } while (!ok);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + u < ex.world) acc += __hiloint2double((int)(unsigned int)whi[u], (int)(unsigned int)wlo[u]);
+        }
+        dst[i - lo] = acc;
+    }
+}
+
+// All threads of ONE CTA: ship src[0..len) to every rank's window.  Advances the local sequence number and
+// returns it.  Ends with a CTA barrier, so src may be overwritten afterwards.  Kept out of line: it runs once per
+// kernel, in one CTA, and must not weigh on the register allocation of the streaming loops.
 static __device__ __noinline__ unsigned int peer_push(const PeerCtx& ex, const double* src, int len) {
     PeerHeader* me = reinterpret_cast<PeerHeader*>(ex.windows[ex.rank]);
     const unsigned int seq = ld_relaxed_gpu_u32(&me->seq) + 1u;
-    const int parity = seq & 1u;
-    const int nt = blockDim.x, tid = threadIdx.x;
-    if (len <= kPeerLLMax) {
-        const int nw = 2 * len;
-        for (int w = tid; w < nw * ex.world; w += nt) {
-            const int r = w / nw, e = w - r * nw;
-            const double v = src[e >> 1];
-            const unsigned int word = (e & 1) ? (unsigned int)__double2hiint(v) : (unsigned int)__double2loint(v);
-            st_relaxed_sys_u64(peer_ll_slot(ex.windows[r], parity, ex.rank, ex.max_len) + e,
-                               ((unsigned long long)seq << 32) | word);
-        }
-        __syncthreads();                            // every thread has read me->seq and src
-    } else {
-        for (int w = tid; w < len * ex.world; w += nt) {
-            const int r = w / len, i = w - r * len;
-            peer_slot(ex.windows[r], parity, ex.rank, ex.max_len)[i] = src[i];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < ex.world)
-            st_release_sys(&reinterpret_cast<PeerHeader*>(ex.windows[tid])->flags[parity][ex.rank], seq);
-    }
-    if (tid == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&me->seq), "r"(seq) : "memory");
+    peer_push_slice(ex, src, 0, len, seq);
+    __syncthreads();                                // every thread has read me->seq and src
+    if (threadIdx.x == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&me->seq), "r"(seq) : "memory");
     return seq;
 }
 
@@ -344,44 +350,7 @@ static __device__ __noinline__ unsigned int peer_push(const PeerCtx& ex, const d
 static __device__ __noinline__ void peer_pull(const PeerCtx& ex, double* dst, int len, unsigned int seq = 0u) {
     PeerHeader* me = reinterpret_cast<PeerHeader*>(ex.windows[ex.rank]);
     if (seq == 0u) seq = ld_relaxed_gpu_u32(&me->seq);
-    const int parity = seq & 1u;
-    const int nt = blockDim.x, tid = threadIdx.x;
-    if (len <= kPeerLLMax) {
-        const unsigned long long* base = peer_ll_slot(ex.windows[ex.rank], parity, 0, ex.max_len);
-        const size_t rstride = 2 * (size_t)peer_ll_len(ex.max_len);
-        for (int i = tid; i < len; i += nt) {
-            double acc = 0.0;
-            for (int r0 = 0; r0 < ex.world; r0 += 4) {              // 8 polls in flight, summed in rank order
-                unsigned long long lo[4], hi[4];
-                bool ok;
-                do {
-                    ok = true;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (r0 + u < ex.world) {
-                            const unsigned long long* c = base + (size_t)(r0 + u) * rstride + 2 * i;
-                            lo[u] = ld_relaxed_sys_u64(c);
-                            hi[u] = ld_relaxed_sys_u64(c + 1);
-                            ok = ok && (unsigned int)(lo[u] >> 32) == seq && (unsigned int)(hi[u] >> 32) == seq;
-                        }
-                    }
-                } while (!ok);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (r0 + u < ex.world) acc += __hiloint2double((int)(unsigned int)hi[u], (int)(unsigned int)lo[u]);
-            }
-            dst[i] = acc;
-        }
-    } else {
-        if (tid < ex.world)
-            while (ld_acquire_sys(&me->flags[parity][tid]) != seq) {}
-        __syncthreads();
-        for (int i = tid; i < len; i += nt) {
-            double acc = 0.0;
-            for (int r = 0; r < ex.world; ++r) acc += __ldcv(peer_slot(ex.windows[ex.rank], parity, r, ex.max_len) + i);
-            dst[i] = acc;
-        }
-    }
+    peer_pull_slice(ex, dst, 0, len, seq);
     __syncthreads();
 }
 

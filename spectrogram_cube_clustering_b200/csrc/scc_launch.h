@@ -123,6 +123,9 @@ int gmm_em_step(const float* z, int64_t n, int d, int K, const float* params, do
 int gmm_finalize(const double* stats, double n_total, int d, int K, double reg_covar, double nk_eps, double tol,
                  double* means, double* weights, double* covariances, double* prec_chol, float* params,
                  double* ctrl, cudaStream_t st);
+int gmm_em_iteration(const float* z, int64_t n, int d, int K, float* params, double* stats, int mode, double n_total,
+                     double reg_covar, double nk_eps, double tol, double* means, double* weights, double* covariances,
+                     double* prec_chol, double* ctrl, void* ws, size_t ws_bytes, const ExchangeDesc* ex, cudaStream_t st);
 int gmm_pack_params(const double* weights, const double* means, const double* covariances, int d, int K,
                     double* prec_chol, float* params, double* ctrl, cudaStream_t st);
 

@@ -269,6 +269,23 @@ class LatentBuffer:
         return stats
 
 
+    def gmm_em_iteration(self, K: int, params, stats, means, weights, covariances, prec_chol, ctrl,
+                         reg_covar: float = 1e-6, nk_eps: float = 10 * 2.220446049250313e-16, tol: float = 1e-3):
+        """One EM iteration over the sharded set: statistics kernel + one tail kernel that reduces, all-reduces
+        (peer exchange inside the kernel) and finalises.  Without a peer exchange on several ranks the three
+        steps run separately with the group's all_reduce in between."""
+        single = self.group is None or self.world == 1
+        fits = self.exchange is not None and stats.numel() <= self.exchange.max_len
+        if single or fits:
+            ops.gmm_em_iteration(self.z, K, params, stats, self.n_total, means, weights, covariances, prec_chol, ctrl,
+                                 reg_covar=reg_covar, nk_eps=nk_eps, tol=tol,
+                                 exchange=None if single else self.exchange.desc)
+        else:
+            self.gmm_em_pass(K, params, stats, ctrl=ctrl)
+            ops.gmm_finalize(stats, self.n_total, means, weights, covariances, prec_chol, params, ctrl,
+                             reg_covar=reg_covar, nk_eps=nk_eps, tol=tol)
+
+
 def update_interval(m: int, batch_size: int, config_update_interval: int = -1) -> int:
     """models.py:985-989."""
     if config_update_interval == -1:

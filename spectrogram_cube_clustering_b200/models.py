@@ -354,11 +354,11 @@ class GaussianMixture:
                 "increase reg_covar, or scale the input data.")
 
     def _em_iteration(self, buf: LatentBuffer):
-        """statistics kernel -> (all-reduce of the packed vector) -> finalize kernel; convergence is decided on the
-        device (a frozen fit turns all three into no-ops), so nothing here reads a result back."""
-        buf.gmm_em_pass(self.n_components, self._params, self._stats, ctrl=self._ctrl)
-        ops.gmm_finalize(self._stats, buf.n_total, self._means, self._weights, self._cov, self._pchol,
-                         self._params, self._ctrl, reg_covar=self.reg_covar, nk_eps=10 * EPS64, tol=self.tol)
+        """statistics kernel -> ONE tail kernel (fixed-order grid reduction, all-reduce of the packed vector over the
+        GPUs, M-step finalisation); convergence is decided on the device (a frozen fit turns both launches into
+        no-ops), so nothing here reads a result back."""
+        buf.gmm_em_iteration(self.n_components, self._params, self._stats, self._means, self._weights, self._cov,
+                             self._pchol, self._ctrl, reg_covar=self.reg_covar, nk_eps=10 * EPS64, tol=self.tol)
 
     def _capture(self, buf: LatentBuffer):
         """One EM iteration as a CUDA graph (every buffer it touches is persistent): a fit is then

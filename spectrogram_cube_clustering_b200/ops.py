@@ -345,6 +345,21 @@ def gmm_em_step(z, K, params, stats=None, labels=None, resp=None, ctrl=None, mod
     return stats
 
 
+def gmm_em_iteration(z, K, params, stats, n_total, means, weights, covariances, prec_chol, ctrl, mode=GMM_SOFT,
+                     reg_covar=1e-6, nk_eps=10 * 2.220446049250313e-16, tol=1e-3, exchange=None):
+    """One whole EM iteration in two launches: the fused statistics pass and ONE tail kernel (grid reduction,
+    cross-GPU all-reduce through ``exchange``, M-step finalisation).  In place on every state tensor."""
+    lib = _lib.load()
+    _require(z, "z"); _require(params, "params")
+    n, d = z.shape
+    ws = workspace(z.device, d, K)
+    rc = lib.scc_gmm_em_iteration(z.data_ptr(), n, d, K, params.data_ptr(), stats.data_ptr(), int(mode), float(n_total),
+                                  float(reg_covar), float(nk_eps), float(tol), means.data_ptr(), weights.data_ptr(),
+                                  covariances.data_ptr(), prec_chol.data_ptr(), ctrl.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  _ex(exchange), _stream())
+    _lib.check(rc, "scc_gmm_em_iteration")
+
+
 def gmm_finalize(stats, n_total, means, weights, covariances, prec_chol, params, ctrl,
                  reg_covar=1e-6, nk_eps=10 * 2.220446049250313e-16, tol=1e-3):
     """M-step finalisation on the device (in place on means/weights/covariances/prec_chol/params/ctrl)."""

@@ -34,7 +34,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_version_and_status_strings(lib):
-    assert lib.scc_abi_version() == 2
+    assert lib.scc_abi_version() == 3
     assert lib.scc_status_string(0) == b"ok"
     for code in (-1, -2, -3, -4, -5):
         assert lib.scc_status_string(code) not in (b"ok", b"unknown status")
