@@ -386,6 +386,12 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
+    if world > 1:
+        # pre-roll (untimed, same stream, no host sync after it): the ranks leave the host barrier tens of
+        # microseconds apart, and with K = 20 steps (~1 ms) that launch skew would be charged to the first timed
+        # step's exchange.  The in-kernel exchanges of these steps align the ranks ON THE DEVICE; the events
+        # below are enqueued while they still run, so they bracket exactly K steps of aligned ranks.
+        run_steps(2 * GRAPH_STEPS)
     ev0.record()
     run_steps(args.steps)
     ev1.record()
@@ -613,7 +619,9 @@ def run_gpu(args):
                                             "target + KL-gradient pass)"] if one_kernel else (
                                            ["dec_assign", "dec_target", "dec_kl_grad"] if unfused else
                                            ["dec_assign", "dec_target_kl_grad"]),
-                       "timing": "CUDA events around the K steps, max over ranks; per-kernel durations from "
+                       "timing": "CUDA events around the K steps, max over ranks (multi-GPU: preceded on the same stream by an "
+                                 "untimed pre-roll of 40 steps so that the ranks are aligned on the device when the first "
+                                 "event is reached); per-kernel durations from "
                                  "CUDA events around replays of single-kernel graphs over the same rotating sets"},
             "clocks": sampler.summary(), "e2e": e2e,
             "gpu_launches": ((1 if one_kernel else (3 if unfused else 2)) +

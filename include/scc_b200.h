@@ -347,6 +347,23 @@ int scc_dec_target_kl_grad(const float* z, int64_t n, int d, const float* mu, in
                            double* stats, void* workspace, size_t workspace_bytes,
                            const scc_exchange* pull_f, const scc_exchange* push, scc_stream_t stream);
 /*
+ * Two-launch DEC step for the shapes the one-kernel step does not cover (K*d > 160, e.g. the d = 32, K = 16 shard of
+ * BASELINE configs[3]), with a hand-off between the passes: scc_dec_assign_u also writes u_ij = 1 / (1 + d_ij / alpha)
+ * ([n, K] float32, the Student's-t kernel before normalisation) and scc_dec_target_kl_grad_u streams it back instead of
+ * recomputing the K*d distance terms — at that shape both passes are bound by the shared-memory reads of the centroid
+ * table (2 KB per point), not by HBM, so 2 x 4K extra bytes per point through HBM are the cheaper way.
+ * Other arguments as scc_dec_assign_ex / scc_dec_target_kl_grad.  Returns SCC_ERR_UNSUPPORTED for the shapes the
+ * one-kernel step serves (use scc_dec_step there).
+ */
+int scc_dec_assign_u(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
+                     float* q, int32_t* labels, const int32_t* labels_prev, float* u_out, double* stats,
+                     void* workspace, size_t workspace_bytes, const scc_exchange* push, scc_stream_t stream);
+int scc_dec_target_kl_grad_u(const float* z, int64_t n, int d, const float* mu, int K, float alpha,
+                             const float* u_in, const double* f_cols, int round_decimals, float scale,
+                             float* p_out, float* dz, double* stats, void* workspace, size_t workspace_bytes,
+                             const scc_exchange* pull_f, const scc_exchange* push, scc_stream_t stream);
+
+/*
  * scc_dec_step — the whole DEC step of one batch in ONE kernel (single GPU):
  *   pass 1 = scc_dec_assign (q, labels, f, label-change count), a grid-wide barrier that all-reduces f
  *   across the CTAs, pass 2 = scc_dec_target_kl_grad (p, loss, dL/dz, dL/dmu) with z re-read from L2.

@@ -79,6 +79,11 @@ _SIGNATURES = {
                                    c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "scc_dec_target_kl_grad": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_void_p, c_int, c_float,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "scc_dec_assign_u": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "scc_dec_target_kl_grad_u": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int,
+                                         c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                                         c_void_p]),
     "scc_dec_step": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_int, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "scc_dec_step_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_int, c_float, c_void_p, c_void_p,

@@ -183,11 +183,12 @@ static void fill_reduction(DecArgs& a, void* ws) {
 
 int dec_assign(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
                float* q, int32_t* labels, const int32_t* labels_prev, double* stats,
-               void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* push) {
+               void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* push, float* u_out) {
     int rc = check_common(z, n, d, mu, K, alpha, stats, ws, ws_bytes);
     if (rc != SCC_OK) return rc;
     if (round_decimals != 0 && round_decimals != 5) return SCC_ERR_INVALID;
     if (q && (K % 4 == 0) && (reinterpret_cast<uintptr_t>(q) & 15u)) return SCC_ERR_MISALIGNED;
+    if (u_out && (K % 4 == 0) && (reinterpret_cast<uintptr_t>(u_out) & 15u)) return SCC_ERR_MISALIGNED;
     if (n == 0) {
         SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * (K + 1), st));
         if (push && push->windows) return peer_push_only(stats, K + 1, push->windows, push->rank, push->world, push->max_len, st);
@@ -195,7 +196,7 @@ int dec_assign(const float* z, int64_t n, int d, const float* mu, int K, float a
     }
     DecArgs a{};
     a.z = z; a.n = n; a.mu = mu; a.K = K; a.alpha = alpha; a.round5 = round_decimals == 5;
-    a.q = q; a.labels = labels; a.labels_prev = labels_prev; a.stats = stats;
+    a.q = q; a.labels = labels; a.labels_prev = labels_prev; a.stats = stats; a.u_out = u_out;
     fill_reduction(a, ws);
     fill_exchange(a, push, /*push=*/1, nullptr);
 #define SCC_CASE(D_, X) if (d == D_) return dec_assign_dim##D_(a, st);
@@ -214,10 +215,12 @@ static int dec_grad_dispatch(const DecArgs& a, int d, int mode, cudaStream_t st)
 int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* p,
                 const double* f_cols, int round_decimals, float scale, float* dz, double* stats,
                 void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* pull_f, const ExchangeDesc* push,
-                float* p_out) {
+                float* p_out, const float* u_in) {
     int rc = check_common(z, n, d, mu, K, alpha, stats, ws, ws_bytes);
     if (rc != SCC_OK) return rc;
     if (!p && !f_cols && !(pull_f && pull_f->windows)) return SCC_ERR_INVALID;
+    if (u_in && p) return SCC_ERR_INVALID;             // the hand-off replaces the distance loop of the fused mode
+    if (u_in && (K % 4 == 0) && (reinterpret_cast<uintptr_t>(u_in) & 15u)) return SCC_ERR_MISALIGNED;
     if (p && p_out) return SCC_ERR_INVALID;            // the target is either given or produced, not both
     if (p_out && (K % 4 == 0) && (reinterpret_cast<uintptr_t>(p_out) & 15u)) return SCC_ERR_MISALIGNED;
     if (round_decimals != 0 && round_decimals != 5) return SCC_ERR_INVALID;
@@ -231,10 +234,10 @@ int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float 
     }
     DecArgs a{};
     a.z = z; a.n = n; a.mu = mu; a.K = K; a.alpha = alpha; a.round5 = round_decimals == 5;
-    a.p = p; a.p_out = p_out; a.f_cols = f_cols; a.scale = scale; a.dz = dz; a.stats = stats;
+    a.p = p; a.p_out = p_out; a.f_cols = f_cols; a.scale = scale; a.dz = dz; a.stats = stats; a.u_in = u_in;
     fill_reduction(a, ws);
     fill_exchange(a, push, /*push + collect in the kernel's tail=*/2, p ? nullptr : pull_f);
-    return dec_grad_dispatch(a, d, p ? MODE_KL : MODE_KLF, st);
+    return dec_grad_dispatch(a, d, p ? MODE_KL : (u_in ? MODE_KLU : MODE_KLF), st);
 }
 
 int dec_step(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals, float scale,

@@ -30,6 +30,11 @@ int SCC_CAT(dec_grad_dim, SCC_DIM)(const DecArgs& a, int mode, cudaStream_t st) 
         if (kp == 8) return DecOps<SCC_DIM, 8>::template grad<MODE_KLF>(a, st);
         return DecOps<SCC_DIM, 16>::template grad<MODE_KLF>(a, st);
     }
+    if (mode == MODE_KLU) {
+        if (kp == 4) return DecOps<SCC_DIM, 4>::template grad<MODE_KLU>(a, st);
+        if (kp == 8) return DecOps<SCC_DIM, 8>::template grad<MODE_KLU>(a, st);
+        return DecOps<SCC_DIM, 16>::template grad<MODE_KLU>(a, st);
+    }
     if (mode == MODE_STEP) {
         if (kp == 4) return DecOps<SCC_DIM, 4>::template grad<MODE_STEP>(a, st);
         if (kp == 8) return DecOps<SCC_DIM, 8>::template grad<MODE_STEP>(a, st);

@@ -223,7 +223,8 @@ __device__ __forceinline__ void cta_reduce(const float (&v)[NV], double* scratch
 template <int D, int KP, bool EXACT, bool ALPHA1, int P>
 __device__ __forceinline__ void soft_assign_rows(const float (&z)[P][D], const float2* __restrict__ nmuT2,
                                                  int K, float inv_alpha, float expo, bool round5,
-                                                 float2 (&q2)[P][KP / 2], int (&label)[P]) {
+                                                 float2 (&q2)[P][KP / 2], int (&label)[P],
+                                                 float* const (&u_out)[P]) {
     constexpr int JP = KP / 2;
     float2 acc2[P][JP];
     sq_distances<D, KP, P>(z, nmuT2, acc2);
@@ -232,6 +233,7 @@ __device__ __forceinline__ void soft_assign_rows(const float (&z)[P][D], const f
         float2 w2[JP], u2[JP];
         float tsum, best;
         student_t_pairs<KP, EXACT, ALPHA1, true>(acc2[r], K, inv_alpha, expo, w2, u2, q2[r], tsum, label[r], best);
+        if (u_out[r]) store_krow2<KP, EXACT>(u_out[r], K, u2);      // hand-off to the gradient pass (MODE_KLU)
         const float inv = rcp_approx(tsum);
 #pragma unroll
         for (int jp = 0; jp < JP; ++jp) {
@@ -243,10 +245,18 @@ __device__ __forceinline__ void soft_assign_rows(const float (&z)[P][D], const f
 
 // points per thread of the assign pass (tile = 256 * P points)
 template <int D, int KP>
-__host__ __device__ constexpr int assign_ppt() { return (KP * D <= 96) ? 2 : 1; }
+__host__ __device__ constexpr int assign_ppt() {
+#ifdef SCC_ASSIGN_PPT2
+    return 2;                           // A/B builds
+#else
+    return (KP * D <= 96) ? 2 : 1;
+#endif
+}
 template <int D, int KP>
 __host__ __device__ constexpr int assign_stages() {
-    return RowLayout<D>::kDense ? (assign_ppt<D, KP>() == 2 ? 3 : 4) : (RowLayout<D>::kVec4 ? 3 : 2);
+    // stages x 256 * P rows must leave room for two CTAs per SM where the registers allow them
+    return RowLayout<D>::kDense ? (assign_ppt<D, KP>() == 2 ? 3 : 4)
+                                : (RowLayout<D>::kVec4 ? ((assign_ppt<D, KP>() == 2 && RowLayout<D>::LD >= 28) ? 2 : 3) : 2);
 }
 
 // ---------------------------------------------------------------------------
@@ -313,7 +323,11 @@ dec_assign_kernel(const DecArgs a) {
         if (active[0]) {
             float2 q2[P][JP];
             int label[P];
-            soft_assign_rows<D, KP, EXACT, ALPHA1, P>(zr, nmuT2, K, inv_alpha, expo, round5, q2, label);
+            float* up[P];
+#pragma unroll
+            for (int r = 0; r < P; ++r)
+                up[r] = (a.u_out && active[r]) ? a.u_out + ((size_t)tile * TILE + threadIdx.x + r * kDecThreads) * K : nullptr;
+            soft_assign_rows<D, KP, EXACT, ALPHA1, P>(zr, nmuT2, K, inv_alpha, expo, round5, q2, label, up);
 #pragma unroll
             for (int r = 0; r < P; ++r) {
                 if (active[r]) {
@@ -365,7 +379,7 @@ __device__ __forceinline__ const float* krow_operand(const DecArgs& a) {
 }
 
 template <int MODE>
-__host__ __device__ constexpr bool mode_is_kl() { return MODE == MODE_KL || MODE == MODE_KLF || MODE == MODE_STEP; }
+__host__ __device__ constexpr bool mode_is_kl() { return MODE == MODE_KL || MODE == MODE_KLF || MODE == MODE_STEP || MODE == MODE_KLU; }
 
 template <int MODE>
 __host__ __device__ __forceinline__ float grad_fold_scale(float scale, float alpha) {
@@ -392,7 +406,7 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
         if constexpr (MODE == MODE_KL) {           // target row streamed from memory
 #pragma unroll
             for (int jp = 0; jp < JP; ++jp) p2[jp] = pre2[jp];
-        } else {                                   // MODE_KLF / MODE_STEP: rebuild p from the column sums
+        } else {                                   // MODE_KLF / MODE_STEP / MODE_KLU: rebuild p from the column sums
             const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
             for (int jp = 0; jp < JP; ++jp) {
@@ -780,7 +794,8 @@ dec_grad_reg_kernel(const DecArgs a_in) {
                     load_row<D>(sp, row_in, zr[0]);
                     float2 q2[1][JP];
                     int label[1];
-                    soft_assign_rows<D, KP, EXACT, ALPHA1, 1>(zr, nmuT2, K, inv_alpha, expo, a.round5 != 0, q2, label);
+                    float* const no_u[1] = {nullptr};
+                    soft_assign_rows<D, KP, EXACT, ALPHA1, 1>(zr, nmuT2, K, inv_alpha, expo, a.round5 != 0, q2, label, no_u);
 #pragma unroll
                     for (int jp = 0; jp < JP; ++jp) facc2[jp] = __fadd2_rn(facc2[jp], q2[0][jp]);
                     if (a.q) store_krow2<KP, EXACT>(a.q + i * K, K, q2[0]);
@@ -967,7 +982,10 @@ dec_grad_tiled_kernel(const DecArgs a_in) {
     constexpr int S = 2;
     using Ring = ZRing<D, kDecTile, S, kDecThreads>;
     using L = RowLayout<D>;
-    constexpr int NB = (KP / 4) * (D / 4);            // 4x4 output blocks
+    // output blocks of W^T Z per lane: 8x8 where the shape allows (two LDS.128 of W + two of Z per 64 FMAs), else 4x4
+    constexpr int BR = (KP % 8 == 0 && D % 8 == 0) ? 8 : 4;     // clusters per block
+    constexpr int BC = BR;                                      // dimensions per block
+    constexpr int NB = (KP / BR) * (D / BC);
     constexpr int G2 = (32 / NB) > 0 ? (32 / NB) : 1; // point groups per warp
     constexpr int NW = kDecThreads / 32;
     constexpr int NSM = KP + 2;                       // loss, sum s, Wsum_j
@@ -1013,27 +1031,31 @@ dec_grad_tiled_kernel(const DecArgs a_in) {
     float small[NSM];
 #pragma unroll
     for (int s = 0; s < NSM; ++s) small[s] = 0.f;
-    float blk[16];
+    float blk[BR * BC];
 #pragma unroll
-    for (int s = 0; s < 16; ++s) blk[s] = 0.f;
+    for (int s = 0; s < BR * BC; ++s) blk[s] = 0.f;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / NB, lb = lane - grp * NB;  // lanes >= G2*NB idle in phase 2
-    const int jb = lb / (D / 4), cb = lb - jb * (D / 4);
+    const int jb = lb / (D / BC), cb = lb - jb * (D / BC);
     const bool p2_active = grp < G2;
 
-    const float* krows = krow_operand<MODE>(a);
+    const float* krows = MODE == MODE_KLU ? a.u_in : krow_operand<MODE>(a);
+    float2 nxt2[JP];                     // operand row of the next tile (requested before phase 2: latency hidden)
+#pragma unroll
+    for (int jp = 0; jp < JP; ++jp) nxt2[jp] = make_float2(0.f, 0.f);
+    if (krows && (int)blockIdx.x < ring.num_tiles && (int)threadIdx.x < ring.points(blockIdx.x))
+        load_krow2<KP, EXACT>(krows + ((size_t)blockIdx.x * kDecTile + threadIdx.x) * K, K, nxt2);
     int stage = 0;
     uint32_t use = 0;
     for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G) {
         const int np = ring.points(tile);
         const int64_t base = (int64_t)tile * kDecTile;
         const bool active = (int)threadIdx.x < np;
+        // the [n, K] operand row (target p / upstream dL/dq / handed-over u) was requested one tile ahead
         float2 pre2[JP];
 #pragma unroll
-        for (int jp = 0; jp < JP; ++jp) pre2[jp] = make_float2(0.f, 0.f);
-        // the [n, K] operand row (target p / upstream dL/dq) is requested before the wait on the z tile
-        if (krows && active) load_krow2<KP, EXACT>(krows + ((size_t)base + threadIdx.x) * K, K, pre2);
+        for (int jp = 0; jp < JP; ++jp) pre2[jp] = nxt2[jp];
         ring.wait(stage, tile, use);
         float* ztile = ring.stage_ptr(stage);
         float2 coef2[JP];
@@ -1043,12 +1065,33 @@ dec_grad_tiled_kernel(const DecArgs a_in) {
             float zr[1][D];
             load_row<D>(ztile, threadIdx.x, zr[0]);
             const size_t i = (size_t)base + threadIdx.x;
-            float2 acc2[1][JP], w2[JP], u2[JP], t2[JP];
-            sq_distances<D, KP, 1>(zr, nmuT2, acc2);
-            int label;
-            float best, tsum;
-            student_t_pairs<KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(acc2[0], K, inv_alpha, expo, w2, u2, t2, tsum,
-                                                                    label, best);
+            float2 w2[JP], u2[JP], t2[JP];
+            int label = 0;
+            float best = 0.f, tsum;
+            if constexpr (MODE == MODE_KLU) {
+                // u_ij = 1 / (1 + d_ij / alpha) handed over by the assign pass: no distance loop (the centroid table
+                // reads of that loop are what bounds this kernel: shared-memory return bandwidth)
+#pragma unroll
+                for (int jp = 0; jp < JP; ++jp) u2[jp] = pre2[jp];
+                float2 ts2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int jp = 0; jp < JP; ++jp) {
+                    const bool vx = EXACT || 2 * jp < K, vy = EXACT || 2 * jp + 1 < K;
+                    const float2 uu = u2[jp];
+                    float2 ww = make_float2(rcp_approx(vx ? uu.x : 1.f), rcp_approx(vy ? uu.y : 1.f));
+                    float2 tt = ALPHA1 ? uu : make_float2(ex2_approx(expo * lg2_approx(vx ? uu.x : 1.f)),
+                                                          ex2_approx(expo * lg2_approx(vy ? uu.y : 1.f)));
+                    if (!EXACT) { tt = pair_sel(vx, vy, tt, 0.f); u2[jp] = pair_sel(vx, vy, uu, 0.f); }
+                    w2[jp] = ww; t2[jp] = tt;
+                    ts2 = __fadd2_rn(ts2, tt);
+                }
+                tsum = ts2.x + ts2.y;
+            } else {
+                float2 acc2[1][JP];
+                sq_distances<D, KP, 1>(zr, nmuT2, acc2);
+                student_t_pairs<KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(acc2[0], K, inv_alpha, expo, w2, u2, t2, tsum,
+                                                                        label, best);
+            }
             grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f2, w2, u2, t2, tsum, expo, label, best, pre2, coef2,
                                                        small[0], small[1]);
             float2 c2 = make_float2(0.f, 0.f);
@@ -1074,21 +1117,31 @@ dec_grad_tiled_kernel(const DecArgs a_in) {
             *reinterpret_cast<float4*>(w_tile + threadIdx.x * KP + j) =
                 make_float4(coef2[j / 2].x, coef2[j / 2].y, coef2[j / 2 + 1].x, coef2[j / 2 + 1].y);
         __syncthreads();
+        {   // request the next tile's operand row now: it lands during phase 2
+            const int nt = tile + G;
+            if (krows && nt < ring.num_tiles && (int)threadIdx.x < ring.points(nt))
+                load_krow2<KP, EXACT>(krows + ((size_t)nt * kDecTile + threadIdx.x) * K, K, nxt2);
+        }
         if (want_dz) copy_tile_out<D, kDecThreads>(out_tile, a.dz + (size_t)base * D, np);
         if (p2_active) {
             for (int r = warp * G2 + grp; r < np; r += NW * G2) {
-                const float4 w = *reinterpret_cast<const float4*>(w_tile + r * KP + 4 * jb);
-                const float4 x = *reinterpret_cast<const float4*>(ztile + r * L::LD + 4 * cb);
-                // scalar FMAs on purpose: the packed form (8 FFMA2 with a broadcast coefficient) was measured
-                // 7 % SLOWER for d = 32, K = 16 — this phase is bound by its two LDS.128 per 16 FMAs
-                blk[0] = fmaf(w.x, x.x, blk[0]);  blk[1] = fmaf(w.x, x.y, blk[1]);
-                blk[2] = fmaf(w.x, x.z, blk[2]);  blk[3] = fmaf(w.x, x.w, blk[3]);
-                blk[4] = fmaf(w.y, x.x, blk[4]);  blk[5] = fmaf(w.y, x.y, blk[5]);
-                blk[6] = fmaf(w.y, x.z, blk[6]);  blk[7] = fmaf(w.y, x.w, blk[7]);
-                blk[8] = fmaf(w.z, x.x, blk[8]);  blk[9] = fmaf(w.z, x.y, blk[9]);
-                blk[10] = fmaf(w.z, x.z, blk[10]); blk[11] = fmaf(w.z, x.w, blk[11]);
-                blk[12] = fmaf(w.w, x.x, blk[12]); blk[13] = fmaf(w.w, x.y, blk[13]);
-                blk[14] = fmaf(w.w, x.z, blk[14]); blk[15] = fmaf(w.w, x.w, blk[15]);
+                // this phase is bound by its shared-memory reads (return bandwidth 128 B/clk/SM): BR/4 + BC/4 LDS.128
+                // per BR*BC FMAs.  Scalar FMAs on purpose: the packed form was measured slower here (round 1).
+                float wv[BR], xv[BC];
+#pragma unroll
+                for (int h = 0; h < BR / 4; ++h) {
+                    const float4 w = *reinterpret_cast<const float4*>(w_tile + r * KP + BR * jb + 4 * h);
+                    wv[4 * h] = w.x; wv[4 * h + 1] = w.y; wv[4 * h + 2] = w.z; wv[4 * h + 3] = w.w;
+                }
+#pragma unroll
+                for (int h = 0; h < BC / 4; ++h) {
+                    const float4 x = *reinterpret_cast<const float4*>(ztile + r * L::LD + BC * cb + 4 * h);
+                    xv[4 * h] = x.x; xv[4 * h + 1] = x.y; xv[4 * h + 2] = x.z; xv[4 * h + 3] = x.w;
+                }
+#pragma unroll
+                for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+                    for (int cc = 0; cc < BC; ++cc) blk[rr * BC + cc] = fmaf(wv[rr], xv[cc], blk[rr * BC + cc]);
             }
         }
         __syncthreads();                 // phase 2 done: stage, w_tile and out_tile reusable
@@ -1099,20 +1152,20 @@ dec_grad_tiled_kernel(const DecArgs a_in) {
     pdl_trigger();
     if (mode_is_kl<MODE>()) small[0] *= a.scale * 0.693147180559945f;      // loss = scale * ln2 * sum p log2(p/q)
     cta_reduce<NSM, kDecThreads>(small, scratch, small_s);
-    // per-(warp, group) 4x4 partials -> shared (the ring buffer is free now), fixed-order sum
-    double* part = reinterpret_cast<double*>(ring_buf);                      // [NW*G2][KP*D]
+    // per-(warp, group) block partials -> shared (the ring buffer is free now), fixed-order sum in float64
+    float* part = ring_buf;                                                  // [NW*G2][KP*D] (fp32 values as accumulated)
     if (p2_active) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < BR; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                part[(size_t)(warp * G2 + grp) * (KP * D) + (4 * jb + r) * D + 4 * cb + c] = (double)blk[4 * r + c];
+            for (int c = 0; c < BC; ++c)
+                part[(size_t)(warp * G2 + grp) * (KP * D) + (BR * jb + r) * D + BC * cb + c] = blk[r * BC + c];
     }
     __syncthreads();
     for (int o = threadIdx.x; o < K * D; o += kDecThreads) {
         double accd = 0.0;
 #pragma unroll
-        for (int g = 0; g < NW * G2; ++g) accd += part[(size_t)g * (KP * D) + o];
+        for (int g = 0; g < NW * G2; ++g) accd += (double)part[(size_t)g * (KP * D) + o];
         const double v = accd - small_s[2 + o / D] * (double)mc_s[o];
         cta_stats[2 + o] = (MODE == MODE_KMEANS) ? v : -(double)cs * v;
     }
@@ -1146,7 +1199,8 @@ constexpr size_t grad_reg_smem() {
 template <int D, int KP>
 constexpr size_t grad_tiled_smem() {
     constexpr int S = 2;
-    constexpr int NB = (KP / 4) * (D / 4);
+    constexpr int BR = (KP % 8 == 0 && D % 8 == 0) ? 8 : 4;
+    constexpr int NB = (KP / BR) * (D / BR);
     constexpr int G2 = (32 / NB) > 0 ? (32 / NB) : 1;
     constexpr int NW = kDecThreads / 32;
     constexpr int NSM = KP + 2;
@@ -1154,8 +1208,8 @@ constexpr size_t grad_tiled_smem() {
     size_t bytes = sizeof(float) * ((S + 1) * kDecTile * RowLayout<D>::LD + kDecTile * KP + 4 * KP * Pairs<D>::N +
                                     KP * D + D + KP) +
                    sizeof(double) * (scr + NSM + KP * D + 2 + KP) + sizeof(uint64_t) * S;
-    // the ring buffer is reused for the [NW*G2][KP*D] float64 partials at the end
-    const size_t part = sizeof(double) * NW * G2 * KP * D;
+    // the ring buffer is reused for the [NW*G2][KP*D] float partials at the end
+    const size_t part = sizeof(float) * NW * G2 * KP * D;
     const size_t ring = sizeof(float) * S * kDecTile * RowLayout<D>::LD;
     if (part > ring) bytes += part - ring;
     return bytes;
@@ -1212,8 +1266,11 @@ struct DecOps {
             else
                 return SCC_ERR_UNSUPPORTED;
         } else {
-            return launch_dec(dec_grad_reg_kernel<D, KP, EXACT, A1, MODE>, a, grad_reg_smem<D, KP>(), st, kRegThreads,
-                              MODE == MODE_STEP, kRegThreads);
+            if constexpr (MODE == MODE_KLU)
+                return SCC_ERR_UNSUPPORTED;          // register-blocked shapes run the one-kernel step instead
+            else
+                return launch_dec(dec_grad_reg_kernel<D, KP, EXACT, A1, MODE>, a, grad_reg_smem<D, KP>(), st, kRegThreads,
+                                  MODE == MODE_STEP, kRegThreads);
         }
     }
     template <int MODE>

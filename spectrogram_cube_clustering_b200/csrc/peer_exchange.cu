@@ -2,11 +2,11 @@
 // GPUs of one NVSwitch box, over peer memory (NVLink P2P stores), in ONE small kernel.
 //
 // The clustering passes exchange only O(K d^2) doubles (<= 72 KB), so the collective is
-// latency-bound: an NCCL all-reduce costs ~15 us of launch + protocol per call, two per DEC step,
-// against an ~80 us step.  Here every rank pushes its vector straight into a slot of every
-// peer's exchange window (symmetric allocation), publishes a sequence flag with system-scope
-// release semantics, waits for the world's flags and sums the slots in RANK ORDER — every rank
-// gets the bit-identical result (replicas stay in lockstep), no ring, no staging copies.
+// latency-bound: an NCCL all-reduce costs ~17-32 us of launch + protocol per call, two per DEC step,
+// against a ~50 us step.  Here every rank pushes its vector straight into the cells of every
+// peer's exchange window (symmetric allocation) as {data, sequence number} words, polls its own
+// window for the world's words and sums them in RANK ORDER — every rank gets the bit-identical
+// result (replicas stay in lockstep), no ring, no staging copies, no system-scope fence.
 //
 // Window layout (identical on every rank; slots double-buffered by sequence parity so a fast rank
 // can run at most one exchange ahead of the slowest without overwriting unread data):
@@ -40,10 +40,11 @@ peer_allreduce_kernel(const double* __restrict__ local, int len, double* __restr
     peer_pull_slice(ex, out + lo, lo, hi, seq);
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int t;
-        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(&me->ticket) : "memory");
+        unsigned int t = 0u;
+        if (gridDim.x > 1)
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(&me->ticket) : "memory");
         if (t == gridDim.x - 1) {                   // every CTA has read me->seq (it takes its ticket at the end)
-            me->ticket = 0u;
+            if (gridDim.x > 1) me->ticket = 0u;
             asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&me->seq), "r"(seq) : "memory");
         }
     }

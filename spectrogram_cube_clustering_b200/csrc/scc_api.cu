@@ -198,6 +198,24 @@ int scc_dec_target_kl_grad(const float* z, int64_t n, int d, const float* mu, in
                             workspace_bytes, (cudaStream_t)stream, as_desc(pull_f, &t1), as_desc(push, &t2), p_out);
 }
 
+int scc_dec_assign_u(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
+                     float* q, int32_t* labels, const int32_t* labels_prev, float* u_out, double* stats, void* workspace,
+                     size_t workspace_bytes, const scc_exchange* push, scc_stream_t stream) {
+    scc::ExchangeDesc t;
+    return scc::dec_assign(z, n, d, mu, K, alpha, round_decimals, q, labels, labels_prev, stats, workspace,
+                           workspace_bytes, (cudaStream_t)stream, as_desc(push, &t), u_out);
+}
+
+int scc_dec_target_kl_grad_u(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* u_in,
+                             const double* f_cols, int round_decimals, float scale, float* p_out, float* dz,
+                             double* stats, void* workspace, size_t workspace_bytes, const scc_exchange* pull_f,
+                             const scc_exchange* push, scc_stream_t stream) {
+    if (!u_in) return SCC_ERR_INVALID;
+    scc::ExchangeDesc t1, t2;
+    return scc::dec_kl_grad(z, n, d, mu, K, alpha, nullptr, f_cols, round_decimals, scale, dz, stats, workspace,
+                            workspace_bytes, (cudaStream_t)stream, as_desc(pull_f, &t1), as_desc(push, &t2), p_out, u_in);
+}
+
 int scc_dec_step(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
                  float scale, float* q, int32_t* labels, const int32_t* labels_prev, double* f_stats, float* p_out,
                  float* dz, double* stats, void* workspace, size_t workspace_bytes, scc_stream_t stream) {

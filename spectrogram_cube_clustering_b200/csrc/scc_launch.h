@@ -21,7 +21,8 @@ constexpr size_t kWorkspaceHeader = 256;   // counters live in front of the part
 
 // MODE_KL: target p streamed from memory;  MODE_KLF: p rebuilt in registers from the column sums (fused mode)
 // MODE_STEP: MODE_KLF preceded, in the same (cooperative) kernel, by the assign pass and a grid-wide all-reduce of f
-enum { MODE_KL = 0, MODE_GENERIC = 1, MODE_KMEANS = 2, MODE_KLF = 3, MODE_STEP = 4 };
+// MODE_KLU: MODE_KLF with the Student's-t u_ij streamed from memory (written by the assign pass) instead of recomputed
+enum { MODE_KL = 0, MODE_GENERIC = 1, MODE_KMEANS = 2, MODE_KLF = 3, MODE_STEP = 4, MODE_KLU = 5 };
 
 struct DecArgs {
     const float* z;
@@ -35,6 +36,8 @@ struct DecArgs {
     int32_t* labels;
     const int32_t* labels_prev;
     float* mindist;            // MODE_KMEANS: squared distance to the nearest centre, or NULL
+    float* u_out;              // assign: [n, K] u_ij = 1 / (1 + d_ij / alpha) for a following MODE_KLU pass, or NULL
+    const float* u_in;         // MODE_KLU
     // grad
     const float* p;
     float* p_out;              // fused mode (p == NULL): also write the rebuilt target rows here, or NULL
@@ -88,7 +91,7 @@ bool gmm_supported(int d, int K);
 
 int dec_assign(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals,
                float* q, int32_t* labels, const int32_t* labels_prev, double* stats,
-               void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* push = nullptr);
+               void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* push = nullptr, float* u_out = nullptr);
 int dec_target(const float* q, int64_t n, int K, double* f, int round_decimals, float* p, cudaStream_t st,
                const ExchangeDesc* pull = nullptr);
 int peer_finish(double* out, int len, void* const* windows_dev, int rank, int world, int max_len, cudaStream_t st);
@@ -98,7 +101,7 @@ int colsum(const float* q, int64_t n, int K, double* f, void* ws, size_t ws_byte
 int dec_kl_grad(const float* z, int64_t n, int d, const float* mu, int K, float alpha, const float* p,
                 const double* f_cols, int round_decimals, float scale, float* dz, double* stats,
                 void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* pull_f = nullptr,
-                const ExchangeDesc* push = nullptr, float* p_out = nullptr);
+                const ExchangeDesc* push = nullptr, float* p_out = nullptr, const float* u_in = nullptr);
 int dec_step(const float* z, int64_t n, int d, const float* mu, int K, float alpha, int round_decimals, float scale,
              float* q, int32_t* labels, const int32_t* labels_prev, double* f_stats, float* p_out, float* dz,
              double* stats, void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeDesc* ex = nullptr);

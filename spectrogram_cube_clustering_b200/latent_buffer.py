@@ -119,6 +119,7 @@ class LatentBuffer:
         self._row_offset = None     # global index of this shard's first row (lazy: one all-gather)
         self.labels = None          # int32 [n_local] of the last assign pass
         self.assign_stats = None    # float64 [K+1] of the last batch_eval pass (f_j, label changes)
+        self._u_scratch = None      # [n_local, K] Student's-t hand-off between the two launches of a tiled-shape step
         self._labels_spare = None
         self.exchange = exchange    # optional NVLink peer-memory exchange (else NCCL / gloo all_reduce)
 
@@ -235,16 +236,25 @@ class LatentBuffer:
             st, stats = r["f"], r["stats"]
             return DecStepResult(loss=stats[0], dmu=stats[2:].view(K, self.d), f=st[:K], n_changed=st[K], dz=r["dz"],
                                  p=r["p"])
-        if self.exchange is not None and self.world > 1:
-            ex = self.exchange.desc
+        if self.world == 1 or self.exchange is not None:
+            # tiled shapes (K*d > 160): two launches with the u hand-off; with a peer exchange f is pushed by the assign
+            # kernel's last CTA, pulled in the gradient kernel's prologue, and the gradient statistics are all-reduced
+            # in that kernel's tail
+            ex = self.exchange.desc if (self.exchange is not None and self.world > 1) else None
             prev = self.labels
             out_labels = self._labels_spare if self._labels_spare is not None else torch.empty(
                 self.n_local, dtype=torch.int32, device=self.z.device)
-            _, labels, st = ops.dec_assign(self.z, mu, alpha, round_decimals, want_q=False, want_labels=True,
-                                           labels_prev=prev, out_labels=out_labels, push=ex)
+            if self._u_scratch is None or tuple(self._u_scratch.shape) != (self.n_local, K):
+                self._u_scratch = torch.empty(self.n_local, K, dtype=torch.float32, device=self.z.device)
+            _, labels, st = ops.dec_assign_u(self.z, mu, self._u_scratch, alpha, round_decimals, want_q=False,
+                                             want_labels=True, labels_prev=prev, out_labels=out_labels, push=ex)
             self._labels_spare, self.labels = self.labels, labels
-            stats, p_out, dz = ops.dec_target_kl_grad(self.z, mu, None, alpha, round_decimals, gamma / self.n_total,
-                                                      want_p=want_p, want_dz=want_dz, pull_f=ex, push=ex)
+            stats, p_out, dz = ops.dec_target_kl_grad_u(self.z, mu, self._u_scratch, None if ex is not None else st, alpha,
+                                                        round_decimals, gamma / self.n_total, want_p=want_p,
+                                                        want_dz=want_dz, pull_f=ex, push=ex)
+            if ex is None:
+                return DecStepResult(loss=stats[0], dmu=stats[2:].view(K, self.d), f=st[:K], n_changed=st[K], dz=dz,
+                                     p=p_out)
             # (push on a gradient kernel = complete all-reduce: its last CTA also collects the world's sum)
             # st holds only this shard's f; the all-reduced f is not needed by the caller of a fused step,
             # the label-change count is: exchange it with the (tiny) standalone kernel

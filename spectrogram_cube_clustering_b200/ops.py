@@ -168,6 +168,53 @@ def dec_target_kl_grad(z, mu, f, alpha=1.0, round_decimals=0, scale=1.0, want_p=
     return stats, p, dz
 
 
+def dec_assign_u(z, mu, u_out, alpha=1.0, round_decimals=0, want_q=False, want_labels=True, labels_prev=None,
+                 out_q=None, out_labels=None, out_stats=None, push=None):
+    """:func:`dec_assign` that also hands u_ij = 1 / (1 + d_ij / alpha) ([n, K] float32) to the gradient pass
+    (:func:`dec_target_kl_grad_u`) — the two-launch step of the shapes the one-kernel step does not cover."""
+    lib = _lib.load()
+    _require(z, "z"); _require(mu, "mu"); _require(u_out, "u_out")
+    n, d = z.shape
+    K = mu.shape[0]
+    if tuple(u_out.shape) != (n, K):
+        raise ValueError("u_out must be [n, K]")
+    q = out_q if out_q is not None else (torch.empty(n, K, dtype=torch.float32, device=z.device) if want_q else None)
+    labels = out_labels if out_labels is not None else (
+        torch.empty(n, dtype=torch.int32, device=z.device) if want_labels else None)
+    if labels_prev is not None:
+        _require(labels_prev, "labels_prev", torch.int32)
+    stats = out_stats if out_stats is not None else torch.empty(K + 1, dtype=torch.float64, device=z.device)
+    ws = workspace(z.device, d, K)
+    rc = lib.scc_dec_assign_u(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), int(round_decimals), _ptr(q),
+                              _ptr(labels), _ptr(labels_prev), u_out.data_ptr(), stats.data_ptr(), ws.data_ptr(),
+                              ws.numel(), _ex(push), _stream())
+    _lib.check(rc, "scc_dec_assign_u")
+    return q, labels, stats
+
+
+def dec_target_kl_grad_u(z, mu, u, f, alpha=1.0, round_decimals=0, scale=1.0, want_p=False, want_dz=False,
+                         out_p=None, out_dz=None, out_stats=None, pull_f=None, push=None):
+    """:func:`dec_target_kl_grad` with the Student's-t u_ij streamed from ``u`` (written by :func:`dec_assign_u` for
+    the same z and mu) instead of recomputed."""
+    lib = _lib.load()
+    _require(z, "z"); _require(mu, "mu"); _require(u, "u")
+    n, d = z.shape
+    K = mu.shape[0]
+    if f is not None:
+        _require(f, "f", torch.float64)
+    elif pull_f is None:
+        raise ValueError("need the column sums f")
+    p = out_p if out_p is not None else (torch.empty(n, K, dtype=torch.float32, device=z.device) if want_p else None)
+    dz = out_dz if out_dz is not None else (torch.empty_like(z) if want_dz else None)
+    stats = out_stats if out_stats is not None else torch.empty(K * d + 2, dtype=torch.float64, device=z.device)
+    ws = workspace(z.device, d, K)
+    rc = lib.scc_dec_target_kl_grad_u(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), u.data_ptr(), _ptr(f),
+                                      int(round_decimals), float(scale), _ptr(p), _ptr(dz), stats.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), _ex(pull_f), _ex(push), _stream())
+    _lib.check(rc, "scc_dec_target_kl_grad_u")
+    return stats, p, dz
+
+
 def dec_step_supported(d: int, K: int) -> bool:
     """Shapes the one-kernel step exists for (the register-blocked gradient kernel: K_padded * d <= 160)."""
     kp = 4 if K <= 4 else (8 if K <= 8 else 16)

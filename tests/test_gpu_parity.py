@@ -390,3 +390,46 @@ def test_gmm_not_positive_definite_flag(ops):
     ops.gmm_finalize(stats, 512, st.means, st.weights, st.cov, st.pchol, st.params, st.ctrl, reg_covar=0.0, tol=0.0)
     c = st.ctrl.cpu().numpy()
     assert c[4] > 0 and c[5] == 1
+
+
+@pytest.mark.parametrize("n,d,K,alpha,rd", [(4097, 32, 16, 1.0, 0), (70001, 32, 16, 1.0, 5), (1000, 16, 16, 2.0, 0),
+                                            (640, 24, 12, 1.0, 5), (513, 12, 16, 1.0, 0), (2000, 20, 9, 0.5, 0)])
+def test_dec_two_launch_step_with_u_handoff(ops, n, d, K, alpha, rd):
+    """Tiled shapes (K*d > 160): the assign pass hands u_ij = 1/(1 + d_ij/alpha) to the gradient pass
+    (scc_dec_assign_u -> scc_dec_target_kl_grad_u) instead of the gradient pass recomputing the distances.
+    Same results as the recomputing chain (to the rounding of one MUFU.RCP) and as the oracle."""
+    from oracle import dec as odec
+    rng = np.random.default_rng(11 * n + d + K)
+    z = dev(rng.normal(size=(n, d)).astype(np.float32) * 1.2 + 0.5)
+    mu = dev(rng.normal(size=(K, d)).astype(np.float32) + 0.5)
+    scale = 1e-3 / n
+    u = torch.empty(n, K, device="cuda")
+    q, lab, f = ops.dec_assign_u(z, mu, u, alpha, rd, want_q=True)
+    q0, lab0, f0 = ops.dec_assign(z, mu, alpha, rd)
+    assert torch.equal(q, q0) and torch.equal(lab, lab0) and torch.equal(f, f0)
+    d2 = ((z[:, None, :].double() - mu[None].double()) ** 2).sum(2)
+    torch.testing.assert_close(u.double(), 1.0 / (1.0 + d2 / alpha), rtol=2e-6, atol=0)
+    st_u, p_u, dz_u = ops.dec_target_kl_grad_u(z, mu, u, f, alpha, rd, scale, want_p=True, want_dz=True)
+    st_r, p_r, dz_r = ops.dec_target_kl_grad(z, mu, f, alpha, rd, scale)
+    dp = (p_u - p_r).abs().max().item()
+    assert dp <= (1.01e-5 if rd else 2e-6)
+    assert abs(st_u[0].item() - st_r[0].item()) <= (2e-4 if rd else 2e-6) * abs(st_r[0].item())
+    assert (st_u[2:] - st_r[2:]).abs().max() <= (2e-4 if rd else 1e-5) * st_r[2:].abs().max()
+    assert (dz_u - dz_r).abs().max() <= (2e-3 if rd else 1e-5) * dz_r.abs().max()
+    if not rd:
+        ref = odec.dec_step(z.cpu().numpy(), mu.cpu().numpy(), alpha, 1e-3, round_to=None)
+        assert abs(st_u[0].item() - ref["loss"]) <= TOL * abs(ref["loss"])
+        assert rel_err(st_u[2:].cpu().numpy().reshape(K, d), ref["dmu"]) < TOL
+        assert rel_err(dz_u.cpu().numpy(), ref["dz"]) < TOL
+        assert rel_err(p_u.cpu().numpy(), ref["p"]) < 2 * TOL
+    st_n, none_p, none_dz = ops.dec_target_kl_grad_u(z, mu, u, f, alpha, rd, scale)
+    assert none_p is None and none_dz is None and torch.equal(st_n, st_u)
+
+
+def test_dec_u_handoff_is_for_tiled_shapes_only(ops):
+    from spectrogram_cube_clustering_b200 import _lib
+    z = torch.randn(1000, 9, device="cuda"); mu = torch.randn(8, 9, device="cuda")
+    u = torch.empty(1000, 8, device="cuda")
+    _, _, f = ops.dec_assign_u(z, mu, u)                    # writing u is always possible
+    with pytest.raises(_lib.SccError):
+        ops.dec_target_kl_grad_u(z, mu, u, f)               # register-blocked shape: use dec_step
