@@ -818,25 +818,27 @@ dec_grad_reg_kernel(const DecArgs a_in) {
         st.rewind();
 #pragma unroll
         for (int s = 0; s < S; ++s) st.issue(s);
-        __syncthreads();
-        float facc[KP + 1];
-#pragma unroll
-        for (int j = 0; j < KP; ++j) facc[j] = (j & 1) ? facc2[j / 2].y : facc2[j / 2].x;
-        facc[KP] = changed;
         double* f_s = cta_stats;                                   // [K+1] (cta_stats is free until the tail)
-        double* mine_s = cta_stats + ((KP + 2) & ~1);              // [KP+1] this CTA's sums
-        cta_reduce<KP + 1, kRegThreads>(facc, scratch, mine_s);
-        if (!EXACT) {
-            if (threadIdx.x == 0 && K < KP) mine_s[K] = mine_s[KP];
-            __syncthreads();
-        }
         const int sp_tail = (K * D + 2 + 1) & ~1;                  // the world's f lives behind the tail's slots
         const PeerCtx ex1{a.ex_windows, a.ex_rank, a.ex_world, a.ex_max_len};
         // f_j and the label-change count are sums of values in [0, 1] over at most n points: fixed point with
-        // 2^shift * n < 2^62, accumulated with integer atomics in the workspace header (bit-reproducible)
+        // 2^shift * n < 2^62, accumulated with integer atomics in the workspace header.  Integer addition is
+        // associative, so the totals are bit-reproducible whatever the arrival order, and every WARP adds its own
+        // sums (float -> warp shuffle tree -> fixed point): no CTA-level reduction in front of the grid barrier.
         const int shift = 61 - (64 - __clzll((long long)(a.n > 0 ? a.n : 1)));
         unsigned long long* fix = reinterpret_cast<unsigned long long*>(a.counter) + kFixOffset;
-        grid_barrier_sum_fixed<kRegThreads>(mine_s, K + 1, fix, a.counter + 1, f_s, ldexp(1.0, shift), ldexp(1.0, -shift),
+        {
+            const double scale_fix = ldexp(1.0, shift);
+            float mine = 0.f;                                      // lane j ends up with the warp's sum of statistic j
+#pragma unroll
+            for (int j = 0; j <= KP; ++j) {
+                const float v = warp_sum(j < KP ? ((j & 1) ? facc2[j / 2].y : facc2[j / 2].x) : changed);
+                const int slot = (j < KP) ? j : K;                 // the count sits right behind the K sums
+                if (lane == slot && (j == KP || j < K)) mine = v;
+            }
+            if (lane <= K) atomicAdd(fix + lane, (unsigned long long)__double2ll_rn((double)mine * scale_fix));
+        }
+        grid_barrier_sum_fixed<kRegThreads>(nullptr, K + 1, fix, a.counter + 1, f_s, 0.0, ldexp(1.0, -shift),
                                             a.partials + (size_t)gridDim.x * sp_tail, &ex1);
         if (threadIdx.x < KP) inv_f[threadIdx.x] = ((int)threadIdx.x < K) ? (float)(1.0 / f_s[threadIdx.x]) : 0.f;
         if (blockIdx.x == 0 && (int)threadIdx.x <= K && a.f_out) a.f_out[threadIdx.x] = f_s[threadIdx.x];
@@ -931,7 +933,6 @@ dec_grad_reg_kernel(const DecArgs a_in) {
             if (++stage == S) stage = 0;
         }
     }
-    if (kBulkOut && lane == 0) bulk_wait0();             // this warp's dz stores are complete
     pdl_trigger();                      // successor may start its prologue under our reduction tail
     SCC_TL(a.timeline, 3);
     if (mode_is_kl<MODE>()) sm[0] *= a.scale * 0.693147180559945f;     // loss = scale * ln2 * sum p log2(p/q)
@@ -959,12 +960,15 @@ dec_grad_reg_kernel(const DecArgs a_in) {
     if (MODE == MODE_KMEANS && o < K) cta_stats[2 + K * D + o] = wj;
     __syncthreads();
     const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
-    const bool last = grid_publish<kRegThreads, 25>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials,
+    // (the warp's last dz bulk stores read the stream buffers, which nothing in the tail touches: their completion
+    //  is only awaited at the very end, behind the reductions)
+    const bool last = grid_publish<kRegThreads, 30>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials,
                                                     a.counter, a.stats, scratch, &push, a.ex_push);
     if (MODE == MODE_STEP && last) {                                          // every CTA is past the pass-1 barrier
         if (threadIdx.x == 0) a.counter[1] = 0u;
         if ((int)threadIdx.x <= K) reinterpret_cast<unsigned long long*>(a.counter)[kFixOffset + threadIdx.x] = 0ull;
     }
+    if (kBulkOut && lane == 0) bulk_wait0();             // this warp's dz stores are complete
     SCC_TL(a.timeline, 5);
 }
 

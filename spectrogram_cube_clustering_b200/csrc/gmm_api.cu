@@ -112,17 +112,16 @@ __device__ __forceinline__ void gmm_finalize_body(const FinArgs& a, unsigned cha
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if ((int)threadIdx.x < K && bad_s == 0) {          // one lane per component: K float64 logarithms side by side
         double tot = 0.0;
-        for (int j = 0; j < K; ++j) tot += nk_s[j];
-        if (bad_s == 0) {
-            for (int j = 0; j < K; ++j) {
-                const double w = nk_s[j] / tot;
-                if (a.weights) a.weights[j] = w;
-                a.params[(size_t)K * d + (size_t)K * TRI + j] =
-                    (float)(logdet_s[j] + log(w) - 0.5 * d * 1.8378770664093453 /* log(2 pi) */);
-            }
-        }
+        for (int j = 0; j < K; ++j) tot += nk_s[j];   // same order in every lane
+        const int j = threadIdx.x;
+        const double w = nk_s[j] / tot;
+        if (a.weights) a.weights[j] = w;
+        a.params[(size_t)K * d + (size_t)K * TRI + j] =
+            (float)(logdet_s[j] + log(w) - 0.5 * d * 1.8378770664093453 /* log(2 pi) */);
+    }
+    if (threadIdx.x == 0) {
         if constexpr (FROM_STATS) {
             const double lower = a.stats[0] / a.n_total;
             const double prev = ctrl[0];
@@ -151,30 +150,46 @@ gmm_finalize_kernel(const FinArgs a) {
 // that finishes last then runs the finalisation (scaling, Cholesky, U = L^-T, lower bound, stop rule).
 // Replaces reduce_partials -> exchange -> finalize (three launches) behind the statistics kernel.
 // ---------------------------------------------------------------------------
-constexpr int kTailSlice = 512;
+constexpr int kTailSlice = 64;             // statistics per CTA: 512 threads = 64 statistics x 8 groups of partial slots
+constexpr int kTailGroups = 8;
 
 __global__ void __launch_bounds__(512, 1)
 gmm_tail_kernel(const double* __restrict__ partials, int G, int NS, double* __restrict__ stats, PeerCtx ex,
                 unsigned int* __restrict__ ticket, const FinArgs fin) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double slice[kTailSlice];
+    __shared__ double part[kTailGroups][kTailSlice];
     __shared__ int s_last;
     if (fin.ctrl[5] != 0.0) return;              // frozen fit (identical on every rank): nothing to exchange
     const int lo = blockIdx.x * kTailSlice, hi = min(NS, lo + kTailSlice);
-    const int s = lo + threadIdx.x;
-    if (s < hi) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int b = 0;
-        for (; b + 3 < G; b += 4) {
-            a0 += partials[(size_t)b * NS + s];
-            a1 += partials[(size_t)(b + 1) * NS + s];
-            a2 += partials[(size_t)(b + 2) * NS + s];
-            a3 += partials[(size_t)(b + 3) * NS + s];
+    {   // thread (g, c): statistic lo + c over the slots g, g + 8, ... — the chain is L2-latency bound, so the slots
+        // of one statistic are spread over 8 threads (up to 8 independent loads in flight each); fixed order
+        const int c = threadIdx.x % kTailSlice, g = threadIdx.x / kTailSlice;
+        const int s = lo + c;
+        double acc = 0.0;
+        if (s < hi) {
+            for (int b = g; b < G; b += kTailGroups * 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int bb = b + u * kTailGroups;
+                    v[u] = (bb < G) ? partials[(size_t)bb * NS + s] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += v[u];
+            }
         }
-        for (; b < G; ++b) a0 += partials[(size_t)b * NS + s];
-        slice[threadIdx.x] = (a0 + a1) + (a2 + a3);
+        part[g][c] = acc;
     }
     __syncthreads();
+    if ((int)threadIdx.x < kTailSlice) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < kTailGroups; ++g) t += part[g][threadIdx.x];
+        slice[threadIdx.x] = t;
+    }
+    __syncthreads();
+    const int s = lo + threadIdx.x;
     if (ex.windows) {
         PeerHeader* me = reinterpret_cast<PeerHeader*>(ex.windows[ex.rank]);
         const unsigned int seq = ld_relaxed_gpu_u32(&me->seq) + 1u;
@@ -192,6 +207,7 @@ gmm_tail_kernel(const double* __restrict__ partials, int G, int NS, double* __re
     } else if (s < hi) {
         stats[s] = slice[threadIdx.x];
     }
+    static_assert(kTailSlice * kTailGroups == 512, "tail kernel: 512 threads");
     // the CTA that finishes last sees every slice of `stats` (writes above -> CTA barrier -> acq_rel ticket)
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -875,11 +875,16 @@ gmm_em_block_kernel(const GmmArgs a) {
     float* cst_s = u_s + ((KP * TRI + 3) & ~3);          // [KP]
     double* ll_s = reinterpret_cast<double*>(cst_s + ((KP + 3) & ~3));   // [NT/32]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ll_s + NT / 32);
+    constexpr int NWB = NT / 32;
+    unsigned int* mask_s = reinterpret_cast<unsigned int*>(bars + S);    // [KP][NWB] ballot of (r >= 2^-30) per warp
+    int* pref_s = reinterpret_cast<int*>(mask_s + KP * NWB);             // [KP][NWB + 1] exclusive prefix, total
+    unsigned short* list_s = reinterpret_cast<unsigned short*>(pref_s + KP * (NWB + 1));   // [KP][TILE] compact point lists
 
     if (a.ctrl && a.ctrl[5] != 0.0) return;
 
     const int K = a.K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float thr = (a.accumulate & SCC_GMM_NOSKIP) ? 0.f : kGmmSkipThreshold;
     for (int i = threadIdx.x; i < KP * D; i += NT) mu_s[i] = (i < K * D) ? a.params[i] : 0.f;
     for (int i = threadIdx.x; i < KP * TRI; i += NT) u_s[i] = (i < K * TRI) ? a.params[K * D + i] : 0.f;
     if (threadIdx.x < KP) cst_s[threadIdx.x] = ((int)threadIdx.x < K) ? a.params[K * D + K * TRI + threadIdx.x] : 0.f;
@@ -953,6 +958,7 @@ gmm_em_block_kernel(const GmmArgs a) {
         const int np = ring.points(tile);
         const float* ztile = ring.stage_ptr(stage);
         // ---------------- phase 1: E-step for point threadIdx.x ----------------
+        float rk[KP];                    // this point's responsibilities (ballots of the sparsity skip below)
         {
             const bool active = (int)threadIdx.x < np;
             float lp[KP];
@@ -998,6 +1004,8 @@ gmm_em_block_kernel(const GmmArgs a) {
                 lp[k] = r;
             }
 #pragma unroll
+            for (int k = 0; k < KP; ++k) rk[k] = lp[k];
+#pragma unroll
             for (int k = 0; k < KP; k += 4)
                 *reinterpret_cast<float4*>(r_s + threadIdx.x * KP + k) = make_float4(lp[k], lp[k + 1], lp[k + 2], lp[k + 3]);
             if (active) {
@@ -1010,15 +1018,43 @@ gmm_em_block_kernel(const GmmArgs a) {
                 }
             }
         }
-        __syncthreads();
-        // ---------------- phase 2: 4x4 moment blocks over all points of the tile ----------------
+        // ---- responsibility-sparsity skip (see gmm_em_sparse_kernel): per-component ballots -> compact point lists
         if (a.accumulate & 3) {
-            for (int t = 0; t < np; ++t) {
-                const float* row = ztile + t * L::LD;
+            const bool active = (int)threadIdx.x < np;
 #pragma unroll
-                for (int m = 0; m < MAXU; ++m) {
-                    if (uk[m] >= 0) {
-                        const float r = r_s[t * KP + uk[m]];
+            for (int k = 0; k < KP; ++k) {
+                const unsigned int mk = __ballot_sync(0xffffffffu, active && k < K && rk[k] >= thr && rk[k] > 0.f);
+                if (lane == 0) mask_s[k * NWB + warp] = mk;
+            }
+        }
+        __syncthreads();
+        // ---------------- phase 2: 4x4 moment blocks over the component's significant points ----------------
+        if (a.accumulate & 3) {
+            if (threadIdx.x < KP * NWB) {
+                const int k = threadIdx.x / NWB, w = threadIdx.x - k * NWB;
+                int pfx = 0;
+                for (int ww = 0; ww < w; ++ww) pfx += __popc(mask_s[k * NWB + ww]);
+                pref_s[k * (NWB + 1) + w] = pfx;
+                if (w == NWB - 1) pref_s[k * (NWB + 1) + NWB] = pfx + __popc(mask_s[k * NWB + w]);
+            }
+            __syncthreads();
+            const unsigned int lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const unsigned int mk = mask_s[k * NWB + warp];
+                if ((mk >> lane) & 1u)
+                    list_s[k * TILE + pref_s[k * (NWB + 1) + warp] + __popc(mk & lt)] = (unsigned short)threadIdx.x;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < MAXU; ++m) {
+                if (uk[m] >= 0) {
+                    const int k = uk[m];
+                    const int cnt = pref_s[k * (NWB + 1) + NWB];
+                    for (int e = 0; e < cnt; ++e) {
+                        const int t = list_s[k * TILE + e];
+                        const float* row = ztile + t * L::LD;
+                        const float r = r_s[t * KP + k];
                         const float4 xa = *reinterpret_cast<const float4*>(row + 4 * ua[m]);
                         const float4 xb = *reinterpret_cast<const float4*>(row + 4 * ub[m]);
                         const float da[4] = {xa.x - mua[m][0], xa.y - mua[m][1], xa.z - mua[m][2], xa.w - mua[m][3]};
@@ -1057,7 +1093,8 @@ constexpr size_t gmm_block_smem() {
     using B = GmmBlock<D, KP>;
     return sizeof(float) * (B::S * B::TILE * RowLayout<D>::LD + B::TILE * KP + KP * D + ((KP * B::TRI + 3) & ~3) +
                             ((KP + 3) & ~3)) +
-           sizeof(double) * (B::NT / 32) + sizeof(uint64_t) * B::S;
+           sizeof(double) * (B::NT / 32) + sizeof(uint64_t) * B::S +
+           sizeof(unsigned int) * KP * (B::NT / 32) + sizeof(int) * KP * (B::NT / 32 + 1) + sizeof(unsigned short) * KP * B::TILE;
 }
 
 template <int D, int KP>

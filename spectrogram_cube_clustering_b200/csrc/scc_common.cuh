@@ -603,8 +603,8 @@ __device__ __forceinline__ void grid_barrier_sum_fixed(const double* cta_stats, 
     unsigned int epoch = 0;
     if (multi && tid == 0)
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(epoch) : "l"(counter + 1) : "memory");
-    if (tid < S) atomicAdd(fix + tid, (unsigned long long)__double2ll_rn(cta_stats[tid] * scale));
-    __syncthreads();
+    if (cta_stats && tid < S) atomicAdd(fix + tid, (unsigned long long)__double2ll_rn(cta_stats[tid] * scale));
+    __syncthreads();                                // (cta_stats == nullptr: the warps have added their sums already)
     if (tid == 0) {
         unsigned int seen;
         asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
