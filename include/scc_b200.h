@@ -190,6 +190,30 @@ int scc_kmeans_batch_update(float* centers, const double* stats, int d, int K, i
 int scc_dec_distances(const float* z, int64_t n, int d, const float* mu, int K, float p, float* out,
                       scc_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * DEC stage, float64 precision path
+ * ------------------------------------------------------------------------- *
+ * The reference runs DEC in float64 (`model.double()`, Cluster/models.py:965; numpy float64 in batch_eval and
+ * target_distribution, models.py:66-71, 1320-1322).  These entry points evaluate the same operators in IEEE float64
+ * in the reference's operation order (any d in [1,32], K in [1,16]; no alignment requirement), so a caller that
+ * keeps the reference's dtype gets its numbers to ~1e-15 and the np.round(., 5) quantisations land on the same
+ * side.  Throughput is ~10x below the float32 kernels (one thread per point, FP64 pipe).
+ *   scc_dec_assign_f64   as scc_dec_assign  (networks.py:279-288, models.py:92-94,1098-1099,1320)
+ *   scc_dec_target_f64   as scc_colsum + scc_dec_target (models.py:1320-1322); have_f = 0: f [K] is computed from q
+ *                        first (and returned), have_f = 1: f is given
+ *   scc_dec_grad_f64     exactly one of p (target, API mode), f_cols (target rebuilt from the column sums, optionally
+ *                        written to p_out) or grad_q (generic upstream gradient dL/dq) is non-NULL;
+ *                        stats [K*d+2] = loss, sum_i s_i, dmu (models.py:1124-1127 + autograd)
+ */
+int scc_dec_assign_f64(const double* z, int64_t n, int d, const double* mu, int K, double alpha, int round_decimals,
+                       double* q, int32_t* labels, const int32_t* labels_prev, double* stats,
+                       void* workspace, size_t workspace_bytes, scc_stream_t stream);
+int scc_dec_target_f64(const double* q, int64_t n, int K, double* f, int have_f, int round_decimals, double* p,
+                       void* workspace, size_t workspace_bytes, scc_stream_t stream);
+int scc_dec_grad_f64(const double* z, int64_t n, int d, const double* mu, int K, double alpha, const double* p,
+                     const double* f_cols, int round_decimals, const double* grad_q, double scale, double* p_out,
+                     double* dz, double* stats, void* workspace, size_t workspace_bytes, scc_stream_t stream);
+
 struct scc_exchange;   /* multi-GPU exchange descriptor, defined below */
 
 /* ------------------------------------------------------------------------- *

@@ -72,6 +72,12 @@ _SIGNATURES = {
     "scc_kmeans_batch_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
     "scc_dec_distances": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "scc_dec_assign_f64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scc_dec_target_f64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                   c_void_p]),
+    "scc_dec_grad_f64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_int,
+                                 c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "scc_dec_assign_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "scc_dec_target_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

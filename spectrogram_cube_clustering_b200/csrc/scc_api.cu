@@ -160,6 +160,25 @@ int scc_dec_distances(const float* z, int64_t n, int d, const float* mu, int K, 
     return scc::dec_distances(z, n, d, mu, K, p, out, (cudaStream_t)stream);
 }
 
+int scc_dec_assign_f64(const double* z, int64_t n, int d, const double* mu, int K, double alpha, int round_decimals,
+                       double* q, int32_t* labels, const int32_t* labels_prev, double* stats, void* workspace,
+                       size_t workspace_bytes, scc_stream_t stream) {
+    return scc::dec_assign_f64(z, n, d, mu, K, alpha, round_decimals, q, labels, labels_prev, stats, workspace,
+                               workspace_bytes, (cudaStream_t)stream);
+}
+
+int scc_dec_target_f64(const double* q, int64_t n, int K, double* f, int have_f, int round_decimals, double* p,
+                       void* workspace, size_t workspace_bytes, scc_stream_t stream) {
+    return scc::dec_target_f64(q, n, K, f, have_f, round_decimals, p, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int scc_dec_grad_f64(const double* z, int64_t n, int d, const double* mu, int K, double alpha, const double* p,
+                     const double* f_cols, int round_decimals, const double* grad_q, double scale, double* p_out,
+                     double* dz, double* stats, void* workspace, size_t workspace_bytes, scc_stream_t stream) {
+    return scc::dec_grad_f64(z, n, d, mu, K, alpha, p, f_cols, round_decimals, grad_q, scale, p_out, dz, stats, workspace,
+                             workspace_bytes, (cudaStream_t)stream);
+}
+
 static const scc::ExchangeDesc* as_desc(const scc_exchange* e, scc::ExchangeDesc* tmp) {
     if (!e || !e->windows) return nullptr;
     tmp->windows = e->windows; tmp->rank = e->rank; tmp->world = e->world; tmp->max_len = e->max_len;

@@ -116,6 +116,15 @@ int kmeans_batch_update(float* centers, const double* stats, int d, int K, int R
                         int32_t* n_iter, double* inertia, cudaStream_t st);
 int dec_distances(const float* z, int64_t n, int d, const float* mu, int K, float p, float* out, cudaStream_t st);
 
+// float64 precision path (dec_f64.cu)
+int dec_assign_f64(const double* z, int64_t n, int d, const double* mu, int K, double alpha, int round_decimals, double* q,
+                   int32_t* labels, const int32_t* labels_prev, double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
+int dec_target_f64(const double* q, int64_t n, int K, double* f, int have_f, int round_decimals, double* p, void* ws,
+                   size_t ws_bytes, cudaStream_t st);
+int dec_grad_f64(const double* z, int64_t n, int d, const double* mu, int K, double alpha, const double* p,
+                 const double* f_cols, int round_decimals, const double* grad_q, double scale, double* p_out, double* dz,
+                 double* stats, void* ws, size_t ws_bytes, cudaStream_t st);
+
 size_t peer_window_bytes(int max_len);
 int peer_allreduce(const double* local, int len, double* out, void* const* windows_dev, int rank, int world,
                    int max_len, cudaStream_t st);

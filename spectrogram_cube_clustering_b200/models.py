@@ -54,16 +54,19 @@ def _as_buffer(z, device=None, group=None) -> LatentBuffer:
 def target_distribution(q, decimals=5):
     """p = normalise_rows(q**2 / q.sum(0)), rounded to 5 decimals (``models.py:1320-1322``).
 
-    numpy in -> float64 numpy out (the reference contract); a CUDA tensor in -> CUDA float32 out.
+    numpy in -> float64 numpy out, computed in float64 like the reference (the 5-decimal rounding lands on the
+    reference's side); a CUDA tensor in -> CUDA tensor out in float64 (float64 in) or float32 (otherwise).
     ``decimals=None`` skips the rounding.
     """
     rd = 0 if decimals is None else int(decimals)
     if isinstance(q, torch.Tensor) and q.is_cuda:
+        if q.dtype == torch.float64:
+            return ops.dec_target_f64(q.contiguous(), None, rd)[0]
         qd = q.to(torch.float32).contiguous()
         return ops.dec_target(qd, ops.colsum(qd), rd)
-    qd = torch.as_tensor(np.ascontiguousarray(q, dtype=np.float32)).to(_device())
-    p = ops.dec_target(qd, ops.colsum(qd), rd)
-    return p.cpu().numpy().astype(np.float64)
+    # the reference's contract: float64 numpy in, float64 numpy out — computed in float64 (scc_dec_target_f64)
+    qd = torch.as_tensor(np.ascontiguousarray(q, dtype=np.float64)).to(_device())
+    return ops.dec_target_f64(qd, None, rd)[0].cpu().numpy()
 
 
 def batch_eval(dataloader, model, device, mute=True, return_buffer=False, labels_prev=None, group=None):

@@ -26,9 +26,13 @@ def _pad_cols(t: torch.Tensor, width: int) -> torch.Tensor:
 
 
 def _operands(x, weights):
-    """float32, contiguous, padded to an instantiated latent dimension (zero-padding z and mu is exact)."""
+    """Kernel operands.  float64 input (the reference's ``model.double()``, ``models.py:965``) stays float64 and runs
+    the float64 kernels; anything else becomes float32, contiguous, padded to an instantiated latent dimension
+    (zero-padding z and mu is exact)."""
     if not x.is_cuda:
         raise SccError("the clustering layer needs CUDA tensors: the B200 path has no CPU fallback")
+    if x.dtype == torch.float64:
+        return x.contiguous(), weights.to(device=x.device, dtype=torch.float64).contiguous()
     dp = ops.padded_dim(x.shape[1])
     x32 = _pad_cols(x.to(torch.float32), dp).contiguous()
     w32 = _pad_cols(weights.to(device=x.device, dtype=torch.float32), dp).contiguous()
@@ -51,7 +55,7 @@ def dec_kl_loss(z, weights, p, alpha=1.0, scale=1.0):
     ``models.py:1124-1125``.  One ``scc_dec_kl_grad`` launch yields loss, dL/dz and dL/dweights
     (``torch.ops.scc_b200.dec_kl_loss``); backward only scales them."""
     z32, w32 = _operands(z, weights)
-    p32 = p.detach().to(device=z.device, dtype=torch.float32).contiguous()
+    p32 = p.detach().to(device=z.device, dtype=z32.dtype).contiguous()
     loss, _, _ = torch.ops.scc_b200.dec_kl_loss(z32, w32, p32, float(alpha), float(scale))
     return loss.to(z.dtype)
 
@@ -61,7 +65,8 @@ class ClusteringLayer(nn.Module):
 
     Arguments (same as the reference, ``networks.py:265``):
         n_clusters, n_features=9, alpha=1.0, weights=None (initial centroids [K, d])
-    Input  x [B, n_features] (CUDA; float32 or float64 — the kernels compute in float32)
+    Input  x [B, n_features] (CUDA).  float32 (or half) input runs the float32 throughput kernels; float64 input —
+           the reference's ``model.double()`` — runs the float64 kernels (reference precision, ~10x slower)
     Output q [B, n_clusters] in x.dtype, rows sum to 1.
     """
 

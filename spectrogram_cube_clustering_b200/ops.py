@@ -65,6 +65,68 @@ def padded_dim(d: int) -> int:
     raise ValueError(f"latent dimension {d} exceeds {_lib.MAX_D}")
 
 
+# --------------------------------------------------------------------------- DEC, float64 precision path
+def dec_assign_f64(z, mu, alpha=1.0, round_decimals=0, want_q=True, want_labels=True, labels_prev=None):
+    """float64 :func:`dec_assign` (the reference's own dtype, ``models.py:965``): q / labels / f in IEEE float64 and the
+    reference's operation order.  z [n,d], mu [K,d] float64; any d <= 32, K <= 16."""
+    lib = _lib.load()
+    _require(z, "z", torch.float64); _require(mu, "mu", torch.float64)
+    n, d = z.shape
+    K = mu.shape[0]
+    if mu.shape[1] != d or d > _lib.MAX_D or K > MAX_K:
+        raise ValueError("mu must be [K <= 16, d] with the latent dimension d <= 32 of z")
+    q = torch.empty(n, K, dtype=torch.float64, device=z.device) if want_q else None
+    labels = torch.empty(n, dtype=torch.int32, device=z.device) if want_labels else None
+    if labels_prev is not None:
+        _require(labels_prev, "labels_prev", torch.int32)
+    stats = torch.empty(K + 1, dtype=torch.float64, device=z.device)
+    ws = workspace(z.device, padded_dim(d), K)
+    rc = lib.scc_dec_assign_f64(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), int(round_decimals), _ptr(q),
+                                _ptr(labels), _ptr(labels_prev), stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "scc_dec_assign_f64")
+    return q, labels, stats
+
+
+def dec_target_f64(q, f=None, round_decimals=0):
+    """float64 ``target_distribution`` (``models.py:1320-1322``): q [n,K] float64 -> (p [n,K] float64, f [K]).  ``f`` =
+    column sums of q; computed from q when not given."""
+    lib = _lib.load()
+    _require(q, "q", torch.float64)
+    n, K = q.shape
+    have_f = f is not None
+    if have_f:
+        _require(f, "f", torch.float64)
+    else:
+        f = torch.empty(K, dtype=torch.float64, device=q.device)
+    p = torch.empty_like(q)
+    ws = workspace(q.device, 4, K)
+    rc = lib.scc_dec_target_f64(q.data_ptr(), n, K, f.data_ptr(), int(have_f), int(round_decimals), p.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "scc_dec_target_f64")
+    return p, f
+
+
+def dec_grad_f64(z, mu, alpha=1.0, p=None, f=None, grad_q=None, round_decimals=0, scale=1.0, want_p=False, want_dz=True):
+    """float64 gradients: exactly one of ``p`` (target), ``f`` (target rebuilt from the column sums) or ``grad_q``
+    (generic upstream dL/dq).  -> (stats float64 [K*d+2] = loss, sum_i s_i, dmu; dz [n,d] | None; p_out | None)."""
+    lib = _lib.load()
+    _require(z, "z", torch.float64); _require(mu, "mu", torch.float64)
+    n, d = z.shape
+    K = mu.shape[0]
+    for t, nm in ((p, "p"), (f, "f"), (grad_q, "grad_q")):
+        if t is not None:
+            _require(t, nm, torch.float64)
+    dz = torch.empty_like(z) if want_dz else None
+    p_out = torch.empty(n, K, dtype=torch.float64, device=z.device) if (want_p and f is not None) else None
+    stats = torch.empty(K * d + 2, dtype=torch.float64, device=z.device)
+    ws = workspace(z.device, padded_dim(d), K)
+    rc = lib.scc_dec_grad_f64(z.data_ptr(), n, d, mu.data_ptr(), K, float(alpha), _ptr(p), _ptr(f), int(round_decimals),
+                              _ptr(grad_q), float(scale), _ptr(p_out), _ptr(dz), stats.data_ptr(), ws.data_ptr(),
+                              ws.numel(), _stream())
+    _lib.check(rc, "scc_dec_grad_f64")
+    return stats, dz, p_out
+
+
 # --------------------------------------------------------------------------- DEC
 def dec_assign(z, mu, alpha=1.0, round_decimals=0, want_q=True, want_labels=True, labels_prev=None,
                out_q=None, out_labels=None, out_stats=None, push=None):
@@ -452,6 +514,8 @@ def _register_custom_ops():
     # ---- ClusteringLayer.forward / backward (networks.py:279-288 + autograd)
     @custom_op("scc_b200::soft_assign", mutates_args=(), device_types="cuda")
     def _soft_assign(z: torch.Tensor, mu: torch.Tensor, alpha: float) -> torch.Tensor:
+        if z.dtype == torch.float64:                 # the reference's dtype: float64 kernels
+            return dec_assign_f64(z, mu, alpha, 0, want_labels=False)[0]
         q, _, _ = dec_assign(z, mu, alpha, 0, want_labels=False)
         return q
 
@@ -462,6 +526,9 @@ def _register_custom_ops():
     @custom_op("scc_b200::soft_assign_backward", mutates_args=(), device_types="cuda")
     def _soft_assign_backward(z: torch.Tensor, mu: torch.Tensor, grad_q: torch.Tensor, alpha: float) -> tuple[
             torch.Tensor, torch.Tensor]:
+        if z.dtype == torch.float64:
+            stats, dz, _ = dec_grad_f64(z, mu, alpha, grad_q=grad_q)
+            return dz, stats[2:].view(mu.shape).clone()
         dz, dmu = dec_backward(z, mu, grad_q, alpha)
         return dz, dmu.to(torch.float32)
 
@@ -485,6 +552,9 @@ def _register_custom_ops():
     @custom_op("scc_b200::dec_kl_loss", mutates_args=(), device_types="cuda")
     def _dec_kl_loss(z: torch.Tensor, mu: torch.Tensor, p: torch.Tensor, alpha: float, scale: float) -> tuple[
             torch.Tensor, torch.Tensor, torch.Tensor]:
+        if z.dtype == torch.float64:
+            stats, dz, _ = dec_grad_f64(z, mu, alpha, p=p, scale=scale)
+            return stats[0].clone(), dz, stats[2:].view(mu.shape).clone()
         stats, dz = dec_kl_grad(z, mu, alpha, p=p, scale=scale)
         return stats[0].to(torch.float32), dz, stats[2:].view(mu.shape).to(torch.float32)
 

@@ -433,3 +433,65 @@ def test_dec_u_handoff_is_for_tiled_shapes_only(ops):
     _, _, f = ops.dec_assign_u(z, mu, u)                    # writing u is always possible
     with pytest.raises(_lib.SccError):
         ops.dec_target_kl_grad_u(z, mu, u, f)               # register-blocked shape: use dec_step
+
+
+# ------------------------------------------------------------------------------ float64 precision path
+@pytest.mark.parametrize("case", DEC_CASES)
+def test_dec_float64_path_matches_reference_to_roundoff(ops, case):
+    """scc_dec_*_f64: the reference's dtype and operation order -> its numbers, including the SIDE on which the
+    5-decimal roundings land (np.round(q, 5), np.round(p, 5)): the rounded chain matches exactly, not to a quantum."""
+    g = load_golden("dec", case)
+    n, d = g["z"].shape
+    K = g["mu"].shape[0]
+    alpha, gamma = float(g["alpha"]), float(g["gamma"])
+    z, mu = dev(g["z"], torch.float64), dev(g["mu"], torch.float64)
+    q, labels, st = ops.dec_assign_f64(z, mu, alpha, 0)
+    assert np.abs(q.cpu().numpy() - g["q"]).max() < 1e-14
+    assert np.array_equal(labels.cpu().numpy(), g["labels"]) or case == "tie"
+    q5, _, st5 = ops.dec_assign_f64(z, mu, alpha, 5)
+    assert np.array_equal(q5.cpu().numpy(), g["q_round"])                   # same side of every rounding boundary
+    assert rel_err(st5[:K].cpu().numpy(), g["f"]) < 1e-13
+    p5, f5 = ops.dec_target_f64(q5, None, 5)
+    dp = np.abs(p5.cpu().numpy() - g["p"])
+    assert dp.max() <= 1.0000001e-5 and (dp > 1e-9).mean() < 1e-4           # a last-bit f difference may flip a rare boundary value
+    assert rel_err(f5.cpu().numpy(), g["f"]) < 1e-13
+    # API mode: the reference's own p -> its loss / dz / dmu
+    stats, dz, _ = ops.dec_grad_f64(z, mu, alpha, p=dev(g["p"], torch.float64), scale=gamma / n)
+    s = stats.cpu().numpy()
+    assert abs(s[0] - float(g["loss"])) < 1e-11 * abs(float(g["loss"]))
+    assert rel_err(dz.cpu().numpy(), g["dz"]) < 1e-11 and rel_err(s[2:].reshape(K, d), g["dmu"]) < 1e-11
+    # fused mode, rounded chain end to end (p rebuilt from f in float64)
+    stats_f, dz_f, p_f = ops.dec_grad_f64(z, mu, alpha, f=st5[:K].contiguous(), round_decimals=5, scale=gamma / n, want_p=True)
+    assert torch.equal(p_f, p5)
+    sf = stats_f.cpu().numpy()
+    flipped = (dp.max(axis=1) > 1e-9)
+    assert abs(sf[0] - float(g["loss"])) < (1e-10 if not flipped.any() else 1e-5) * abs(float(g["loss"]))
+    assert rel_err(dz_f.cpu().numpy()[~flipped], g["dz"][~flipped]) < 1e-10
+    # generic upstream gradient
+    stats_g, dz_g, _ = ops.dec_grad_f64(z, mu, alpha, grad_q=dev(g["G"], torch.float64))
+    assert rel_err(dz_g.cpu().numpy(), g["dz_generic"]) < 1e-11
+    assert rel_err(stats_g[2:].cpu().numpy().reshape(K, d), g["dmu_generic"]) < 1e-11
+
+
+def test_dec_float64_layer_and_target_distribution_api():
+    """model.double() callers: ClusteringLayer keeps float64 end to end; models.target_distribution(numpy float64)
+    computes in float64 (weak point of round 1: it computed in float32)."""
+    from spectrogram_cube_clustering_b200.networks import ClusteringLayer
+    from spectrogram_cube_clustering_b200.models import target_distribution
+    g = load_golden("dec", "c1")
+    n = g["z"].shape[0]
+    layer = ClusteringLayer(8, 9, 1.0, weights=torch.from_numpy(g["mu"])).double().cuda()
+    z = torch.from_numpy(g["z"]).double().cuda().requires_grad_(True)
+    q = layer(z)
+    assert q.dtype == torch.float64 and np.abs(q.detach().cpu().numpy() - g["q"]).max() < 1e-14
+    loss = float(g["gamma"]) * torch.nn.KLDivLoss(reduction="sum")(torch.log(q), torch.from_numpy(g["p"]).cuda()) / n
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-12 * abs(float(g["loss"]))
+    assert rel_err(z.grad.cpu().numpy(), g["dz"]) < 1e-10 and rel_err(layer.weights.grad.cpu().numpy(), g["dmu"]) < 1e-10
+    p = target_distribution(g["q_round"])
+    assert p.dtype == np.float64
+    d = np.abs(p - g["p"])
+    assert d.max() <= 1.0000001e-5 and (d > 1e-9).mean() < 1e-4
+    # float32 input still takes the float32 throughput kernels
+    q32 = ClusteringLayer(8, 9, 1.0, weights=torch.from_numpy(g["mu"]).float()).cuda()(torch.from_numpy(g["z"]).float().cuda())
+    assert q32.dtype == torch.float32 and rel_err(q32.detach().cpu().numpy(), g["q"]) < 1e-5
