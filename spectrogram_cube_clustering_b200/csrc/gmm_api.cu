@@ -49,18 +49,26 @@ __device__ __forceinline__ void gmm_finalize_body(const FinArgs& a, unsigned cha
             const double* S2 = a.stats + 1 + K + (size_t)K * d;
             const double nk = N[k] + a.nk_add;
             if (lane == 0) nk_s[k] = nk;
+            // loads first (independent, nothing stored to global memory in between: they overlap instead of paying one
+            // L2 round trip per matrix entry), then the arithmetic; the mean shift of the other rows comes by shuffle
+            const double di = (i < d) ? S1[k * d + i] / nk : 0.0;
             if (i < d) {
-                const double di = S1[k * d + i] / nk;
+                const double* __restrict__ s2k = S2 + (size_t)k * TRI;
                 for (int c = 0; c < d; ++c) {
-                    const double dc = S1[k * d + c] / nk;
                     const int lo = i < c ? i : c, hi = i < c ? c : i;
-                    double v = S2[(size_t)k * TRI + tri(hi) + lo] / nk - di * dc;
+                    A[i * LDA + c] = s2k[tri(hi) + lo];
+                }
+            }
+            for (int c = 0; c < d; ++c) {
+                const double dc = __shfl_sync(0xffffffffu, di, c);
+                if (i < d) {
+                    double v = A[i * LDA + c] / nk - di * dc;
                     if (c == i) v += a.reg_covar;
                     A[i * LDA + c] = v;
                     a.covariances[((size_t)k * d + i) * d + c] = v;
                 }
-                a.means[k * d + i] += di;
             }
+            if (i < d) a.means[k * d + i] += di;
         } else {
             if (lane == 0) nk_s[k] = a.weights_in[k];
             if (i < d)
