@@ -24,7 +24,7 @@ static __device__ __noinline__ void target_pull_f(const PeerCtx& pull, int K, do
 }
 
 template <int LPR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)          // <= 32 registers: 8 CTAs per SM keep enough loads in flight to stream at HBM rate
 dec_target_kernel(const float* __restrict__ q, int64_t n, int K, double* __restrict__ f,
                   int round5, float* __restrict__ p, PeerCtx pull) {
     __shared__ float inv_f[SCC_MAX_K];
