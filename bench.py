@@ -414,9 +414,11 @@ def run_gpu(args):
 
     dbg('per-kernel pass')
     # ---------------- per-kernel durations ----------------
-    # One CUDA graph per kernel holding that launch on each of the N_SETS rotating input sets; the
+    # One CUDA graph per kernel holding GRAPH_STEPS launches that rotate over the N_SETS input sets; the
     # replays are timed with CUDA events on the launching stream, so a kernel's figure is its average
     # launch duration in steady state (in-graph launch gaps included), inputs cold in L2 like the step.
+    KERNEL_GRAPH_ROUNDS = GRAPH_STEPS // N_SETS     # as many launches per replay as the step graphs hold
+
     def graph_of(fn):
         cs = torch.cuda.Stream()
         with torch.cuda.stream(cs):
@@ -425,8 +427,9 @@ def run_gpu(args):
             cs.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=cs):
-                for s_ in sets:
-                    fn(s_)
+                for _ in range(KERNEL_GRAPH_ROUNDS):
+                    for s_ in sets:
+                        fn(s_)
         torch.cuda.synchronize()
         return g
 
@@ -448,7 +451,7 @@ def run_gpu(args):
         {"dec_assign": k_assign, "dec_target_kl_grad": k_tgrad})
     for s_ in sets:                      # q / f / p of every set valid for the stand-alone kernels
         k_assign(s_); k_target(s_)
-    kavg = {k: time_graph(graph_of(fn), N_SETS, reps) for k, fn in kfns.items()}
+    kavg = {k: time_graph(graph_of(fn), N_SETS * KERNEL_GRAPH_ROUNDS, max(3, reps // 2)) for k, fn in kfns.items()}
     alg_bytes = {"dec_assign": 4 * D + 4 * K + 4, "dec_target": 8 * K, "dec_kl_grad": 8 * D + 4 * K,
                  "dec_target_kl_grad": 8 * D + 4 * K,
                  "dec_step": (4 * D + 4 * K + 4) + (8 * D + 4 * K)}                    # per point
@@ -464,7 +467,7 @@ def run_gpu(args):
         pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic,
-                "traffic_note": "ncu --set full cold-cache capture (profiles/traffic.json, profiles/r01_ncu_kernels.txt); rows "
+                "traffic_note": "ncu --set full cold-cache capture (profiles/traffic.json, profiles/r02_ncu_kernels.txt); rows "
                                 "written by the kernel are still in the 126 MB L2 when it ends, so DRAM writes are "
                                 "below the algorithmic store bytes",
                 "peak_source": peak_src,
@@ -482,13 +485,13 @@ def run_gpu(args):
     unfused_extra, two_extra = None, None
     if world == 1 and not unfused:       # the three-kernel chain of the earlier sessions, for comparison
         g3 = graph_of(lambda s_: (k_assign(s_), k_target(s_), k_grad(s_)))
-        ms3 = time_graph(g3, N_SETS, reps)
+        ms3 = time_graph(g3, N_SETS * KERNEL_GRAPH_ROUNDS, max(3, reps // 2))
         unfused_extra = {"workload": "dec_assign -> dec_target -> dec_kl_grad(p): the 3-kernel chain (240 B/point)",
                          "ms": ms3, "points_per_s": N_PER_GPU / (ms3 * 1e-3),
                          "hbm_frac": 240 * N_PER_GPU / (ms3 * 1e-3) / 1e9 / hbm_peak}
     if one_kernel:                       # the two-kernel chain every rank runs when N > 1
         g2 = graph_of(lambda s_: (k_assign(s_), k_tgrad(s_)))
-        ms2 = time_graph(g2, N_SETS, reps)
+        ms2 = time_graph(g2, N_SETS * KERNEL_GRAPH_ROUNDS, max(3, reps // 2))
         two_extra = {"workload": "dec_assign -> dec_target_kl_grad: the 2-kernel chain (176 B/point)",
                      "ms": ms2, "points_per_s": N_PER_GPU / (ms2 * 1e-3),
                      "hbm_frac": 176 * N_PER_GPU / (ms2 * 1e-3) / 1e9 / hbm_peak}

@@ -14,6 +14,7 @@
 // Instantiated per dimension by dec_inst.cu (one translation unit per D, built in parallel).
 #pragma once
 
+#include <cstdlib>
 #include "scc_common.cuh"
 #include "scc_launch.h"
 
@@ -408,12 +409,17 @@ __device__ __forceinline__ void grad_coefficients(const DecArgs& a, size_t i, in
             for (int jp = 0; jp < JP; ++jp) p2[jp] = pre2[jp];
         } else {                                   // MODE_KLF / MODE_STEP / MODE_KLU: rebuild p from the column sums
             const float2 inv2 = make_float2(inv, inv);
+            float2 qrow[JP];
 #pragma unroll
             for (int jp = 0; jp < JP; ++jp) {
                 float2 q = __fmul2_rn(t2[jp], inv2);
                 if (a.round5) q = round_dec5_2(q);
+                if (MODE == MODE_STEP) qrow[jp] = q;
                 p2[jp] = __fmul2_rn(__fmul2_rn(q, q), inv_f2[jp]);         // inv_f is 0 for clusters >= K
             }
+            // one-kernel step: q leaves from the FP32-bound second pass (the same value, bit for bit, as the assign
+            // pass computes), which takes 4K bytes per point off the HBM-bound first pass (47.2 -> 45.8 us at 1M points)
+            if (MODE == MODE_STEP && a.q) store_krow2<KP, EXACT>(a.q + i * K, K, qrow);
             // row sum in the order dec_target_kernel uses (groups of 4, then a pairwise tree over the
             // groups; sequential when K is not 4, 8 or 16), so the rebuilt p is bit-identical to its output
             float wsum;
@@ -500,6 +506,36 @@ __device__ __forceinline__ void dz_from_coefficients(const float2 (&zc2)[Pairs<D
     }
 #pragma unroll
     for (int c = 0; c < D; ++c) dzr[c] = (c & 1) ? dz2[c >> 1].y : dz2[c >> 1].x;
+}
+
+// The same for RB rows of one thread sharing every load of the -(mu - c0) table.
+template <int D, int KP, bool EXACT, int RB>
+__device__ __forceinline__ void dz_from_coefficients_rows(const float2 (&zc2)[RB][Pairs<D>::N],
+                                                          const float2 (&coef2)[RB][KP / 2], const float (&csum)[RB],
+                                                          const float2* __restrict__ nmc2_s, int K,
+                                                          float (&dzr)[RB][D]) {
+    constexpr int DP2 = Pairs<D>::N;
+    float2 dz2[RB][DP2];
+#pragma unroll
+    for (int k = 0; k < RB; ++k)
+#pragma unroll
+        for (int c = 0; c < DP2; ++c) dz2[k][c] = __fmul2_rn(splat2(csum[k]), zc2[k][c]);
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+        if (EXACT || j < K) {
+#pragma unroll
+            for (int c = 0; c < DP2; ++c) {
+                const float2 m = nmc2_s[j * DP2 + c];
+#pragma unroll
+                for (int k = 0; k < RB; ++k)
+                    dz2[k][c] = __ffma2_rn(splat2((j & 1) ? coef2[k][j / 2].y : coef2[k][j / 2].x), m, dz2[k][c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RB; ++k)
+#pragma unroll
+        for (int c = 0; c < D; ++c) dzr[k][c] = (c & 1) ? dz2[k][c >> 1].y : dz2[k][c >> 1].x;
 }
 
 // Coalesced copy of a staged [np, D] tile (row stride LD) to global rows.
@@ -669,6 +705,22 @@ __host__ __device__ constexpr int reg_ppt() {
 #endif
 }
 constexpr int kRegStages = 2;
+// rows a thread of the register-blocked kernels holds at once: the broadcast operand loads (centroid table of
+// the distance loop, -(mu - c0) table of dz) are shared by the RB rows.  A warp-wide LDS.128 occupies the
+// shared-memory return path for 4 cycles whatever the broadcast, so with one row at a time those loads alone
+// are ~150 LSU cycles per 32-row slice and pass (d = 9, K = 8).
+// Measured (profiles/r02_variants.txt, 16M points, d = 9, K = 8): two rows at once pay where a second [n, K]
+// operand is streamed from HBM (dec_kl_grad(p): 439 -> 355 us, the rows' p loads overlap) and cost where the row's
+// own chain is the limit (one-kernel step 560 -> 598 us: the operand loads were not the bound, the extra live
+// registers spill) — so the block is 2 rows for MODE_KL / MODE_GENERIC and 1 row otherwise.
+template <int MODE>
+__host__ __device__ constexpr int reg_row_block() {
+#ifdef SCC_REG_RB
+    return SCC_REG_RB;                     // A/B builds
+#else
+    return (MODE == MODE_KL || MODE == MODE_GENERIC) ? 2 : 1;
+#endif
+}
 
 // Copy `rows` staged rows (row stride LD) of this warp to rows * D contiguous floats at dst, all lanes.
 template <int D>
@@ -724,12 +776,27 @@ __device__ __forceinline__ bool batch_view(DecArgs& a, int K) {
 // ---------------------------------------------------------------------------
 template <int D, int KP>
 __host__ __device__ constexpr int grad_reg_accumulators() { return 2 + KP * (D + 1); }
+template <int D, int KP>
+__host__ __device__ constexpr int grad_reg_ctas_per_sm() { return grad_reg_accumulators<D, KP>() <= 100 ? 2 : 1; }
+
+template <int D, int KP>
+__host__ __device__ constexpr size_t grad_reg_smem() {
+    constexpr int S = kRegStages, P = reg_ppt<D>(), NW = kRegThreads / 32;
+    constexpr int NV = 2 + KP + KP * D;
+    constexpr int SCR = reduce_scratch(NV, kRegThreads);
+    return sizeof(float) * (((NW * S * 32 * P * RowLayout<D>::LD + 3) & ~3) + 2 * ((D * (KP / 2) + 1) & ~1) +
+                            2 * ((KP * Pairs<D>::N + 1) & ~1) +
+                            ((KP * D + 3) & ~3) + ((D + 3) & ~3) + ((KP + 3) & ~3) + 2 * ((Pairs<D>::N + 1) & ~1)) +
+           sizeof(double) * (SCR + NV) + sizeof(uint64_t) * S * NW;
+}
 
 template <int D, int KP, bool EXACT, bool ALPHA1, int MODE>
-__global__ void __launch_bounds__(kRegThreads, grad_reg_accumulators<D, KP>() <= 100 ? 2 : 1)
+__global__ void __launch_bounds__(kRegThreads, grad_reg_ctas_per_sm<D, KP>())
 dec_grad_reg_kernel(const DecArgs a_in) {
     constexpr int S = kRegStages;
     constexpr int P = reg_ppt<D>();
+    constexpr int RB = (P % reg_row_block<MODE>() == 0 && grad_reg_accumulators<D, KP>() <= 100)
+                           ? reg_row_block<MODE>() : 1;                     // rows in registers at once
     constexpr int DP2 = Pairs<D>::N;
     constexpr int JP = KP / 2;
     constexpr int DW = D + 1;                                                // accumulator row: B_c (c < D), W
@@ -763,6 +830,9 @@ dec_grad_reg_kernel(const DecArgs a_in) {
     SCC_TL(a.timeline, 0);
 #pragma unroll
     for (int s = 0; s < S; ++s) st.issue(s);
+    __shared__ unsigned int s_seq1;             // sequence number of the f exchange (multi-GPU step): read here, made
+    if (MODE == MODE_STEP && threadIdx.x == 0)  // visible by the barrier below, before any CTA can have advanced it
+        s_seq1 = a.ex_windows ? ld_relaxed_gpu_u32(&reinterpret_cast<PeerHeader*>(a.ex_windows[a.ex_rank])->seq) + 1u : 0u;
     load_grad_constants<D, KP>(a, K, cs, nmuT2, nmc2_s, mc_s, c0_s, inv_f);
     if (threadIdx.x < DP2)
         nc0_s[threadIdx.x] = make_float2(-c0_s[2 * threadIdx.x], (2 * threadIdx.x + 1 < D) ? -c0_s[2 * threadIdx.x + 1] : 0.f);
@@ -786,21 +856,34 @@ dec_grad_reg_kernel(const DecArgs a_in) {
             st.wait(stage, rows);
             const float* sp = st.stage_ptr(stage);
             const int nsl = (rows + 31) >> 5;
-            for (int r = 0; r < nsl; ++r) {
-                const int row_in = 32 * r + lane;
-                if (row_in < rows) {
-                    const size_t i = (size_t)st.row_begin + (cons + row_in);
-                    float zr[1][D];
-                    load_row<D>(sp, row_in, zr[0]);
-                    float2 q2[1][JP];
-                    int label[1];
-                    float* const no_u[1] = {nullptr};
-                    soft_assign_rows<D, KP, EXACT, ALPHA1, 1>(zr, nmuT2, K, inv_alpha, expo, a.round5 != 0, q2, label, no_u);
+            for (int r = 0; r < nsl; r += RB) {
+                if (32 * r + lane < rows) {             // row k of the block: slice r + k (rows ascend: k = 0 is valid)
+                    float zr[RB][D];
+                    bool valid[RB];
 #pragma unroll
-                    for (int jp = 0; jp < JP; ++jp) facc2[jp] = __fadd2_rn(facc2[jp], q2[0][jp]);
-                    if (a.q) store_krow2<KP, EXACT>(a.q + i * K, K, q2[0]);
-                    if (a.labels) a.labels[i] = label[0];
-                    if (a.labels_prev) changed += (a.labels_prev[i] != label[0]) ? 1.f : 0.f;
+                    for (int k = 0; k < RB; ++k) {
+                        valid[k] = 32 * (r + k) + lane < rows;
+#pragma unroll
+                        for (int c = 0; c < D; ++c) zr[k][c] = 0.f;
+                        if (valid[k]) load_row<D>(sp, 32 * (r + k) + lane, zr[k]);
+                    }
+                    float2 q2[RB][JP];
+                    int label[RB];
+                    float* no_u[RB];
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) no_u[k] = nullptr;
+                    soft_assign_rows<D, KP, EXACT, ALPHA1, RB>(zr, nmuT2, K, inv_alpha, expo, a.round5 != 0, q2, label, no_u);
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) {
+                        if (valid[k]) {
+                            const size_t i = (size_t)st.row_begin + (cons + 32 * (r + k) + lane);
+#pragma unroll
+                            for (int jp = 0; jp < JP; ++jp) facc2[jp] = __fadd2_rn(facc2[jp], q2[k][jp]);
+                            // (q itself is written by the second pass, see grad_coefficients())
+                            if (a.labels) a.labels[i] = label[k];
+                            if (a.labels_prev) changed += (a.labels_prev[i] != label[k]) ? 1.f : 0.f;
+                        }
+                    }
                 }
                 if (r == 0 && pending >= 0) {           // refill the stage consumed before this one
                     __syncwarp();
@@ -819,27 +902,29 @@ dec_grad_reg_kernel(const DecArgs a_in) {
 #pragma unroll
         for (int s = 0; s < S; ++s) st.issue(s);
         double* f_s = cta_stats;                                   // [K+1] (cta_stats is free until the tail)
-        const int sp_tail = (K * D + 2 + 1) & ~1;                  // the world's f lives behind the tail's slots
         const PeerCtx ex1{a.ex_windows, a.ex_rank, a.ex_world, a.ex_max_len};
         // f_j and the label-change count are sums of values in [0, 1] over at most n points: fixed point with
-        // 2^shift * n < 2^62, accumulated with integer atomics in the workspace header.  Integer addition is
+        // 2^shift * n < 2^41, accumulated with integer atomics in the workspace header.  Integer addition is
         // associative, so the totals are bit-reproducible whatever the arrival order, and every WARP adds its own
         // sums (float -> warp shuffle tree -> fixed point): no CTA-level reduction in front of the grid barrier.
-        const int shift = 61 - (64 - __clzll((long long)(a.n > 0 ? a.n : 1)));
+        // Every accumulator word also COUNTS its contributions (CountedFix, scc_common.cuh): a CTA knows the sums are
+        // final by polling the K + 1 words themselves — no ticket, no separate read of the sums.
         unsigned long long* fix = reinterpret_cast<unsigned long long*>(a.counter) + kFixOffset;
+        const int shift = CountedFix::kValueBits - 1 - (64 - __clzll((long long)(a.n > 0 ? a.n : 1)));
+        const unsigned int seq1 = s_seq1;      // read in the prologue: no CTA can have advanced it by then
         {
             const double scale_fix = ldexp(1.0, shift);
-            float mine = 0.f;                                      // lane j ends up with the warp's sum of statistic j
+            float mine = 0.f;
 #pragma unroll
             for (int j = 0; j <= KP; ++j) {
                 const float v = warp_sum(j < KP ? ((j & 1) ? facc2[j / 2].y : facc2[j / 2].x) : changed);
-                const int slot = (j < KP) ? j : K;                 // the count sits right behind the K sums
+                const int slot = (j < KP) ? j : K;
                 if (lane == slot && (j == KP || j < K)) mine = v;
             }
-            if (lane <= K) atomicAdd(fix + lane, (unsigned long long)__double2ll_rn((double)mine * scale_fix));
+            if (lane <= K) atomicAdd(fix + lane, CountedFix::word(mine, scale_fix, (double)a.n));
         }
-        grid_barrier_sum_fixed<kRegThreads>(nullptr, K + 1, fix, a.counter + 1, f_s, 0.0, ldexp(1.0, -shift),
-                                            a.partials + (size_t)gridDim.x * sp_tail, &ex1);
+        grid_barrier_counted<kRegThreads>(K + 1, fix, gridDim.x * NW, ldexp(1.0, -shift), f_s,
+                                          reinterpret_cast<double*>(scratch), &ex1, seq1);
         if (threadIdx.x < KP) inv_f[threadIdx.x] = ((int)threadIdx.x < K) ? (float)(1.0 / f_s[threadIdx.x]) : 0.f;
         if (blockIdx.x == 0 && (int)threadIdx.x <= K && a.f_out) a.f_out[threadIdx.x] = f_s[threadIdx.x];
         __syncthreads();
@@ -860,50 +945,90 @@ dec_grad_reg_kernel(const DecArgs a_in) {
             if (first) { SCC_TL(a.timeline, 2); first = false; }
             float* sp = st.stage_ptr(stage);
             const int nsl = (rows + 31) >> 5;
-            for (int r = 0; r < nsl; ++r) {
-                const int row_in = 32 * r + lane;
-                if (row_in < rows) {
-                    const size_t i = (size_t)st.row_begin + (cons + row_in);
-                    // the [n, K] operand row (target p / upstream dL/dq) is requested before the z row is read
-                    float2 pre2[JP];
+            for (int r = 0; r < nsl; r += RB) {
+                if (32 * r + lane < rows) {             // row k of the block: slice r + k (rows ascend: k = 0 is valid)
+                    bool valid[RB];
+                    int row_in[RB];
 #pragma unroll
-                    for (int jp = 0; jp < JP; ++jp) pre2[jp] = make_float2(0.f, 0.f);
-                    if (krows) load_krow2<KP, EXACT>(krows + i * K, K, pre2);
-                    float zr[1][D];
-                    load_row<D>(sp, row_in, zr[0]);
-                    float2 acc2[1][JP], w2[JP], u2[JP], t2[JP], coef2[JP];
-                    sq_distances<D, KP, 1>(zr, nmuT2, acc2);
-                    int label;
-                    float best, tsum;
-                    student_t_pairs<KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(acc2[0], K, inv_alpha, expo, w2, u2, t2, tsum,
-                                                                            label, best);
-                    grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i, K, inv_f2, w2, u2, t2, tsum, expo, label, best, pre2,
-                                                               coef2, sm[0], sm[1]);
-                    // the row is read a second time for the accumulation phase: keeping it in registers across the
-                    // coefficient phase costs D registers the 128-register budget does not have (spills)
+                    for (int k = 0; k < RB; ++k) {
+                        row_in[k] = 32 * (r + k) + lane;
+                        valid[k] = row_in[k] < rows;
+                    }
+                    const size_t i0 = (size_t)st.row_begin + (cons + row_in[0]);
+                    // the [n, K] operand rows (target p / upstream dL/dq) are requested before the z rows are read
+                    float2 pre2[RB][JP];
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) {
+#pragma unroll
+                        for (int jp = 0; jp < JP; ++jp) pre2[k][jp] = make_float2(0.f, 0.f);
+                        if (krows && valid[k]) load_krow2<KP, EXACT>(krows + (i0 + 32 * k) * K, K, pre2[k]);
+                    }
+                    float2 coef2[RB][JP];
+                    {
+                        float zr[RB][D];
+#pragma unroll
+                        for (int k = 0; k < RB; ++k) {
+#pragma unroll
+                            for (int c = 0; c < D; ++c) zr[k][c] = 0.f;
+                            if (valid[k]) load_row<D>(sp, row_in[k], zr[k]);
+                        }
+                        float2 acc2[RB][JP];
+                        sq_distances<D, KP, RB>(zr, nmuT2, acc2);
+#pragma unroll
+                        for (int k = 0; k < RB; ++k) {
+#pragma unroll
+                            for (int jp = 0; jp < JP; ++jp) coef2[k][jp] = make_float2(0.f, 0.f);
+                            if (valid[k]) {
+                                float2 w2[JP], u2[JP], t2[JP];
+                                int label;
+                                float best, tsum;
+                                student_t_pairs<KP, EXACT, ALPHA1, MODE == MODE_KMEANS>(acc2[k], K, inv_alpha, expo, w2, u2, t2,
+                                                                                        tsum, label, best);
+                                grad_coefficients<KP, EXACT, ALPHA1, MODE>(a, i0 + 32 * k, K, inv_f2, w2, u2, t2, tsum, expo,
+                                                                           label, best, pre2[k], coef2[k], sm[0], sm[1]);
+                            }
+                        }
+                    }
+                    // the rows are read a second time for the accumulation phase: keeping them in registers across the
+                    // coefficient phase costs D registers per row the budget does not have (spills)
                     asm volatile("" ::: "memory");
-                    float zb[D];
-                    load_row<D>(sp, row_in, zb);
-                    float2 zc2[DP2];                               // centred point as dimension pairs
+                    float2 zc2[RB][DP2];                           // centred points as dimension pairs
 #pragma unroll
-                    for (int c = 0; c < DP2; ++c)
-                        zc2[c] = __fadd2_rn(make_float2(zb[2 * c], (2 * c + 1 < D) ? zb[2 * c + 1] : 0.f), nc0_s[c]);
+                    for (int k = 0; k < RB; ++k) {
+                        float zb[D];
 #pragma unroll
-                    for (int c = 0; c < D; ++c) {
-                        const float zc = (c & 1) ? zc2[c >> 1].y : zc2[c >> 1].x;
+                        for (int c = 0; c < D; ++c) zb[c] = 0.f;
+                        if (valid[k]) load_row<D>(sp, row_in[k], zb);
 #pragma unroll
-                        for (int jp = 0; jp < JP; ++jp)
-                            B2[jp * DW + c] = __ffma2_rn(coef2[jp], make_float2(zc, zc), B2[jp * DW + c]);
+                        for (int c = 0; c < DP2; ++c)
+                            zc2[k][c] = __fadd2_rn(make_float2(zb[2 * c], (2 * c + 1 < D) ? zb[2 * c + 1] : 0.f), nc0_s[c]);
                     }
 #pragma unroll
-                    for (int jp = 0; jp < JP; ++jp) B2[jp * DW + D] = __fadd2_rn(B2[jp * DW + D], coef2[jp]);
-                    if (want_dz) {
-                        float2 c2 = make_float2(0.f, 0.f);
+                    for (int k = 0; k < RB; ++k) {                 // row after row: the summation order of RB = 1
 #pragma unroll
-                        for (int jp = 0; jp < JP; ++jp) c2 = __fadd2_rn(c2, coef2[jp]);
-                        float dzr[D];
-                        dz_from_coefficients<D, KP, EXACT>(zc2, coef2, cs * (c2.x + c2.y), nmc2_s, K, dzr);
-                        store_row<D>(sp, row_in, dzr);             // in place: the z row is in registers
+                        for (int c = 0; c < D; ++c) {
+                            const float zc = (c & 1) ? zc2[k][c >> 1].y : zc2[k][c >> 1].x;
+#pragma unroll
+                            for (int jp = 0; jp < JP; ++jp)
+                                B2[jp * DW + c] = __ffma2_rn(coef2[k][jp], make_float2(zc, zc), B2[jp * DW + c]);
+                        }
+#pragma unroll
+                        for (int jp = 0; jp < JP; ++jp) B2[jp * DW + D] = __fadd2_rn(B2[jp * DW + D], coef2[k][jp]);
+                    }
+                    if (want_dz) {
+                        float csum[RB];
+#pragma unroll
+                        for (int k = 0; k < RB; ++k) {
+                            float2 c2 = make_float2(0.f, 0.f);
+#pragma unroll
+                            for (int jp = 0; jp < JP; ++jp) c2 = __fadd2_rn(c2, coef2[k][jp]);
+                            csum[k] = cs * (c2.x + c2.y);
+                        }
+                        float dzr[RB][D];
+                        dz_from_coefficients_rows<D, KP, EXACT, RB>(zc2, coef2, csum, nmc2_s, K, dzr);
+#pragma unroll
+                        for (int k = 0; k < RB; ++k)
+                            if (valid[k]) store_row<D>(sp, row_in[k], dzr[k]);     // in place: the z rows are in registers
                     }
                 }
                 if (r == 0 && pending >= 0) {           // refill the stage consumed before this one: its dz store
@@ -965,7 +1090,6 @@ dec_grad_reg_kernel(const DecArgs a_in) {
     const bool last = grid_publish<kRegThreads, 30>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials,
                                                     a.counter, a.stats, scratch, &push, a.ex_push);
     if (MODE == MODE_STEP && last) {                                          // every CTA is past the pass-1 barrier
-        if (threadIdx.x == 0) a.counter[1] = 0u;
         if ((int)threadIdx.x <= K) reinterpret_cast<unsigned long long*>(a.counter)[kFixOffset + threadIdx.x] = 0ull;
     }
     if (kBulkOut && lane == 0) bulk_wait0();             // this warp's dz stores are complete
@@ -1191,16 +1315,6 @@ constexpr size_t assign_smem() {
            sizeof(double) * (KP + 1) + sizeof(uint64_t) * S;
 }
 template <int D, int KP>
-constexpr size_t grad_reg_smem() {
-    constexpr int S = kRegStages, P = reg_ppt<D>(), NW = kRegThreads / 32;
-    constexpr int NV = 2 + KP + KP * D;
-    constexpr int SCR = reduce_scratch(NV, kRegThreads);
-    return sizeof(float) * (((NW * S * 32 * P * RowLayout<D>::LD + 3) & ~3) + 2 * ((D * (KP / 2) + 1) & ~1) +
-                            2 * ((KP * Pairs<D>::N + 1) & ~1) +
-                            ((KP * D + 3) & ~3) + ((D + 3) & ~3) + ((KP + 3) & ~3) + 2 * ((Pairs<D>::N + 1) & ~1)) +
-           sizeof(double) * (SCR + NV) + sizeof(uint64_t) * S * NW;
-}
-template <int D, int KP>
 constexpr size_t grad_tiled_smem() {
     constexpr int S = 2;
     constexpr int BR = (KP % 8 == 0 && D % 8 == 0) ? 8 : 4;
@@ -1228,22 +1342,34 @@ static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t 
     if (grid > kMaxDecGrid) grid = kMaxDecGrid;
     if (grid > num_tiles) grid = num_tiles;
     if (args.batch > 0 && grid > kBatchGridX) grid = kBatchGridX;    // R restarts share the machine (workspace bound)
+    if (cooperative && grid * (threads / 32) > (int64_t)CountedFix::kMaxContributors)
+        grid = CountedFix::kMaxContributors / (threads / 32);      // one counted contribution per warp at the grid barrier
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid, args.batch > 0 ? (unsigned)args.batch : 1u);
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    int nattr = 1;
     if (cooperative) {              // grid-wide barrier inside: every CTA must be resident (grid <= SMs x occupancy)
+        static const int step_launch = [] {          // experiment knob: 0 cooperative, 1 cooperative + PDL, 2 PDL only
+            const char* e = getenv("SCC_STEP_LAUNCH");
+            return e ? atoi(e) : 0;
+        }();
         attr[0].id = cudaLaunchAttributeCooperative;
         attr[0].val.cooperative = 1;
+        if (step_launch >= 1) {
+            attr[step_launch == 1 ? 1 : 0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[step_launch == 1 ? 1 : 0].val.programmaticStreamSerializationAllowed = 1;
+            nattr = step_launch == 1 ? 2 : 1;
+        }
     } else {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL, see scc_common.cuh
         attr[0].val.programmaticStreamSerializationAllowed = 1;
     }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = nattr;
     SCC_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
     return SCC_OK;
 }

@@ -55,7 +55,8 @@ int persistent_grid(const void* kernel, int threads, size_t smem, int max_ctas_p
 size_t workspace_bytes(int d, int K) {
     if (d < 1 || d > SCC_MAX_D || K < 1 || K > SCC_MAX_K) return 0;
     // per CTA: the tail's slot (grid_publish, even stride; MODE_KMEANS appends K counts) and — one-kernel step —
-    // the pass-1 slot behind all tail slots; then the world's f vector behind those (grid_barrier_sum)
+    // room for a pass-1 slot behind all tail slots and a K + 2 vector behind those (the one-kernel step's f barrier
+    // now lives in the header's counted accumulators, see CountedFix; the space is kept for ABI stability)
     const size_t dec = (size_t)kMaxDecGrid * (size_t)(((K * d + 2 + K + 1) & ~1) + ((K + 2) & ~1)) + (size_t)(K + 2);
     const size_t gmm = (size_t)kMaxGmmGrid * (size_t)SCC_GMM_STAT_DOUBLES(K, d);
     return kWorkspaceHeader + sizeof(double) * (dec > gmm ? dec : gmm) + (size_t)(64 << 10);   // + staged GMM params

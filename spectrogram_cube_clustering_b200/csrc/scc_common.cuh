@@ -495,151 +495,55 @@ __device__ __forceinline__ bool grid_publish(const double* cta_stats, int S, dou
     return true;
 }
 
-// Grid-wide barrier + all-reduce of a short per-CTA statistics vector INSIDE a kernel whose CTAs are all
-// co-resident (cooperative launch): every CTA publishes its S doubles and takes a ticket.
-//   * single GPU (ex == nullptr): every CTA waits until the whole grid has arrived and then sums all slots
-//     itself in the same fixed order (thread t: column t % SP, rows t / SP, t / SP + R, ...; row groups combined
-//     in order) — every CTA ends with the bit-identical vector in out_s (shared memory, S doubles);
-//   * multi GPU (ex != nullptr): the CTA that arrives LAST sums the slots, pushes the vector to every rank's
-//     exchange window over NVLink, waits for the world's vectors, sums them in rank order, stores the result
-//     behind the slots and releases a ready flag (an epoch number); the other CTAs wait on that flag only —
-//     the collective runs inside the compute kernel, between its two passes.
-// `counter[0]` (tickets) must be 0 on entry and is reset by the caller once no CTA can still be waiting;
-// `counter[1]` is the ready epoch (monotonic).  scratch: NT doubles.
-template <int NT>
-__device__ __forceinline__ void grid_sum_slots(const double* slots, int S, double* out_s, double* scratch) {
-    const int tid = threadIdx.x;
-    const int SP = (S + 1) & ~1;
-    const int G = gridDim.x;
-    const int R = NT / SP;                        // SP <= NT
-    const int c = tid % SP, r = tid / SP;
-    double acc = 0.0;
-    if (r < R) {
-        for (int b = r; b < G; b += 16 * R) {
-            double v[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int bb = b + u * R;
-                v[u] = (bb < G) ? __ldcg(slots + (size_t)bb * SP + c) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 16; ++u) acc += v[u];
-        }
-        scratch[r * SP + c] = acc;
+// Grid-wide barrier + all-reduce of a short vector of NON-NEGATIVE, bounded statistics INSIDE a kernel whose
+// CTAs are all co-resident (cooperative launch): the column sums f_j <= n and the label-change count of the
+// one-kernel DEC step.  Every warp of the grid adds its S values as 64-bit FIXED-POINT integers to S global
+// accumulators with integer atomics; every 64-bit accumulator word carries, above its fixed-point value, the NUMBER of
+// contributions it has received, so a waiter learns that a sum is final from the sum's own word:
+//   bits  0..41  value: sum of non-negative fixed-point contributions, total < 2^41
+//   bits 42..52  poison: contributions that were negative, NaN or above the bound (at most 2047 contributors)
+//   bits 53..63  count of contributions
+// Every warp of the grid adds ONE word per statistic; every CTA then polls the S words until the count field
+// reads `contributors` — a single L2 round trip per poll, against ticket -> poll -> read for the ticket barrier.
+// Integer addition is associative: the sums are bit-reproducible whatever the arrival order.  A poisoned sum
+// reads as NaN.  Multi-GPU: CTA 0 ships the local sums to every rank's window once it has them and EVERY CTA
+// pulls the rank-ordered world sum from the (local) window itself — no relay through one CTA and a ready flag.
+// The words must be 0 on entry; the caller resets them once no CTA can still be polling.
+struct CountedFix {
+    static constexpr int kValueBits = 42, kPoisonShift = 42, kCountShift = 53;
+    static constexpr unsigned int kMaxContributors = 2047;
+    __device__ static __forceinline__ unsigned long long word(float v, double scale, double bound) {
+        const bool ok = v >= 0.f && (double)v <= bound;            // false for NaN
+        return (1ull << kCountShift) + (ok ? (unsigned long long)__double2ll_rn((double)v * scale) : (1ull << kPoisonShift));
     }
-    __syncthreads();
+};
+template <int NT>
+__device__ __forceinline__ void grid_barrier_counted(int S, const unsigned long long* fix, unsigned int contributors,
+                                                     double inv_scale, double* out_s, double* scratch,
+                                                     const PeerCtx* ex, unsigned int seq) {
+    const int tid = threadIdx.x;
+    const bool multi = ex && ex->windows;
+    double* local = multi ? scratch : out_s;
     if (tid < S) {
-        double t = 0.0;
-        for (int rr = 0; rr < R; ++rr) t += scratch[rr * SP + tid];
-        out_s[tid] = t;
+        unsigned long long v;
+        do {
+            v = ld_relaxed_sys_u64(fix + tid);
+        } while ((unsigned int)(v >> CountedFix::kCountShift) != contributors);
+        const bool poisoned = ((v >> CountedFix::kPoisonShift) & 0x7ffull) != 0ull;
+        const double val = (double)(v & ((1ull << CountedFix::kValueBits) - 1ull)) * inv_scale;
+        local[tid] = poisoned ? __longlong_as_double(0x7ff8000000000000ll) : val;
     }
     __syncthreads();
-}
-
-template <int NT>
-__device__ __forceinline__ void grid_barrier_sum(const double* cta_stats, int S, double* slots, unsigned int* counter,
-                                                 double* out_s, double* scratch, const PeerCtx* ex = nullptr) {
-    __shared__ unsigned int s_ticket;
-    const int tid = threadIdx.x;
-    const int SP = (S + 1) & ~1;
-    const int G = gridDim.x;
-    const bool multi = ex && ex->windows;
-    unsigned int epoch = 0;
-    if (multi && tid == 0)          // read before this CTA's ticket: nobody can advance it until all tickets are in
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(epoch) : "l"(counter + 1) : "memory");
-    double* mine = slots + (size_t)blockIdx.x * SP;
-    for (int s = tid; s < SP; s += NT) __stcg(mine + s, (s < S) ? cta_stats[s] : 0.0);
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int seen;
-        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
-        s_ticket = seen;
-        if (!multi) {
-            ++seen;
-            while (seen < (unsigned int)G)
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-        }
-    }
-    __syncthreads();
-    if (!multi) {
-        grid_sum_slots<NT>(slots, S, out_s, scratch);
-        return;
-    }
-    double* global_vec = slots + (size_t)G * SP;                    // [S] the world's sum, behind the slots
-    if (s_ticket == (unsigned int)G - 1) {                          // last CTA of this GPU: local sum, then the exchange
-        grid_sum_slots<NT>(slots, S, out_s, scratch);
-        const unsigned int seq = peer_push(*ex, out_s, S);
-        peer_pull(*ex, out_s, S, seq);                              // rank-ordered sum of every GPU's vector
-        if (tid < S) __stcg(global_vec + tid, out_s[tid]);
-        __syncthreads();
-        if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + 1), "r"(epoch + 1u) : "memory");
-    } else {
+    if (!multi) return;
+    if (blockIdx.x == 0) {
+        peer_push_slice(*ex, local, 0, S, seq);
         if (tid == 0) {
-            unsigned int now;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(counter + 1) : "memory");
-            } while (now != epoch + 1u);
-        }
-        __syncthreads();
-        if (tid < S) out_s[tid] = __ldcg(global_vec + tid);
-        __syncthreads();
-    }
-}
-
-// Variant for NON-NEGATIVE statistics bounded by a known value (the column sums f_j <= n and the label-change
-// count of the DEC assign pass): every CTA adds its S values as 64-bit FIXED-POINT integers to S global
-// accumulators with integer atomics before taking its ticket — integer addition is associative, so the totals
-// are bit-reproducible whatever the arrival order — and after the barrier every CTA just reads S values
-// instead of summing gridDim.x slots (~1.5 us at 296 CTAs).  `inv_scale` = 2^-shift with 2^shift * bound < 2^62.
-// fix[0..S) must be 0 on entry; the caller resets them once no CTA can still be reading.
-template <int NT>
-__device__ __forceinline__ void grid_barrier_sum_fixed(const double* cta_stats, int S, unsigned long long* fix,
-                                                       unsigned int* counter, double* out_s, double scale,
-                                                       double inv_scale, double* global_vec, const PeerCtx* ex = nullptr) {
-    __shared__ unsigned int s_ticket;
-    const int tid = threadIdx.x;
-    const int G = gridDim.x;
-    const bool multi = ex && ex->windows;
-    unsigned int epoch = 0;
-    if (multi && tid == 0)
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(epoch) : "l"(counter + 1) : "memory");
-    if (cta_stats && tid < S) atomicAdd(fix + tid, (unsigned long long)__double2ll_rn(cta_stats[tid] * scale));
-    __syncthreads();                                // (cta_stats == nullptr: the warps have added their sums already)
-    if (tid == 0) {
-        unsigned int seen;
-        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
-        s_ticket = seen;
-        if (!multi) {
-            ++seen;
-            while (seen < (unsigned int)G)
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            PeerHeader* me = reinterpret_cast<PeerHeader*>(ex->windows[ex->rank]);
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&me->seq), "r"(seq) : "memory");
         }
     }
+    peer_pull_slice(*ex, out_s, 0, S, seq);                       // rank-ordered sum of every GPU's vector
     __syncthreads();
-    if (!multi) {
-        if (tid < S) out_s[tid] = (double)__ldcg(fix + tid) * inv_scale;
-        __syncthreads();
-        return;
-    }
-    if (s_ticket == (unsigned int)G - 1) {                          // last CTA of this GPU: the exchange
-        if (tid < S) out_s[tid] = (double)__ldcg(fix + tid) * inv_scale;
-        __syncthreads();
-        const unsigned int seq = peer_push(*ex, out_s, S);
-        peer_pull(*ex, out_s, S, seq);                              // rank-ordered sum of every GPU's vector
-        if (tid < S) __stcg(global_vec + tid, out_s[tid]);
-        __syncthreads();
-        if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + 1), "r"(epoch + 1u) : "memory");
-    } else {
-        if (tid == 0) {
-            unsigned int now;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(counter + 1) : "memory");
-            } while (now != epoch + 1u);
-        }
-        __syncthreads();
-        if (tid < S) out_s[tid] = __ldcg(global_vec + tid);
-        __syncthreads();
-    }
 }
 
 // Stand-alone fixed-order reduction of per-CTA partial slots, for statistics vectors too long
