@@ -21,15 +21,6 @@
 namespace scc {
 
 constexpr int kDecThreads = 256;
-#ifdef SCC_REG_THREADS
-constexpr int kRegThreads = SCC_REG_THREADS;   // A/B builds (make variant VFLAGS=-DSCC_REG_THREADS=192)
-#else
-// threads per CTA of the register-blocked gradient / step kernel.  192 (2 CTAs = 12 warps per SM, 168 registers per
-// thread): the K*(d+1) per-thread accumulators + the per-cluster chain fit without spilling.  Measured against 256
-// threads at the 128-register cap (16 warps per SM, ~40 local-memory accesses per point): one-kernel step 51.3 vs
-// 57.3 us at 1M points, 561 vs 672 us at 16M (profiles/r02_variants.txt).
-constexpr int kRegThreads = 192;
-#endif
 constexpr int kDecTile = 256;
 constexpr int kBatchGridX = 296;       // grid.x bound of a batched (grid.y = restarts) Lloyd launch
 constexpr int kFixOffset = 8;          // workspace header: u64[8 .. 8+K] = fixed-point f accumulators of the one-kernel step
@@ -776,14 +767,34 @@ __device__ __forceinline__ bool batch_view(DecArgs& a, int K) {
 // ---------------------------------------------------------------------------
 template <int D, int KP>
 __host__ __device__ constexpr int grad_reg_accumulators() { return 2 + KP * (D + 1); }
+// Threads per CTA of the register-blocked gradient / step kernel: ONE CTA per SM.
+//   * K*(d+1) + 2 <= 100 accumulators (d = 9, K = 8: 82): 384 threads = 12 warps at 168 registers — the accumulators
+//     plus the per-cluster chain fit without spilling (at the 128-register cap of 16 warps the kernel carried ~40
+//     local-memory accesses per point: one-kernel step 57.3 vs 51.3 us at 1M points).  One CTA of 12 warps instead
+//     of two of 6 halves the per-CTA slots of the grid reduction and shares one set of constant tables:
+//     step 44.7 -> 43.5 us at 1M, 562 -> 537 us at 16M; dec_target_kl_grad 369 -> 340 us at 16M (r02_variants.txt).
+//   * more accumulators (d = 9, K = 16: 162): 192 threads at up to 255 registers.
 template <int D, int KP>
-__host__ __device__ constexpr int grad_reg_ctas_per_sm() { return grad_reg_accumulators<D, KP>() <= 100 ? 2 : 1; }
-
+__host__ __device__ constexpr int reg_threads() {
+#ifdef SCC_REG_THREADS
+    return SCC_REG_THREADS;                    // A/B builds (make variant VFLAGS="-DSCC_REG_THREADS=192 -DSCC_REG_CTAS=2")
+#else
+    return grad_reg_accumulators<D, KP>() <= 100 ? 384 : 192;
+#endif
+}
+template <int D, int KP>
+__host__ __device__ constexpr int grad_reg_ctas_per_sm() {
+#ifdef SCC_REG_CTAS
+    return SCC_REG_CTAS;
+#else
+    return 1;
+#endif
+}
 template <int D, int KP>
 __host__ __device__ constexpr size_t grad_reg_smem() {
-    constexpr int S = kRegStages, P = reg_ppt<D>(), NW = kRegThreads / 32;
+    constexpr int S = kRegStages, P = reg_ppt<D>(), NT = reg_threads<D, KP>(), NW = NT / 32;
     constexpr int NV = 2 + KP + KP * D;
-    constexpr int SCR = reduce_scratch(NV, kRegThreads);
+    constexpr int SCR = reduce_scratch(NV, NT);
     return sizeof(float) * (((NW * S * 32 * P * RowLayout<D>::LD + 3) & ~3) + 2 * ((D * (KP / 2) + 1) & ~1) +
                             2 * ((KP * Pairs<D>::N + 1) & ~1) +
                             ((KP * D + 3) & ~3) + ((D + 3) & ~3) + ((KP + 3) & ~3) + 2 * ((Pairs<D>::N + 1) & ~1)) +
@@ -791,7 +802,7 @@ __host__ __device__ constexpr size_t grad_reg_smem() {
 }
 
 template <int D, int KP, bool EXACT, bool ALPHA1, int MODE>
-__global__ void __launch_bounds__(kRegThreads, grad_reg_ctas_per_sm<D, KP>())
+__global__ void __launch_bounds__((reg_threads<D, KP>()), (grad_reg_ctas_per_sm<D, KP>()))
 dec_grad_reg_kernel(const DecArgs a_in) {
     constexpr int S = kRegStages;
     constexpr int P = reg_ppt<D>();
@@ -800,7 +811,8 @@ dec_grad_reg_kernel(const DecArgs a_in) {
     constexpr int DP2 = Pairs<D>::N;
     constexpr int JP = KP / 2;
     constexpr int DW = D + 1;                                                // accumulator row: B_c (c < D), W
-    constexpr int NW = kRegThreads / 32;
+    constexpr int NT = reg_threads<D, KP>();
+    constexpr int NW = NT / 32;
     using Stream = WarpStream<D, P, S>;
     using L = RowLayout<D>;
     constexpr int NV = 2 + KP + KP * D;                                      // [loss, sum s, W[KP], B[KP*D]]
@@ -812,8 +824,8 @@ dec_grad_reg_kernel(const DecArgs a_in) {
     float* c0_s = mc_s + ((KP * D + 3) & ~3);                                // [D]
     float* inv_f = c0_s + ((D + 3) & ~3);                                    // [KP] (read as cluster pairs)
     float2* nc0_s = reinterpret_cast<float2*>(inv_f + ((KP + 3) & ~3));      // [DP2] -c0 as dimension pairs
-    double* scratch = reinterpret_cast<double*>(nc0_s + ((DP2 + 1) & ~1));   // [reduce_scratch(NV, kRegThreads)]
-    double* cta_stats = scratch + reduce_scratch(NV, kRegThreads);                        // [NV]  (>= K*D + 2 + K)
+    double* scratch = reinterpret_cast<double*>(nc0_s + ((DP2 + 1) & ~1));   // [reduce_scratch(NV, NT)]
+    double* cta_stats = scratch + reduce_scratch(NV, NT);                        // [NV]  (>= K*D + 2 + K)
     uint64_t* bars = reinterpret_cast<uint64_t*>(cta_stats + NV);            // [NW][S]
     constexpr bool kBulkOut = L::kDense;
 
@@ -923,7 +935,7 @@ dec_grad_reg_kernel(const DecArgs a_in) {
             }
             if (lane <= K) atomicAdd(fix + lane, CountedFix::word(mine, scale_fix, (double)a.n));
         }
-        grid_barrier_counted<kRegThreads>(K + 1, fix, gridDim.x * NW, ldexp(1.0, -shift), f_s,
+        grid_barrier_counted<NT>(K + 1, fix, gridDim.x * NW, ldexp(1.0, -shift), f_s,
                                           reinterpret_cast<double*>(scratch), &ex1, seq1);
         if (threadIdx.x < KP) inv_f[threadIdx.x] = ((int)threadIdx.x < K) ? (float)(1.0 / f_s[threadIdx.x]) : 0.f;
         if (blockIdx.x == 0 && (int)threadIdx.x <= K && a.f_out) a.f_out[threadIdx.x] = f_s[threadIdx.x];
@@ -1071,11 +1083,11 @@ dec_grad_reg_kernel(const DecArgs a_in) {
         for (int c = 0; c < D; ++c)
             acc[2 + KP + j * D + c] = (j & 1) ? B2[(j / 2) * DW + c].y : B2[(j / 2) * DW + c].x;
     __syncthreads();
-    cta_reduce<NV, kRegThreads>(acc, scratch, cta_stats);
+    cta_reduce<NV, NT>(acc, scratch, cta_stats);
     SCC_TL(a.timeline, 4);
     // dmu_jc = -cs (B_jc - W_j (mu_jc - c0_c)), compacted to [loss, sum s, dmu[K*D]]
     // (MODE_KMEANS: [inertia, 0, sum_{i in j} (z_i - mu_j) [K*D], counts[K]])
-    static_assert(KP * D <= kRegThreads, "one thread per statistic in the tail");
+    static_assert(KP * D <= NT, "one thread per statistic in the tail");
     double dmu = 0.0, wj = 0.0;
     const int o = threadIdx.x;
     if (o < K * D) dmu = -(double)cs * (cta_stats[2 + KP + o] - cta_stats[2 + o / D] * (double)mc_s[o]);
@@ -1087,7 +1099,7 @@ dec_grad_reg_kernel(const DecArgs a_in) {
     const PeerCtx push{a.ex_push ? a.ex_windows : nullptr, a.ex_rank, a.ex_world, a.ex_max_len};
     // (the warp's last dz bulk stores read the stream buffers, which nothing in the tail touches: their completion
     //  is only awaited at the very end, behind the reductions)
-    const bool last = grid_publish<kRegThreads, 30>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials,
+    const bool last = grid_publish<NT, 30>(cta_stats, K * D + 2 + (MODE == MODE_KMEANS ? K : 0), a.partials,
                                                     a.counter, a.stats, scratch, &push, a.ex_push);
     if (MODE == MODE_STEP && last) {                                          // every CTA is past the pass-1 barrier
         if ((int)threadIdx.x <= K) reinterpret_cast<unsigned long long*>(a.counter)[kFixOffset + threadIdx.x] = 0ull;
@@ -1353,9 +1365,13 @@ static int launch_dec(Kern kern, const DecArgs& args, size_t smem, cudaStream_t 
     cudaLaunchAttribute attr[2];
     int nattr = 1;
     if (cooperative) {              // grid-wide barrier inside: every CTA must be resident (grid <= SMs x occupancy)
-        static const int step_launch = [] {          // experiment knob: 0 cooperative, 1 cooperative + PDL, 2 PDL only
+        // Cooperative launch (co-residency guaranteed by the driver) + programmatic dependent launch: the next
+        // kernel's CTAs are scheduled while this kernel's reduction tail drains and wait in griddepcontrol.wait
+        // (step 47.3 -> 46.4 us in 20-step graphs).  SCC_STEP_LAUNCH=0 drops the PDL attribute; 2 (experiments
+        // only) drops the cooperative one.
+        static const int step_launch = [] {
             const char* e = getenv("SCC_STEP_LAUNCH");
-            return e ? atoi(e) : 0;
+            return e ? atoi(e) : 1;
         }();
         attr[0].id = cudaLaunchAttributeCooperative;
         attr[0].val.cooperative = 1;
@@ -1399,8 +1415,8 @@ struct DecOps {
             if constexpr (MODE == MODE_KLU)
                 return SCC_ERR_UNSUPPORTED;          // register-blocked shapes run the one-kernel step instead
             else
-                return launch_dec(dec_grad_reg_kernel<D, KP, EXACT, A1, MODE>, a, grad_reg_smem<D, KP>(), st, kRegThreads,
-                                  MODE == MODE_STEP, kRegThreads);
+                return launch_dec(dec_grad_reg_kernel<D, KP, EXACT, A1, MODE>, a, grad_reg_smem<D, KP>(), st,
+                                  reg_threads<D, KP>(), MODE == MODE_STEP, reg_threads<D, KP>());
         }
     }
     template <int MODE>
