@@ -695,7 +695,11 @@ __host__ __device__ constexpr int reg_ppt() {
     return 40 / RowLayout<D>::LD > 4 ? 4 : (40 / RowLayout<D>::LD < 1 ? 1 : 40 / RowLayout<D>::LD);
 #endif
 }
+#ifdef SCC_REG_STAGES
+constexpr int kRegStages = SCC_REG_STAGES;     // A/B builds
+#else
 constexpr int kRegStages = 2;
+#endif
 // rows a thread of the register-blocked kernels holds at once: the broadcast operand loads (centroid table of
 // the distance loop, -(mu - c0) table of dz) are shared by the RB rows.  A warp-wide LDS.128 occupies the
 // shared-memory return path for 4 cycles whatever the broadcast, so with one row at a time those loads alone
@@ -862,31 +866,36 @@ dec_grad_reg_kernel(const DecArgs a_in) {
 #pragma unroll
         for (int jp = 0; jp < JP; ++jp) facc2[jp] = make_float2(0.f, 0.f);
         float changed = 0.f;
+#ifdef SCC_STEP_RB1
+        constexpr int RB1 = (P % SCC_STEP_RB1 == 0) ? SCC_STEP_RB1 : 1;      // A/B builds
+#else
+        constexpr int RB1 = 1;                  // rows of the assign pass in registers at once
+#endif
         int cons = 0, stage = 0, pending = -1;
         while (cons < st.total) {
             const int rows = st.stage_rows(cons);
             st.wait(stage, rows);
             const float* sp = st.stage_ptr(stage);
             const int nsl = (rows + 31) >> 5;
-            for (int r = 0; r < nsl; r += RB) {
+            for (int r = 0; r < nsl; r += RB1) {
                 if (32 * r + lane < rows) {             // row k of the block: slice r + k (rows ascend: k = 0 is valid)
-                    float zr[RB][D];
-                    bool valid[RB];
+                    float zr[RB1][D];
+                    bool valid[RB1];
 #pragma unroll
-                    for (int k = 0; k < RB; ++k) {
+                    for (int k = 0; k < RB1; ++k) {
                         valid[k] = 32 * (r + k) + lane < rows;
 #pragma unroll
                         for (int c = 0; c < D; ++c) zr[k][c] = 0.f;
                         if (valid[k]) load_row<D>(sp, 32 * (r + k) + lane, zr[k]);
                     }
-                    float2 q2[RB][JP];
-                    int label[RB];
-                    float* no_u[RB];
+                    float2 q2[RB1][JP];
+                    int label[RB1];
+                    float* no_u[RB1];
 #pragma unroll
-                    for (int k = 0; k < RB; ++k) no_u[k] = nullptr;
-                    soft_assign_rows<D, KP, EXACT, ALPHA1, RB>(zr, nmuT2, K, inv_alpha, expo, a.round5 != 0, q2, label, no_u);
+                    for (int k = 0; k < RB1; ++k) no_u[k] = nullptr;
+                    soft_assign_rows<D, KP, EXACT, ALPHA1, RB1>(zr, nmuT2, K, inv_alpha, expo, a.round5 != 0, q2, label, no_u);
 #pragma unroll
-                    for (int k = 0; k < RB; ++k) {
+                    for (int k = 0; k < RB1; ++k) {
                         if (valid[k]) {
                             const size_t i = (size_t)st.row_begin + (cons + 32 * (r + k) + lane);
 #pragma unroll
