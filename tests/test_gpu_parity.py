@@ -213,6 +213,27 @@ def test_dec_step_in_cuda_graph_and_unsupported_shape(ops):
         ops.dec_step(z32, mu32)
 
 
+def test_dec_step_nonfinite_point_poisons_f_like_the_reference(ops):
+    """A NaN (or infinite) latent point makes its whole q row NaN in the reference (networks.py:280-288), hence every
+    f_j (models.py:1320), every p and the loss.  The one-kernel step sums f in fixed point: the contribution is flagged
+    in the accumulator word (CountedFix) and the sums read as NaN — the barrier still completes, on every later launch too."""
+    from spectrogram_cube_clustering_b200 import synth
+    z, mu = synth.latent_points(50_000, 9, 8, device="cuda", rank=11)
+    clean = ops.dec_step(z, mu, 1.0, 5, 1e-8)
+    for bad in (float("nan"), float("inf")):
+        zb = z.clone()
+        zb[12_345, 3] = bad
+        out = ops.dec_step(zb, mu, 1.0, 5, 1e-8)
+        torch.cuda.synchronize()
+        assert torch.isnan(out["f"][:8]).all() and torch.isnan(out["stats"][0])
+        assert torch.isnan(out["q"][12_345]).all()
+        good = torch.ones(50_000, dtype=torch.bool, device="cuda"); good[12_345] = False
+        assert torch.equal(out["q"][good], clean["q"][good]) and torch.equal(out["labels"][good], clean["labels"][good])
+    again = ops.dec_step(z, mu, 1.0, 5, 1e-8)          # the accumulators were reset: the next launch is clean
+    torch.cuda.synchronize()
+    assert all(torch.equal(again[k], clean[k]) for k in ("q", "labels", "f", "p", "dz", "stats"))
+
+
 @pytest.mark.parametrize("case", DEC_CASES)
 def test_dec_backward_generic_golden(ops, case):
     g = load_golden("dec", case)
