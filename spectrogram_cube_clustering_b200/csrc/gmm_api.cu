@@ -24,6 +24,7 @@ struct FinArgs {
     double* prec_chol;         // out, may be NULL
     float* params;             // out
     double* ctrl;
+    unsigned long long* tl;    // profiling builds: timeline row of the tail kernel (slots 3..6), or NULL
 };
 
 // All threads of one CTA of at least 32 * K threads.
@@ -43,6 +44,7 @@ __device__ __forceinline__ void gmm_finalize_body(const FinArgs& a, unsigned cha
     if (k < K) {
         double* A = mats + (size_t)k * d * LDA;
         const int i = lane;                         // row owned by this lane
+        double mean_new = 0.0;                      // this lane's coordinate of the updated mean
         if constexpr (FROM_STATS) {
             const double* N = a.stats + 1;
             const double* S1 = a.stats + 1 + K;
@@ -68,13 +70,18 @@ __device__ __forceinline__ void gmm_finalize_body(const FinArgs& a, unsigned cha
                     a.covariances[((size_t)k * d + i) * d + c] = v;
                 }
             }
-            if (i < d) a.means[k * d + i] += di;
+            if (i < d) {
+                mean_new = a.means[k * d + i] + di;
+                a.means[k * d + i] = mean_new;
+            }
         } else {
+            if (i < d) mean_new = a.means[k * d + i];
             if (lane == 0) nk_s[k] = a.weights_in[k];
             if (i < d)
                 for (int c = 0; c < d; ++c) A[i * LDA + c] = a.cov_in[((size_t)k * d + i) * d + c];
         }
         __syncwarp();
+        if (k == 0) SCC_TL(a.tl, 3);
         // Cholesky, lower, in place (left-looking; lane i owns row i)
         bool ok = true;
         for (int j = 0; j < d; ++j) {
@@ -85,11 +92,12 @@ __device__ __forceinline__ void gmm_finalize_body(const FinArgs& a, unsigned cha
             }
             const double piv = __shfl_sync(0xffffffffu, s, j);
             if (!(piv > 0.0)) { ok = false; break; }
-            const double root = sqrt(piv);
-            if (i == j) A[i * LDA + j] = root;
-            else if (i > j && i < d) A[i * LDA + j] = s / root;
+            const double rinv = rsqrt(piv);                  // one dependent special-function chain per column, not two
+            if (i == j) A[i * LDA + j] = piv * rinv;
+            else if (i > j && i < d) A[i * LDA + j] = s * rinv;
             __syncwarp();
         }
+        if (k == 0) SCC_TL(a.tl, 4);
         if (!ok) {
             if (lane == 0) atomicMax(&bad_s, k + 1);
         } else {
@@ -97,29 +105,32 @@ __device__ __forceinline__ void gmm_finalize_body(const FinArgs& a, unsigned cha
             // is parked in the strict UPPER triangle at A[c][r]; Y[c][c] = 1 / L[c][c].  The upper
             // triangle of A with the diagonal inverted is then exactly U = L^-T.
             const int c = lane;
-            if (c < d) {
-                const double ycc = 1.0 / A[c * LDA + c];
-                for (int r = c + 1; r < d; ++r) {
+            const double ycc = (c < d) ? 1.0 / A[c * LDA + c] : 1.0;   // the d reciprocals side by side, then shuffled
+            for (int r = 1; r < d; ++r) {
+                const double yrr = __shfl_sync(0xffffffffu, ycc, r);
+                if (c < r) {
                     double acc = A[r * LDA + c] * ycc;
                     for (int m = c + 1; m < r; ++m) acc += A[r * LDA + m] * A[c * LDA + m];
-                    A[c * LDA + r] = -acc / A[r * LDA + r];
+                    A[c * LDA + r] = -acc * yrr;
                 }
             }
             __syncwarp();
-            double ld = (i < d) ? -log(A[i * LDA + i]) : 0.0;          // log det U = -sum log L_ii
+            if (k == 0) SCC_TL(a.tl, 5);
+            double ld = (i < d) ? log(ycc) : 0.0;                      // log det U = -sum log L_ii
             ld = warp_sum(ld);
             if (lane == 0) logdet_s[k] = ld;
             if (i < d) {
                 for (int b = 0; b < d; ++b) {
-                    const double u = (i < b) ? A[i * LDA + b] : ((i == b) ? 1.0 / A[i * LDA + i] : 0.0);   // U[i][b]
+                    const double u = (i < b) ? A[i * LDA + b] : ((i == b) ? ycc : 0.0);   // U[i][b]
                     if (a.prec_chol) a.prec_chol[((size_t)k * d + i) * d + b] = u;
                     if (i <= b) a.params[(size_t)K * d + (size_t)k * TRI + tri(b) + i] = (float)u;
                 }
-                a.params[k * d + i] = (float)a.means[k * d + i];
+                a.params[k * d + i] = (float)mean_new;
             }
         }
     }
     __syncthreads();
+    SCC_TL(a.tl, 6);
     if ((int)threadIdx.x < K && bad_s == 0) {          // one lane per component: K float64 logarithms side by side
         double tot = 0.0;
         for (int j = 0; j < K; ++j) tot += nk_s[j];   // same order in every lane
@@ -163,12 +174,13 @@ constexpr int kTailGroups = 8;
 
 __global__ void __launch_bounds__(512, 1)
 gmm_tail_kernel(const double* __restrict__ partials, int G, int NS, double* __restrict__ stats, PeerCtx ex,
-                unsigned int* __restrict__ ticket, const FinArgs fin) {
+                unsigned int* __restrict__ ticket, const FinArgs fin, unsigned long long* tl) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double slice[kTailSlice];
     __shared__ double part[kTailGroups][kTailSlice];
     __shared__ int s_last;
     if (fin.ctrl[5] != 0.0) return;              // frozen fit (identical on every rank): nothing to exchange
+    SCC_TL(tl, 0);
     const int lo = blockIdx.x * kTailSlice, hi = min(NS, lo + kTailSlice);
     {   // thread (g, c): statistic lo + c over the slots g, g + 8, ... — the chain is L2-latency bound, so the slots
         // of one statistic are spread over 8 threads (up to 8 independent loads in flight each); fixed order
@@ -225,8 +237,10 @@ gmm_tail_kernel(const double* __restrict__ partials, int G, int NS, double* __re
         if (s_last) *ticket = 0u;
     }
     __syncthreads();
+    SCC_TL(tl, 1);
     if (!s_last) return;
     gmm_finalize_body<true>(fin, smem_raw);
+    SCC_TL(tl, 2);
 }
 
 
@@ -250,7 +264,7 @@ int gmm_em_step(const float* z, int64_t n, int d, int K, const float* params, do
     if (n == 0) { SCC_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * SCC_GMM_STAT_DOUBLES(K, d), st)); return SCC_OK; }
     GmmArgs a{};
     a.z = z; a.n = n; a.K = K; a.params = params; a.labels = labels; a.resp = resp; a.ctrl = ctrl;
-    a.accumulate = mode; a.stats = stats;
+    a.accumulate = mode; a.stats = stats; a.timeline = g_timeline;
     a.counter = reinterpret_cast<unsigned int*>(ws);
     a.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + kWorkspaceHeader);
 #define SCC_CASE(D_) if (d == D_) return gmm_em_dim##D_(a, st);
@@ -277,7 +291,7 @@ int gmm_em_iteration(const float* z, int64_t n, int d, int K, float* params, dou
     a.z = z; a.n = n; a.K = K; a.params = params; a.ctrl = ctrl; a.accumulate = mode; a.stats = stats;
     a.counter = reinterpret_cast<unsigned int*>(ws);
     a.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + kWorkspaceHeader);
-    a.skip_reduce = 1; a.grid_out = &grid;
+    a.skip_reduce = 1; a.grid_out = &grid; a.timeline = g_timeline;
     if (n > 0) {
         int rc = SCC_ERR_UNSUPPORTED;
 #define SCC_CASE(D_) if (d == D_) rc = gmm_em_dim##D_(a, st);
@@ -289,11 +303,13 @@ int gmm_em_iteration(const float* z, int64_t n, int d, int K, float* params, dou
     f.stats = stats; f.n_total = n_total; f.reg_covar = reg_covar; f.nk_add = nk_eps; f.tol = tol;
     f.d = d; f.K = K; f.means = means; f.weights = weights; f.covariances = covariances;
     f.prec_chol = prec_chol; f.params = params; f.ctrl = ctrl;
+    f.tl = g_timeline ? g_timeline + 8 * 1024 : nullptr;
     PeerCtx px{nullptr, 0, 1, 0};
     if (ex && ex->windows) px = PeerCtx{reinterpret_cast<unsigned char* const*>(ex->windows), ex->rank, ex->world, ex->max_len};
     const size_t smem = finalize_smem(d, K);
     SCC_CUDA(cudaFuncSetAttribute(gmm_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gmm_tail_kernel<<<(NS + kTailSlice - 1) / kTailSlice, 512, smem, st>>>(a.partials, grid, NS, stats, px, a.counter + 4, f);
+    gmm_tail_kernel<<<(NS + kTailSlice - 1) / kTailSlice, 512, smem, st>>>(a.partials, grid, NS, stats, px, a.counter + 4, f,
+                                                                               g_timeline ? g_timeline + 8 * 1024 : nullptr);
     SCC_CUDA(cudaGetLastError());
     return SCC_OK;
 }

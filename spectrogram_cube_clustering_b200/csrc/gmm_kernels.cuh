@@ -35,6 +35,7 @@ struct GmmArgs {
     unsigned int* counter;
     int skip_reduce;           // leave the per-CTA partial slots for gmm_tail_kernel (fused EM iteration)
     int* grid_out;             // host: number of partial slots written (grid of the statistics kernel)
+    unsigned long long* timeline;   // profiling builds (-DSCC_TIMELINE), see scc_common.cuh
 };
 
 // after the statistics kernel: stand-alone fixed-order reduction, or hand the slots to the fused tail
@@ -550,6 +551,7 @@ gmm_em_sparse_kernel(const GmmArgs a) {
 
     const int K = a.K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SCC_TL(a.timeline, 0);
     {   // parameters -> component-pair layouts
         float* nmu = reinterpret_cast<float*>(nmu2_s);
         for (int i = threadIdx.x; i < JP * DP * 2; i += NT) {
@@ -569,13 +571,23 @@ gmm_em_sparse_kernel(const GmmArgs a) {
     const float thr = (a.accumulate & SCC_GMM_NOSKIP) ? 0.f : kGmmSkipThreshold;
     const int acc_mode = a.accumulate & 3;
 
-    Ring ring;
-    ring.init(ring_buf, bars, a.z, a.n);
-    __syncthreads();
+    // Blocked partition: CTA b owns a contiguous range of 32-point slices (ranges differ by at most one slice) and
+    // walks it in tiles of TILE points with one partial tile at the end — instead of whole tiles dealt out cyclically,
+    // where ceil(tiles / grid) rounds of a 12 us tile decide the kernel time (1.25M points per GPU: 8.25 -> 9 rounds).
     const int G = gridDim.x;
-#pragma unroll
-    for (int s = 0; s < S; ++s) ring.issue(s, blockIdx.x + s * G);
+    const int64_t slices = (a.n + 31) >> 5;
+    const int64_t per = slices / G, rem = slices - per * G;
+    const int64_t s0 = (int64_t)blockIdx.x * per + ((int64_t)blockIdx.x < rem ? (int64_t)blockIdx.x : rem);
+    const int64_t lo = 32 * s0 < a.n ? 32 * s0 : a.n;
+    const int64_t hi_ = 32 * (s0 + per + ((int64_t)blockIdx.x < rem ? 1 : 0));
+    const int64_t hi = hi_ < a.n ? hi_ : a.n;
+    Ring ring;
+    ring.init(ring_buf, bars, a.z + (size_t)lo * D, hi - lo);      // lo is a multiple of 32 points: 16-byte aligned
     __syncthreads();
+#pragma unroll
+    for (int s = 0; s < S; ++s) ring.issue(s, s);
+    __syncthreads();
+    SCC_TL(a.timeline, 1);
 
     // phase-2 state of this warp's component
     const int kc = warp;
@@ -599,19 +611,25 @@ gmm_em_sparse_kernel(const GmmArgs a) {
     };
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < ring.num_tiles; tile += G, ++it) {
+    for (int tile = 0; tile < ring.num_tiles; ++tile, ++it) {
         const int stage = it % S;
         ring.wait(stage, tile, (uint32_t)(it / S));
         const int np = ring.points(tile);
         const float* ztile = ring.stage_ptr(stage);
+        if (tile == 0) SCC_TL(a.timeline, 2);
         // ---------------- phase 1: E-step for points threadIdx.x + p * NT ----------------
         bool active[PP];
         float2 r2[PP][JP];
-        {
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+            active[p] = (int)threadIdx.x + p * NT < np;
+#pragma unroll
+            for (int kp = 0; kp < JP; ++kp) r2[p][kp] = make_float2(0.f, 0.f);
+        }
+        if (__any_sync(0xffffffffu, active[0])) {       // warps beyond the end of a partial tile skip the E-step
             float x[PP][D];
 #pragma unroll
             for (int p = 0; p < PP; ++p) {
-                active[p] = (int)threadIdx.x + p * NT < np;
 #pragma unroll
                 for (int c = 0; c < D; ++c) x[p][c] = 0.f;
                 if (active[p]) load_row<D>(ztile, threadIdx.x + p * NT, x[p]);
@@ -687,7 +705,7 @@ gmm_em_sparse_kernel(const GmmArgs a) {
                         r2[p][kp] = make_float2(label == 2 * kp ? 1.f : 0.f, label == 2 * kp + 1 ? 1.f : 0.f);
                 }
                 if (active[p]) {
-                    const size_t i = (size_t)tile * TILE + threadIdx.x + p * NT;
+                    const size_t i = (size_t)lo + (size_t)tile * TILE + threadIdx.x + p * NT;
                     if (a.labels) a.labels[i] = label;
                     if (a.resp) {
 #pragma unroll
@@ -756,14 +774,16 @@ gmm_em_sparse_kernel(const GmmArgs a) {
             }
         }
         __syncthreads();
-        ring.issue(stage, tile + S * G);
+        ring.issue(stage, tile + S);
     }
+    SCC_TL(a.timeline, 3);
     if (acc_mode) flush();
     {
         const float w = warp_sum(loglik);
         if (lane == 0) ll_s[warp] = (double)w;
     }
     __syncthreads();
+    SCC_TL(a.timeline, 4);
     // pack CTA statistics with the true K: [ll, N_k[K], S1[K*D], S2[K*TRI]]
     const int NS = 1 + K * NM;
     for (int s = threadIdx.x; s < NS; s += NT) {
@@ -784,6 +804,7 @@ gmm_em_sparse_kernel(const GmmArgs a) {
     }
     __syncthreads();
     for (int s = threadIdx.x; s < NS; s += NT) a.partials[(size_t)blockIdx.x * NS + s] = cta_stats[s];
+    SCC_TL(a.timeline, 5);
 }
 
 template <int D, int KP>
@@ -815,7 +836,7 @@ static int launch_gmm_small(const GmmArgs& a, cudaStream_t st) {
         auto kern = gmm_em_sparse_kernel<D, KP>;
         constexpr size_t smem = gmm_sparse_smem<D, KP>();
         constexpr int tile_points = NT * gmm_ppt<KP>();
-        const int64_t tiles = (a.n + tile_points - 1) / tile_points;
+        const int64_t tiles = (a.n + tile_points - 1) / tile_points;       // (no CTA with less than one tile of work)
         int64_t grid = persistent_grid(reinterpret_cast<const void*>(kern), NT, smem, 2);
         if (grid < 0) return (int)grid;
         if (grid > kMaxGmmGrid) grid = kMaxGmmGrid;

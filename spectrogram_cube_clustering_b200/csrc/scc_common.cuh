@@ -198,6 +198,7 @@ struct ZRing {
     }
     __device__ __forceinline__ int points(int tile) const { return tile == num_tiles - 1 ? last_points : TILE; }
     __device__ __forceinline__ float* stage_ptr(int stage) const { return buf + stage * kTileFloats; }
+    static __device__ __forceinline__ bool tma_ok(int np) { return L::kDense && np > 0 && ((np * D) & 3) == 0; }
 
     // padded float4 layouts are filled with cp.async (one commit group per issue() call per thread)
     static constexpr bool kCpAsync = L::kVec4 && !L::kDense;
@@ -208,10 +209,10 @@ struct ZRing {
             float* dst = stage_ptr(stage);
             const float* src = z + (size_t)tile * (TILE * D);
             const int np = points(tile);
-            if (L::kDense && np == TILE) {
+            if (tma_ok(np)) {                     // also a partial tile, when it is a whole number of 16-byte units
                 if (threadIdx.x == 0) {
-                    mbar_expect_tx(&bar[stage], kTileBytes);
-                    bulk_g2s(dst, src, kTileBytes, &bar[stage]);
+                    mbar_expect_tx(&bar[stage], (uint32_t)np * D * sizeof(float));
+                    bulk_g2s(dst, src, (uint32_t)np * D * sizeof(float), &bar[stage]);
                 }
             } else if constexpr (L::kVec4) {
                 const int nvec = np * (D / 4);
@@ -238,7 +239,7 @@ struct ZRing {
             cp_async_wait<STAGES - 1>();                  // this thread's copies of the oldest stage landed
             __syncthreads();                              // ... and everybody else's
         } else {
-            if (L::kDense && points(tile) == TILE) mbar_wait(&bar[stage], use_index & 1u);
+            if (tma_ok(points(tile))) mbar_wait(&bar[stage], use_index & 1u);
         }
     }
 };
