@@ -179,6 +179,7 @@ gmm_tail_kernel(const double* __restrict__ partials, int G, int NS, double* __re
     __shared__ double slice[kTailSlice];
     __shared__ double part[kTailGroups][kTailSlice];
     __shared__ int s_last;
+    pdl_wait();                                  // launched under the statistics kernel's drain: no global access before
     if (fin.ctrl[5] != 0.0) return;              // frozen fit (identical on every rank): nothing to exchange
     SCC_TL(tl, 0);
     const int lo = blockIdx.x * kTailSlice, hi = min(NS, lo + kTailSlice);
@@ -308,9 +309,20 @@ int gmm_em_iteration(const float* z, int64_t n, int d, int K, float* params, dou
     if (ex && ex->windows) px = PeerCtx{reinterpret_cast<unsigned char* const*>(ex->windows), ex->rank, ex->world, ex->max_len};
     const size_t smem = finalize_smem(d, K);
     SCC_CUDA(cudaFuncSetAttribute(gmm_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gmm_tail_kernel<<<(NS + kTailSlice - 1) / kTailSlice, 512, smem, st>>>(a.partials, grid, NS, stats, px, a.counter + 4, f,
-                                                                               g_timeline ? g_timeline + 8 * 1024 : nullptr);
-    SCC_CUDA(cudaGetLastError());
+    // programmatic dependent launch: the tail's CTAs are scheduled as the statistics kernel's CTAs retire and wait in
+    // griddepcontrol.wait for the whole grid (the launch gap, ~2.5 us per iteration, disappears under the drain)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((NS + kTailSlice - 1) / kTailSlice));
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    unsigned long long* tl = g_timeline ? g_timeline + 8 * 1024 : nullptr;
+    SCC_CUDA(cudaLaunchKernelEx(&cfg, gmm_tail_kernel, (const double*)a.partials, grid, NS, stats, px, a.counter + 4, f, tl));
     return SCC_OK;
 }
 

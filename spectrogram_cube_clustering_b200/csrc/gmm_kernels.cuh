@@ -776,6 +776,7 @@ gmm_em_sparse_kernel(const GmmArgs a) {
         __syncthreads();
         ring.issue(stage, tile + S);
     }
+    pdl_trigger();                      // the fused tail kernel may be scheduled under this kernel's drain
     SCC_TL(a.timeline, 3);
     if (acc_mode) flush();
     {
