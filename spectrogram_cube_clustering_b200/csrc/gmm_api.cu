@@ -27,8 +27,51 @@ struct FinArgs {
     unsigned long long* tl;    // profiling builds: timeline row of the tail kernel (slots 3..6), or NULL
 };
 
+// One component, one warp, the matrix in REGISTERS (d <= 12): lane i holds row i of the covariance / of L in
+// a[0..D), lane c ends with column c of Y = L^-1 in y[c+1..D) and 1 / L[c][c] in ycc.  Right-looking Cholesky —
+// after column j the trailing rows are updated with shuffled L[c][j] — and forward substitution with shuffled
+// L[r][m]: the same products in the same order as the shared-memory version (bit-identical L and Y), without
+// its dependent shared-memory round trips.  Returns false when a pivot is not positive (warp-uniform).
+template <int D>
+__device__ __forceinline__ bool chol_inverse_regs(double (&a)[D], double (&y)[D], double& ycc, int lane) {
+    constexpr unsigned int kFull = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const double piv = __shfl_sync(kFull, a[j], j);
+        if (!(piv > 0.0)) return false;
+        const double rinv = rsqrt(piv);
+        const double l = (lane == j) ? piv * rinv : a[j] * rinv;       // L[lane][j] (lanes < j: never read)
+        a[j] = l;
+#pragma unroll
+        for (int c = j + 1; c < D; ++c) {
+            const double lc = __shfl_sync(kFull, l, c);                // L[c][j]
+            a[c] = fma(-l, lc, a[c]);
+        }
+    }
+    double diag = 1.0;
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+        if (m == lane) diag = a[m];
+        y[m] = 0.0;
+    }
+    ycc = 1.0 / diag;
+#pragma unroll
+    for (int r = 1; r < D; ++r) {
+        const double yrr = __shfl_sync(kFull, ycc, r);
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < r; ++m) {
+            const double lrm = __shfl_sync(kFull, a[m], r);            // L[r][m]
+            if (m == lane) acc = lrm * ycc;
+            else if (m > lane) acc = fma(lrm, y[m], acc);
+        }
+        if (lane < r) y[r] = -acc * yrr;
+    }
+    return true;
+}
+
 // All threads of one CTA of at least 32 * K threads.
-template <bool FROM_STATS>
+template <bool FROM_STATS, int DR>          // DR: compile-time d of the register path, 0 = any d through shared memory
 __device__ __forceinline__ void gmm_finalize_body(const FinArgs& a, unsigned char* smem_raw) {
     const int d = a.d, K = a.K, LDA = d + 1, TRI = tri(d);
     double* mats = reinterpret_cast<double*>(smem_raw);       // [K][d*LDA]  L below, Y^T above
@@ -41,7 +84,66 @@ __device__ __forceinline__ void gmm_finalize_body(const FinArgs& a, unsigned cha
     if (threadIdx.x == 0) bad_s = 0;
     __syncthreads();
 
-    if (k < K) {
+    if constexpr (DR > 0) {
+        if (k < K) {
+            constexpr int D = DR;
+            const int i = lane;
+            double row[D], y[D], ycc, mean_new = 0.0;
+            if constexpr (FROM_STATS) {
+                const double* N = a.stats + 1;
+                const double* S1 = a.stats + 1 + K;
+                const double* s2k = a.stats + 1 + K + (size_t)K * D + (size_t)k * TRI;
+                // every load first (independent: one L2 round trip), one reciprocal instead of d + 1 divisions
+                const double nk = N[k] + a.nk_add;
+                const double s1 = (i < D) ? S1[k * D + i] : 0.0;
+                const double mean_old = (i < D) ? a.means[k * D + i] : 0.0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    const int lo = i < c ? i : c, hi = i < c ? c : i;
+                    row[c] = (i < D) ? s2k[tri(hi) + lo] : 0.0;
+                }
+                if (lane == 0) nk_s[k] = nk;
+                const double rnk = 1.0 / nk;
+                const double di = s1 * rnk;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    const double dc = __shfl_sync(0xffffffffu, di, c);
+                    double v = row[c] * rnk - di * dc;
+                    if (c == i) v += a.reg_covar;
+                    row[c] = v;
+                    if (i < D) a.covariances[((size_t)k * D + i) * D + c] = v;
+                }
+                if (i < D) {
+                    mean_new = mean_old + di;
+                    a.means[k * D + i] = mean_new;
+                }
+            } else {
+                if (lane == 0) nk_s[k] = a.weights_in[k];
+#pragma unroll
+                for (int c = 0; c < D; ++c) row[c] = (i < D) ? a.cov_in[((size_t)k * D + i) * D + c] : 0.0;
+                if (i < D) mean_new = a.means[k * D + i];
+            }
+            if (k == 0) SCC_TL(a.tl, 3);
+            const bool ok = chol_inverse_regs<D>(row, y, ycc, lane);
+            if (k == 0) SCC_TL(a.tl, 5);
+            if (!ok) {
+                if (lane == 0) atomicMax(&bad_s, k + 1);
+            } else {
+                double ld = (i < D) ? log(ycc) : 0.0;                  // log det U = -sum log L_ii
+                ld = warp_sum(ld);
+                if (lane == 0) logdet_s[k] = ld;
+                if (i < D) {
+#pragma unroll
+                    for (int b = 0; b < D; ++b) {
+                        const double u = (i < b) ? y[b] : ((i == b) ? ycc : 0.0);       // U[i][b] = Y[b][i]
+                        if (a.prec_chol) a.prec_chol[((size_t)k * D + i) * D + b] = u;
+                        if (i <= b) a.params[(size_t)K * D + (size_t)k * TRI + tri(b) + i] = (float)u;
+                    }
+                    a.params[k * D + i] = (float)mean_new;
+                }
+            }
+        }
+    } else if (k < K) {
         double* A = mats + (size_t)k * d * LDA;
         const int i = lane;                         // row owned by this lane
         double mean_new = 0.0;                      // this lane's coordinate of the updated mean
@@ -154,11 +256,24 @@ __device__ __forceinline__ void gmm_finalize_body(const FinArgs& a, unsigned cha
     }
 }
 
+// d <= 12 of the built dimensions take the register path
+template <bool FROM_STATS>
+__device__ __forceinline__ void gmm_finalize_dispatch(const FinArgs& a, unsigned char* smem_raw) {
+    switch (a.d) {
+        case 4: gmm_finalize_body<FROM_STATS, 4>(a, smem_raw); break;
+        case 8: gmm_finalize_body<FROM_STATS, 8>(a, smem_raw); break;
+        case 9: gmm_finalize_body<FROM_STATS, 9>(a, smem_raw); break;
+        case 10: gmm_finalize_body<FROM_STATS, 10>(a, smem_raw); break;
+        case 12: gmm_finalize_body<FROM_STATS, 12>(a, smem_raw); break;
+        default: gmm_finalize_body<FROM_STATS, 0>(a, smem_raw); break;
+    }
+}
+
 template <bool FROM_STATS>
 __global__ void __launch_bounds__(512, 1)
 gmm_finalize_kernel(const FinArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    gmm_finalize_body<FROM_STATS>(a, smem_raw);
+    gmm_finalize_dispatch<FROM_STATS>(a, smem_raw);
 }
 
 // ---------------------------------------------------------------------------
@@ -240,7 +355,7 @@ gmm_tail_kernel(const double* __restrict__ partials, int G, int NS, double* __re
     __syncthreads();
     SCC_TL(tl, 1);
     if (!s_last) return;
-    gmm_finalize_body<true>(fin, smem_raw);
+    gmm_finalize_dispatch<true>(fin, smem_raw);
     SCC_TL(tl, 2);
 }
 
