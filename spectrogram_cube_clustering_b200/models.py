@@ -305,6 +305,11 @@ class GaussianMixture:
 
     # -- state helpers
     def _alloc(self, dev, K, d):
+        key = (str(dev), K, d)
+        if getattr(self, "_alloc_key", None) == key:     # same shapes as the previous fit: keep the state tensors, and
+            self._ctrl.zero_()                           # with them the captured EM-iteration graph that points at them
+            return
+        self._alloc_key, self._graph, self._graph_key = key, None, None
         f64 = dict(dtype=torch.float64, device=dev)
         self._means = torch.empty(K, d, **f64)
         self._weights = torch.empty(K, **f64)
@@ -366,8 +371,14 @@ class GaussianMixture:
     def _capture(self, buf: LatentBuffer):
         """One EM iteration as a CUDA graph (every buffer it touches is persistent): a fit is then
         ``poll_interval`` graph replays per host poll — at C3 on 8 GPUs an iteration is ~0.2 ms of GPU work, the
-        same order as four eager launches through Python."""
-        self._graph = None
+        same order as four eager launches through Python.  The graph bakes in every argument of the two launches, so
+        it is reused by a later fit only for the same buffer object (shard pointer, sizes, workspaces, exchange
+        window) and the same tol / reg_covar; anything else recaptures."""
+        key = (id(buf), buf.z.data_ptr(), buf.n_local, buf.n_total, float(self.tol), float(self.reg_covar))
+        if getattr(self, "_graph", None) is not None and getattr(self, "_graph_key", None) == key \
+                and self.use_graph and self._graph_buf is buf:
+            return
+        self._graph, self._graph_key, self._graph_buf = None, None, None
         if not (self.use_graph and buf.z.is_cuda):
             return
         try:
@@ -384,7 +395,7 @@ class GaussianMixture:
             torch.cuda.synchronize(buf.z.device)
             for t, v in zip((self._means, self._weights, self._cov, self._pchol, self._params, self._ctrl), saved):
                 t.copy_(v)                           # the warm-up iteration must not count
-            self._graph = g
+            self._graph, self._graph_key, self._graph_buf = g, key, buf
         except Exception as exc:  # pragma: no cover - depends on the box
             warnings.warn(f"CUDA graph capture of the EM iteration failed ({exc}); launching eagerly")
             self._graph = None
@@ -419,8 +430,7 @@ class GaussianMixture:
         self.means_ = self._means.cpu().numpy()
         self.covariances_ = self._cov.cpu().numpy()
         self.precisions_cholesky_ = self._pchol.cpu().numpy()
-        self._buf = buf
-        self._graph = None                               # the graph pins buffers of this fit only
+        self._buf = buf                                  # (the captured graph is kept for a later fit of the same buffer)
         return self
 
     def predict_device(self, buf: LatentBuffer | None = None) -> torch.Tensor:

@@ -95,6 +95,34 @@ def test_gaussian_mixture_front_end_matches_sklearn_fit(case):
     assert labels.dtype == np.int64 and (labels != g["fit_labels"]).mean() < 2e-3
 
 
+def test_gaussian_mixture_reuses_its_graph_on_the_same_buffer():
+    """A second fit of the same LatentBuffer replays the EM-iteration graph captured by the first (same state
+    tensors, same kernel arguments) and gives the same result; another buffer or tolerance recaptures."""
+    import warnings
+    from spectrogram_cube_clustering_b200 import synth
+    from spectrogram_cube_clustering_b200.latent_buffer import LatentBuffer
+    from spectrogram_cube_clustering_b200.models import GaussianMixture
+    d, K = 9, 4
+    z, _ = synth.latent_points(20_000, d, K, rank=3, device="cuda")
+    w0, mu0, cov0 = [t.numpy() for t in synth.gmm_initial_state(d, K, "cpu")]
+    buf = LatentBuffer(z)
+    gm = GaussianMixture(K, max_iter=12, tol=0.0, weights_init=w0, means_init=mu0, covariances_init=cov0, poll_interval=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gm.fit(buf)
+        g1, first = gm._graph, (gm.means_.copy(), gm.covariances_.copy(), gm.lower_bound_, gm.n_iter_)
+        gm.fit(buf)
+        assert g1 is not None and gm._graph is g1
+        assert np.array_equal(gm.means_, first[0]) and np.array_equal(gm.covariances_, first[1])
+        assert gm.lower_bound_ == first[2] and gm.n_iter_ == first[3] == 12
+        gm.fit(LatentBuffer(z.clone()))
+        assert gm._graph is not g1 and np.array_equal(gm.means_, first[0])
+        g2 = gm._graph
+        gm.tol = 1e-3
+        gm.fit(gm._buf)
+        assert gm._graph is not g2
+
+
 def test_gaussian_mixture_errors():
     from spectrogram_cube_clustering_b200.models import GaussianMixture, ConvergenceWarning
     with pytest.raises(ValueError):                       # n_samples < n_components (sklearn _base.py:232-237)
