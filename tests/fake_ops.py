@@ -94,3 +94,92 @@ def gmm_em_step(z, K, params, stats=None, labels=None, resp=None, ctrl=None, mod
         stats.copy_(res)
         return stats
     return res
+
+
+# ---- GMM state: pack / finalize / whole iteration (the device control block of gmm_api.cu, restated) ----
+def gmm_param_floats(K, d):
+    return K * d + K * (d * (d + 1) // 2) + K
+
+
+def gmm_stat_doubles(K, d):
+    return 1 + K + K * d + K * (d * (d + 1) // 2)
+
+
+def gmm_supported(d, K):
+    return True
+
+
+def _pack(weights, means, pchol, params):
+    K, d = means.shape
+    tri = d * (d + 1) // 2
+    U = pchol.numpy()
+    flat = [means.numpy().ravel()]
+    flat.append(np.concatenate([[U[k][a, b] for b in range(d) for a in range(b + 1)] for k in range(K)]))
+    flat.append(ogmm.log_det_cholesky(U) + np.log(weights.numpy()) - 0.5 * d * np.log(2 * np.pi))
+    params.copy_(torch.from_numpy(np.concatenate(flat).astype(np.float32)))
+    assert params.numel() == K * d + K * tri + K
+
+
+def _chol_or_bad(cov):
+    """U = L^-T per component, or the 1-based index of the first component that is not positive definite."""
+    K = cov.shape[0]
+    out = np.zeros_like(cov)
+    for k in range(K):
+        try:
+            L = np.linalg.cholesky(cov[k])
+        except np.linalg.LinAlgError:
+            return None, k + 1
+        out[k] = np.linalg.inv(L).T
+    return out, 0
+
+
+def gmm_pack_params(weights, means, covariances, params=None, prec_chol=None, ctrl=None):
+    K, d = means.shape
+    params = params if params is not None else torch.empty(gmm_param_floats(K, d), dtype=torch.float32)
+    prec_chol = prec_chol if prec_chol is not None else torch.empty(K, d, d, dtype=torch.float64)
+    ctrl = ctrl if ctrl is not None else torch.zeros(8, dtype=torch.float64)
+    U, bad = _chol_or_bad(covariances.numpy())
+    ctrl.copy_(torch.tensor([-np.inf, -np.inf, 0.0, 0.0, float(bad), 1.0 if bad else 0.0, 0.0, 0.0], dtype=torch.float64))
+    if not bad:
+        prec_chol.copy_(torch.from_numpy(U))
+        _pack(weights, means, prec_chol, params)
+    return params, prec_chol, ctrl
+
+
+def gmm_finalize(stats, n_total, means, weights, covariances, prec_chol, params, ctrl,
+                 reg_covar=1e-6, nk_eps=10 * 2.220446049250313e-16, tol=1e-3):
+    """sklearn _m_step from moments centred on the CURRENT means + stop rule, in place (gmm_api.cu)."""
+    if ctrl[5] != 0:
+        return
+    K, d = means.shape
+    tri_idx = [(a, b) for b in range(d) for a in range(b + 1)]
+    s = stats.numpy()
+    nk = s[1:1 + K] + nk_eps
+    di = s[1 + K:1 + K + K * d].reshape(K, d) / nk[:, None]
+    s2 = s[1 + K + K * d:].reshape(K, len(tri_idx))
+    cov = np.zeros((K, d, d))
+    for k in range(K):
+        for e, (a, b) in enumerate(tri_idx):
+            cov[k, a, b] = cov[k, b, a] = s2[k, e] / nk[k] - di[k, a] * di[k, b]
+        cov[k] += reg_covar * np.eye(d)
+    means.add_(torch.from_numpy(di))
+    covariances.copy_(torch.from_numpy(cov))
+    U, bad = _chol_or_bad(cov)
+    lower, prev = s[0] / n_total, float(ctrl[0])
+    ctrl[1] = prev; ctrl[0] = lower; ctrl[2] += 1.0
+    if bad:
+        ctrl[4] = float(bad); ctrl[5] = 1.0
+        return
+    weights.copy_(torch.from_numpy(nk / nk.sum()))
+    prec_chol.copy_(torch.from_numpy(U))
+    _pack(weights, means, prec_chol, params)
+    if abs(lower - prev) < tol:
+        ctrl[3] = 1.0; ctrl[5] = 1.0
+
+
+def gmm_em_iteration(z, K, params, stats, n_total, means, weights, covariances, prec_chol, ctrl, mode=GMM_SOFT,
+                     reg_covar=1e-6, nk_eps=10 * 2.220446049250313e-16, tol=1e-3, exchange=None):
+    if ctrl[5] != 0:                    # frozen fit: both launches are no-ops
+        return
+    gmm_em_step(z, K, params, stats=stats, mode=mode)
+    gmm_finalize(stats, n_total, means, weights, covariances, prec_chol, params, ctrl, reg_covar, nk_eps, tol)
