@@ -183,3 +183,64 @@ def gmm_em_iteration(z, K, params, stats, n_total, means, weights, covariances, 
         return
     gmm_em_step(z, K, params, stats=stats, mode=mode)
     gmm_finalize(stats, n_total, means, weights, covariances, prec_chol, params, ctrl, reg_covar, nk_eps, tol)
+
+
+# ---- Lloyd scans (MODE_KMEANS of the gradient kernel + the batched update kernel, restated) ----
+def _lloyd_stats(X, C):
+    K, d = C.shape
+    d2 = ((X[:, None, :] - C[None]) ** 2).sum(-1) if len(X) else np.zeros((0, K))
+    lab = d2.argmin(1) if len(X) else np.zeros(0, dtype=np.int64)
+    best = d2.min(1) if len(X) else np.zeros(0)
+    shift = np.zeros((K, d)); cnt = np.zeros(K)
+    for j in range(K):
+        m = lab == j
+        cnt[j] = m.sum()
+        if cnt[j]:
+            shift[j] = (X[m] - C[j]).sum(0)
+    return np.concatenate([[best.sum(), 0.0], shift.ravel(), cnt]), lab, best
+
+
+def kmeans_step(z, centers, labels=None, mindist=None, out_stats=None):
+    st, lab, best = _lloyd_stats(z.numpy().astype(np.float64), centers.numpy().astype(np.float64))
+    if labels is not None:
+        labels.copy_(torch.from_numpy(lab.astype(np.int32)))
+    if mindist is not None:
+        mindist.copy_(torch.from_numpy(best.astype(np.float32)))
+    res = torch.from_numpy(st)
+    if out_stats is not None:
+        out_stats.copy_(res)
+        return out_stats
+    return res
+
+
+def kmeans_batch_step(z, centers, done=None, labels=None, mindist=None, out_stats=None):
+    R, K, d = centers.shape
+    stats = out_stats if out_stats is not None else torch.zeros(R, K * d + 2 + K, dtype=torch.float64)
+    X = z.numpy().astype(np.float64)
+    for r in range(R):
+        if done is not None and done[r]:
+            continue                                    # finished restarts are skipped (their stats stay)
+        st, lab, best = _lloyd_stats(X, centers[r].numpy().astype(np.float64))
+        stats[r] = torch.from_numpy(st)
+        if labels is not None:
+            labels[r] = torch.from_numpy(lab.astype(np.int32))
+        if mindist is not None:
+            mindist[r] = torch.from_numpy(best.astype(np.float32))
+    return stats
+
+
+def kmeans_batch_update(centers, stats, shift_tol, done, n_iter=None, inertia=None):
+    R, K, d = centers.shape
+    for r in range(R):
+        if done[r]:
+            continue
+        st = stats[r].numpy()
+        cnt = st[2 + K * d:]
+        step = np.where(cnt[:, None] > 0, st[2:2 + K * d].reshape(K, d) / np.maximum(cnt[:, None], 1.0), 0.0)
+        centers[r] = (centers[r].double() + torch.from_numpy(step)).float()
+        if inertia is not None:
+            inertia[r] = st[0]
+        if n_iter is not None:
+            n_iter[r] += 1
+        if (step ** 2).sum() <= shift_tol:
+            done[r] = 1
